@@ -1,0 +1,89 @@
+#!/usr/bin/env python
+"""Generate the golden vectors in tests/golden/ from the UNMODIFIED reference.
+
+Run in the build container (needs /root/reference and `python oracle/build_ref.py`):
+
+    python tests/golden/make_golden.py
+
+Every array is produced by the reference's own compiled Cython classes
+(LB_D2Q9/dimensionless/cython_dim.pyx, LB_D2Q9/OLD/cython.pyx) from a seeded
+legacy NumPy RNG; nothing in here comes from this repository's oracle or CUDA
+code.  Arrays are stored in the reference's own host layout ((9,nx,ny) C-order
+for f, (nx,ny) for rho/u/v).
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import build_ref, refload  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def snapshot(sim, tag, d):
+    d[f"f_{tag}"] = np.array(sim.f, copy=True)
+    d[f"rho_{tag}"] = np.array(sim.rho, copy=True)
+    d[f"u_{tag}"] = np.array(sim.u, copy=True)
+    d[f"v_{tag}"] = np.array(sim.v, copy=True)
+
+
+def record(sim, steps, extra=None):
+    d = dict(nx=sim.nx, ny=sim.ny, omega=float(sim.omega), inlet_rho=float(sim.inlet_rho),
+             outlet_rho=float(sim.outlet_rho), steps=np.array(steps))
+    if extra:
+        d.update(extra)
+    snapshot(sim, 0, d)
+    done = 0
+    for s in steps:
+        sim.run(s - done)
+        done = s
+        snapshot(sim, s, d)
+    return d
+
+
+def main():
+    build_ref.build()
+    cd = refload.cython_dim()
+    old = refload.old_cython()
+
+    # 1. cython_dim.Pipe_Flow, 65x33, omega ~ 1.0003 (SURVEY 8d "better-conditioned C1", scaled down)
+    kw = dict(diameter=1., rho=1., viscosity=0.0757, pressure_grad=-1., pipe_length=64 / 32., N=32,
+              time_prefactor=6.)
+    np.random.seed(0)
+    with refload.quiet() as out:
+        sim = cd.Pipe_Flow(**kw)
+    d = record(sim, [1, 10, 100], dict(printout=out.getvalue(), ctor_kwargs=repr(kw), seed=0))
+    np.savez_compressed(os.path.join(OUT, "cython_pipe_65x33.npz"), **d)
+
+    # 2. cython_dim.Pipe_Flow_Cylinder, 121x41 (the authors' cylinder set-up at N=4)
+    kw = dict(cylinder_center=[0.75, 0.5], cylinder_radius=0.1, diameter=1., rho=1., viscosity=1.,
+              pressure_grad=-10., pipe_length=3., N=4)
+    np.random.seed(1)
+    with refload.quiet() as out:
+        sim = cd.Pipe_Flow_Cylinder(**kw)
+    d = record(sim, [1, 10, 100],
+               dict(printout=out.getvalue(), ctor_kwargs=repr(kw), seed=1,
+                    mask=np.array(sim.obstacle_mask, dtype=np.uint8)))
+    np.savez_compressed(os.path.join(OUT, "cython_cylinder_121x41.npz"), **d)
+
+    # 3. OLD/cython.Pipe_Flow_Obstacles, 49x25, two rectangular obstacles (no init noise in OLD)
+    lx, ly = 48, 24
+    mask = np.zeros((lx + 1, ly + 1), dtype=bool)
+    mask[10:14, 8:15] = True
+    mask[30:33, 3:9] = True
+    kw = dict(lx=lx, ly=ly, omega=1.2, deltaP=-0.02)
+    np.random.seed(2)
+    sim = old.Pipe_Flow_Obstacles(obstacle_mask=mask, **kw)
+    d = record(sim, [1, 10, 100], dict(ctor_kwargs=repr(kw), seed=2, mask=mask.astype(np.uint8)))
+    np.savez_compressed(os.path.join(OUT, "old_obstacles_49x25.npz"), **d)
+
+    for n in sorted(os.listdir(OUT)):
+        if n.endswith(".npz"):
+            print(n, os.path.getsize(os.path.join(OUT, n)) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    main()
