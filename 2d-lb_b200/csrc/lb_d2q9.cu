@@ -1,0 +1,923 @@
+// C-ABI implementation of include/lb_d2q9.h: handle management, the fused-step launcher
+// (CUDA-graph batched), single-stage kernels, device-side initialisers and the NVLink
+// peer-memory halo plumbing.  Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false
+// (see __graft_entry__.build()).
+#include "../../include/lb_d2q9.h"
+#include "lb_fused.cuh"
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace lb;
+
+// =====================================================================================
+// handle
+// =====================================================================================
+struct HaloLayout {
+    size_t ghost_bytes;     // one ghost column: 3*(ny+2) elements, rounded to 256 B
+    size_t off_ghost_w[2], off_ghost_e[2];
+    size_t off_flag_w, off_flag_e, off_done_w, off_done_e, off_error;
+    size_t total;
+};
+
+static HaloLayout halo_layout(int ny, int elem)
+{
+    HaloLayout h;
+    h.ghost_bytes = (((size_t)3 * (ny + 2) * elem) + 255) / 256 * 256;
+    size_t o = 0;
+    for (int p = 0; p < 2; ++p) { h.off_ghost_w[p] = o; o += h.ghost_bytes; }
+    for (int p = 0; p < 2; ++p) { h.off_ghost_e[p] = o; o += h.ghost_bytes; }
+    h.off_flag_w = o; o += 128;
+    h.off_flag_e = o; o += 128;
+    h.off_done_w = o; o += 128;
+    h.off_done_e = o; o += 128;
+    h.off_error = o; o += 128;
+    h.total = o;
+    return h;
+}
+
+struct lb_sim {
+    lb_config cfg;
+    int elem = 4;                 // bytes per population value
+    int pitch = 0;                // row pitch in elements (multiple of 512 B)
+    long long plane = 0;          // elements per plane
+    size_t buf_bytes = 0;         // bytes of one guarded 9-plane buffer
+    char *buf_base[2] = {nullptr, nullptr};
+    void *buf[2] = {nullptr, nullptr};   // plane 0 / row 0 of each ping-pong buffer
+    int cur = 0;                  // buffer holding the current post-collision state
+    void *rho = nullptr, *u = nullptr, *v = nullptr, *feq = nullptr;
+    uint8_t *mask = nullptr, *span_solid = nullptr;
+    int mask_pitch = 0, nspans = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int variant = -1;
+    int64_t launches = 0;
+    uint32_t state_index = 0;     // number of fused steps taken (halo parity / flag value)
+    // CUDA graphs of `graph_len` moment-free steps starting from buffer `cur` == index
+    cudaGraphExec_t graph[2] = {nullptr, nullptr};
+    int graph_len[2] = {0, 0};
+    int graph_variant[2] = {-2, -2};
+    // halo
+    char *halo = nullptr;         // my arena
+    HaloLayout hl{};
+    char *peer[2] = {nullptr, nullptr};   // neighbour arenas (mapped)
+    bool peer_ipc[2] = {false, false};
+    double *mass_scratch = nullptr;
+    std::string err;
+};
+
+static thread_local std::string g_create_error;
+
+static int fail(lb_sim *s, int code, const std::string &msg)
+{
+    if (s) s->err = msg; else g_create_error = msg;
+    return code;
+}
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            return fail(sim, LB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));    \
+    } while (0)
+
+// =====================================================================================
+// fused kernel variants
+// =====================================================================================
+struct Variant {
+    const char *name;
+    int dtype, math, V, WX, WY, R;
+    void (*launch)(const StepParams &, cudaStream_t);
+    bool is_default;
+};
+
+template <typename T, int V, int MATH, int WX, int WY, int R, int MINB, int LDP, int STP>
+static void launch_variant(const StepParams &p_in, cudaStream_t st)
+{
+    StepParams p = p_in;
+    constexpr int SPAN = 32 * V;
+    p.tiles_x = (p.pitch + SPAN * WX - 1) / (SPAN * WX);
+    p.tiles_y = (p.ny + WY * R - 1) / (WY * R);
+    const unsigned grid = (unsigned)p.tiles_x * (unsigned)p.tiles_y;
+    fused_step_kernel<T, V, MATH, WX, WY, R, MINB, LDP, STP><<<grid, 32 * WX * WY, 0, st>>>(p);
+}
+
+#define VAR(T, TN, DT, V, M, MN, WX, WY, R, MINB, LDP, STP, DEF)                                    \
+    {TN "." MN ".v" #V ".wx" #WX ".wy" #WY ".r" #R ".b" #MINB ".ld" #LDP ".st" #STP, DT, M, V, WX,  \
+     WY, R, &launch_variant<T, V, M, WX, WY, R, MINB, LDP, STP>, DEF}
+
+#define VARS_FOR(T, TN, DT, VMAX, VHALF)                                                            \
+    VAR(T, TN, DT, VMAX, MATH_FAST, "fast", 2, 2, 1, 6, 1, 0, true),                                \
+    VAR(T, TN, DT, VMAX, MATH_FAST, "fast", 2, 2, 1, 4, 1, 0, false),                               \
+    VAR(T, TN, DT, VMAX, MATH_FAST, "fast", 2, 2, 1, 8, 1, 0, false),                               \
+    VAR(T, TN, DT, VMAX, MATH_FAST, "fast", 2, 2, 2, 4, 1, 0, false),                               \
+    VAR(T, TN, DT, VMAX, MATH_FAST, "fast", 2, 2, 2, 3, 1, 0, false),                               \
+    VAR(T, TN, DT, VMAX, MATH_FAST, "fast", 2, 2, 2, 2, 1, 0, false),                               \
+    VAR(T, TN, DT, VMAX, MATH_FAST, "fast", 2, 2, 4, 2, 1, 0, false),                               \
+    VAR(T, TN, DT, VMAX, MATH_FAST, "fast", 4, 1, 1, 4, 1, 0, false),                               \
+    VAR(T, TN, DT, VMAX, MATH_FAST, "fast", 4, 1, 2, 4, 1, 0, false),                               \
+    VAR(T, TN, DT, VMAX, MATH_FAST, "fast", 1, 4, 2, 4, 1, 0, false),                               \
+    VAR(T, TN, DT, VMAX, MATH_FAST, "fast", 2, 4, 1, 2, 1, 0, false),                               \
+    VAR(T, TN, DT, VMAX, MATH_FAST, "fast", 2, 4, 1, 3, 1, 0, false),                               \
+    VAR(T, TN, DT, VMAX, MATH_FAST, "fast", 2, 4, 1, 4, 1, 0, false),                               \
+    VAR(T, TN, DT, VMAX, MATH_FAST, "fast", 4, 2, 1, 4, 1, 0, false),                               \
+    VAR(T, TN, DT, VMAX, MATH_FAST, "fast", 2, 2, 1, 6, 0, 0, false),                               \
+    VAR(T, TN, DT, VMAX, MATH_FAST, "fast", 2, 2, 1, 6, 2, 1, false),                               \
+    VAR(T, TN, DT, VMAX, MATH_FAST, "fast", 2, 2, 1, 6, 1, 1, false),                               \
+    VAR(T, TN, DT, VHALF, MATH_FAST, "fast", 2, 2, 1, 8, 1, 0, false),                              \
+    VAR(T, TN, DT, VHALF, MATH_FAST, "fast", 2, 2, 2, 8, 1, 0, false),                              \
+    VAR(T, TN, DT, VHALF, MATH_FAST, "fast", 2, 2, 2, 6, 1, 0, false),                              \
+    VAR(T, TN, DT, VHALF, MATH_FAST, "fast", 4, 2, 1, 4, 1, 0, false),                              \
+    VAR(T, TN, DT, VHALF, MATH_FAST, "fast", 2, 2, 4, 6, 1, 0, false),                              \
+    VAR(T, TN, DT, VMAX, MATH_STRICT, "strict", 2, 2, 1, 4, 1, 0, true),                            \
+    VAR(T, TN, DT, VMAX, MATH_STRICT, "strict", 2, 2, 1, 6, 1, 0, false),                           \
+    VAR(T, TN, DT, VMAX, MATH_STRICT, "strict", 2, 2, 2, 3, 1, 0, false),                           \
+    VAR(T, TN, DT, VHALF, MATH_STRICT, "strict", 2, 2, 1, 8, 1, 0, false),                          \
+    VAR(T, TN, DT, VHALF, MATH_STRICT, "strict", 2, 2, 2, 6, 1, 0, false)
+
+static const Variant g_variants[] = {
+    VARS_FOR(float, "f32", LB_F32, 4, 2),
+    VARS_FOR(double, "f64", LB_F64, 2, 1),
+};
+static const int g_nvariants = (int)(sizeof(g_variants) / sizeof(g_variants[0]));
+
+static int default_variant(int dtype, int math)
+{
+    for (int i = 0; i < g_nvariants; ++i)
+        if (g_variants[i].dtype == dtype && g_variants[i].math == math && g_variants[i].is_default) return i;
+    return -1;
+}
+
+// =====================================================================================
+// auxiliary kernels (not on the hot path)
+// =====================================================================================
+template <typename T>
+__global__ void k_feq_from_moments(int nx, int ny, int pitch, long long plane, const T *rho, const T *u,
+                                   const T *v, T *feq, Consts<T> c)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= nx || y >= ny) return;
+    const long long i = (long long)y * pitch + x;
+    T e[9];
+    feq_strict<T>(c, rho[i], u[i], v[i], e);
+#pragma unroll
+    for (int j = 0; j < 9; ++j) feq[j * plane + i] = e[j];
+}
+
+// D2Q9.cl `move` (+ `copy_buffer`): pull form into the other buffer; destinations whose source
+// lies outside the domain keep whatever that buffer held (the reference's stale f_streamed slot).
+template <typename T>
+__global__ void k_stage_move(int nx, int ny, int pitch, long long plane, int periodic, const T *src, T *dst)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= nx || y >= ny) return;
+    const int ex[9] = {0, 1, 0, -1, 0, 1, -1, -1, 1}, ey[9] = {0, 0, 1, 0, -1, 1, 1, -1, -1};
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+        int sx = x - ex[j], sy = y - ey[j];
+        if (periodic) {
+            if (sx < 0) sx += nx;
+            if (sx >= nx) sx -= nx;
+            if (sy < 0) sy += ny;
+            if (sy >= ny) sy -= ny;
+        } else if (sx < 0 || sx >= nx || sy < 0 || sy >= ny) continue;
+        dst[j * plane + (long long)y * pitch + x] = src[j * plane + (long long)sy * pitch + sx];
+    }
+}
+
+template <typename T>
+__global__ void k_stage_bcs(int nx, int ny, int pitch, long long plane, int gnx, int x_off, int do_pipe,
+                            const uint8_t *mask, int mask_pitch, T *f, Consts<T> c)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= nx || y >= ny) return;
+    const long long i = (long long)y * pitch + x;
+    const bool solid = mask && mask[(long long)y * mask_pitch + x] == 1;
+    const int gx = x_off + x;
+    const bool bnd = do_pipe && (gx == 0 || gx == gnx - 1 || y == 0 || y == ny - 1);
+    if (!solid && !bnd) return;
+    T g[9];
+#pragma unroll
+    for (int j = 0; j < 9; ++j) g[j] = f[j * plane + i];
+    if (bnd) pipe_bc<T>(c, gx, y, gnx, ny, g);
+    if (solid) bounce_back<T>(g);
+#pragma unroll
+    for (int j = 0; j < 9; ++j) f[j * plane + i] = g[j];
+}
+
+template <typename T>
+__global__ void k_stage_hydro(int nx, int ny, int pitch, long long plane, const T *f, T *rho, T *u, T *v)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= nx || y >= ny) return;
+    const long long i = (long long)y * pitch + x;
+    T g[9];
+#pragma unroll
+    for (int j = 0; j < 9; ++j) g[j] = f[j * plane + i];
+    T r, a, b;
+    moments<T, MATH_STRICT>(g, r, a, b);
+    rho[i] = r; u[i] = a; v[i] = b;
+}
+
+template <typename T>
+__global__ void k_stage_collide(int nx, int ny, int pitch, long long plane, T *f, const T *feq, Consts<T> c)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= nx || y >= ny) return;
+    const long long i = (long long)y * pitch + x;
+#pragma unroll
+    for (int j = 0; j < 9; ++j) f[j * plane + i] = f[j * plane + i] * c.keep + c.omega * feq[j * plane + i];
+}
+
+template <typename T>
+__global__ void k_zero_velocity(int nx, int ny, int pitch, const uint8_t *mask, int mask_pitch, T *u, T *v)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= nx || y >= ny) return;
+    if (mask[(long long)y * mask_pitch + x] == 1) {
+        u[(long long)y * pitch + x] = (T)0;
+        v[(long long)y * pitch + x] = (T)0;
+    }
+}
+
+// one flag byte per 32 cells of a row: does the group contain a solid node
+__global__ void k_span_solid(int nx, int ny, const uint8_t *mask, int mask_pitch, uint8_t *span_solid, int nspans)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (s >= nspans || y >= ny) return;
+    uint8_t any = 0;
+    for (int e = 0; e < 32; ++e) {
+        const int x = s * 32 + e;
+        if (x < nx && mask[(long long)y * mask_pitch + x] == 1) any = 1;
+    }
+    span_solid[(long long)y * nspans + s] = any;
+}
+
+__global__ void k_mask_disk(int nx, int ny, int x_off, double cx, double cy, double r2, uint8_t *mask, int mask_pitch)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= nx || y >= ny) return;
+    const double dx = (double)(x_off + x) - cx, dy = (double)y - cy;
+    mask[(long long)y * mask_pitch + x] = (dx * dx + dy * dy < r2) ? 1 : 0;
+}
+
+// counter-based N(0,1): splitmix64 of (seed, global cell, population) -> Box-Muller
+__device__ __forceinline__ unsigned long long mix64(unsigned long long z)
+{
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__device__ __forceinline__ double normal01(unsigned long long seed, unsigned long long cell, int j)
+{
+    const unsigned long long h = mix64(mix64(seed ^ (cell * 9ull + (unsigned long long)j)));
+    const double u1 = ((double)(h >> 40) + 0.5) * (1.0 / 16777216.0);            // (0,1)
+    const double u2 = ((double)((h >> 16) & 0xFFFFFFull) + 0.5) * (1.0 / 16777216.0);
+    return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+}
+
+template <typename T>
+__global__ void k_init_synth(int nx, int ny, int pitch, long long plane, int gnx, int x_off, int kind, double u0,
+                             double amplitude, unsigned long long seed, double inlet_rho, double outlet_rho,
+                             const uint8_t *mask, int mask_pitch, T *f0, T *f1, T *rho, T *u, T *v, Consts<T> c)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= nx || y >= ny) return;
+    const long long i = (long long)y * pitch + x;
+    const int gx = x_off + x;
+    T r, a, b;
+    if (kind == LB_SYNTH_PIPE_RAMP) {
+        r = (T)(inlet_rho - (double)gx * (inlet_rho - outlet_rho) / (double)gnx);
+        a = (T)0; b = (T)0;
+    } else {
+        const double yy = (double)y / (double)ny;
+        r = (T)1;
+        a = (T)(yy < 0.5 ? u0 * tanh(80.0 * (yy - 0.25)) : u0 * tanh(80.0 * (0.75 - yy)));
+        b = (T)(0.05 * u0 * sinpi(2.0 * ((double)gx / (double)gnx + 0.25)));
+    }
+    if (mask && mask[(long long)y * mask_pitch + x] == 1) { a = (T)0; b = (T)0; }
+    rho[i] = r; u[i] = a; v[i] = b;
+    T e[9];
+    feq_strict<T>(c, r, a, b, e);
+    const unsigned long long cell = (unsigned long long)y * (unsigned long long)gnx + (unsigned long long)gx;
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+        T val = e[j];
+        if (amplitude != 0.0) val = (T)((double)val * (1.0 + amplitude * normal01(seed, cell, j)));
+        f0[j * plane + i] = val;
+        f1[j * plane + i] = val;
+    }
+}
+
+template <typename T>
+__global__ void k_mass(int nx, int ny, int pitch, long long plane, const T *f, double *out)
+{
+    __shared__ double sh[256];
+    double acc = 0.0;
+    const int y = blockIdx.x;
+    for (int x = threadIdx.x; x < nx; x += blockDim.x) {
+        const long long i = (long long)y * pitch + x;
+#pragma unroll
+        for (int j = 0; j < 9; ++j) acc += (double)f[j * plane + i];
+    }
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[y] = sh[0];
+}
+
+// copies the current boundary columns into the neighbours' ghost columns and publishes the flag
+template <typename T>
+__global__ void k_halo_prime(int nx, int ny, int pitch, long long plane, const T *f, T *out_w, T *out_e,
+                             unsigned int *flag_w_remote, unsigned int *flag_e_remote, unsigned int value)
+{
+    for (int y = threadIdx.x; y < ny; y += blockDim.x) {
+        const long long row = (long long)y * pitch;
+        if (out_w) {
+            out_w[0 * (ny + 2) + y + 1] = f[3 * plane + row];
+            out_w[1 * (ny + 2) + y + 1] = f[6 * plane + row];
+            out_w[2 * (ny + 2) + y + 1] = f[7 * plane + row];
+        }
+        if (out_e) {
+            out_e[0 * (ny + 2) + y + 1] = f[1 * plane + row + nx - 1];
+            out_e[1 * (ny + 2) + y + 1] = f[5 * plane + row + nx - 1];
+            out_e[2 * (ny + 2) + y + 1] = f[8 * plane + row + nx - 1];
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (flag_w_remote) st_release_sys(flag_w_remote, value);
+        if (flag_e_remote) st_release_sys(flag_e_remote, value);
+    }
+}
+
+// =====================================================================================
+// helpers
+// =====================================================================================
+static inline dim3 grid2d(const lb_sim *s, int bx = 128) { return dim3((s->cfg.nx + bx - 1) / bx, s->cfg.ny); }
+
+template <typename T>
+static Consts<T> consts_of(const lb_sim *s)
+{
+    return make_consts<T>(s->cfg.omega, s->cfg.inlet_rho, s->cfg.outlet_rho, s->cfg.cs2, s->cfg.cs22, s->cfg.two_cs4);
+}
+
+static void drop_graphs(lb_sim *s)
+{
+    for (int i = 0; i < 2; ++i) {
+        if (s->graph[i]) cudaGraphExecDestroy(s->graph[i]);
+        s->graph[i] = nullptr; s->graph_len[i] = 0; s->graph_variant[i] = -2;
+    }
+}
+
+static bool uses_halo(const lb_sim *s) { return s->cfg.west_edge == LB_EDGE_HALO || s->cfg.east_edge == LB_EDGE_HALO; }
+
+static void fill_params(lb_sim *s, StepParams &p, int src_idx, int write_moments, uint32_t state_index)
+{
+    memset(&p, 0, sizeof(p));
+    p.src = s->buf[src_idx];
+    p.dst = s->buf[src_idx ^ 1];
+    p.plane = s->plane;
+    p.nx = s->cfg.nx; p.ny = s->cfg.ny; p.pitch = s->pitch;
+    p.gnx = s->cfg.global_nx; p.x_off = s->cfg.x_offset;
+    p.bc = s->cfg.bc; p.west = s->cfg.west_edge; p.east = s->cfg.east_edge;
+    p.write_moments = write_moments;
+    p.zero_obstacle_velocity = s->cfg.zero_obstacle_velocity;
+    p.mask = s->mask; p.span_solid = s->span_solid; p.mask_pitch = s->mask_pitch; p.nspans = s->nspans;
+    p.rho = s->rho; p.u = s->u; p.v = s->v;
+    p.omega = s->cfg.omega; p.inlet_rho = s->cfg.inlet_rho; p.outlet_rho = s->cfg.outlet_rho;
+    p.cs2 = s->cfg.cs2; p.cs22 = s->cfg.cs22; p.two_cs4 = s->cfg.two_cs4;
+    if (uses_halo(s)) {
+        const int rp = state_index & 1, wp = (state_index + 1) & 1;
+        const HaloLayout &h = s->hl;
+        p.ghost_w = s->halo + h.off_ghost_w[rp];
+        p.ghost_e = s->halo + h.off_ghost_e[rp];
+        p.flag_w_local = (unsigned int *)(s->halo + h.off_flag_w);
+        p.flag_e_local = (unsigned int *)(s->halo + h.off_flag_e);
+        p.done_w = (unsigned int *)(s->halo + h.off_done_w);
+        p.done_e = (unsigned int *)(s->halo + h.off_done_e);
+        p.error_word = (unsigned int *)(s->halo + h.off_error);
+        if (s->peer[LB_WEST]) {   // my westward populations land in the west neighbour's EAST ghost
+            p.out_w = s->peer[LB_WEST] + h.off_ghost_e[wp];
+            p.flag_w_remote = (unsigned int *)(s->peer[LB_WEST] + h.off_flag_e);
+        }
+        if (s->peer[LB_EAST]) {
+            p.out_e = s->peer[LB_EAST] + h.off_ghost_w[wp];
+            p.flag_e_remote = (unsigned int *)(s->peer[LB_EAST] + h.off_flag_w);
+        }
+        p.step_id = state_index + 1;
+        p.edge_first = 1;
+    }
+}
+
+static int launch_step(lb_sim *sim, int src_idx, int write_moments, uint32_t state_index)
+{
+    StepParams p;
+    fill_params(sim, p, src_idx, write_moments, state_index);
+    g_variants[sim->variant].launch(p, sim->stream);
+    CU(cudaGetLastError());
+    sim->launches++;
+    return LB_OK;
+}
+
+// =====================================================================================
+// C ABI
+// =====================================================================================
+extern "C" {
+
+int lb_abi_version(void) { return LB_ABI_VERSION; }
+
+int lb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+const char *lb_last_error(const lb_sim *sim) { return sim ? sim->err.c_str() : g_create_error.c_str(); }
+
+int lb_variant_count(void) { return g_nvariants; }
+const char *lb_variant_name(int v) { return (v >= 0 && v < g_nvariants) ? g_variants[v].name : nullptr; }
+
+int lb_create(const lb_config *cfg, lb_sim **out)
+{
+    lb_sim *sim = nullptr;
+    if (!cfg || !out) return fail(nullptr, LB_ERR_INVALID, "lb_create: null argument");
+    *out = nullptr;
+    if (cfg->struct_size != (int32_t)sizeof(lb_config))
+        return fail(nullptr, LB_ERR_INVALID, "lb_create: lb_config size mismatch (ABI)");
+    if (cfg->nx < 2 || cfg->ny < 2) return fail(nullptr, LB_ERR_INVALID, "lb_create: nx, ny must be >= 2");
+    if (cfg->dtype != LB_F32 && cfg->dtype != LB_F64) return fail(nullptr, LB_ERR_INVALID, "lb_create: bad dtype");
+    if (cfg->bc != LB_BC_PIPE && cfg->bc != LB_BC_PERIODIC) return fail(nullptr, LB_ERR_INVALID, "lb_create: bad bc");
+    if (cfg->math != LB_MATH_STRICT && cfg->math != LB_MATH_FAST) return fail(nullptr, LB_ERR_INVALID, "lb_create: bad math");
+    for (int e : {cfg->west_edge, cfg->east_edge}) {
+        if (e < LB_EDGE_BOUNDARY || e > LB_EDGE_HALO) return fail(nullptr, LB_ERR_INVALID, "lb_create: bad edge kind");
+        if (cfg->bc == LB_BC_PERIODIC && e == LB_EDGE_BOUNDARY)
+            return fail(nullptr, LB_ERR_INVALID, "lb_create: a periodic box needs WRAP or HALO edges");
+        if (cfg->bc == LB_BC_PIPE && e == LB_EDGE_WRAP)
+            return fail(nullptr, LB_ERR_INVALID, "lb_create: pipe flow cannot wrap in x");
+    }
+    if (cfg->global_nx < cfg->nx || cfg->x_offset < 0 || cfg->x_offset + cfg->nx > cfg->global_nx)
+        return fail(nullptr, LB_ERR_INVALID, "lb_create: slab does not fit the global lattice");
+    if (!(cfg->omega > 0.0 && cfg->omega < 2.0)) return fail(nullptr, LB_ERR_INVALID, "lb_create: omega must be in (0,2)");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(nullptr, LB_ERR_CUDA, "lb_create: no CUDA device (this library has no CPU fallback)");
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, LB_ERR_INVALID, "lb_create: bad device ordinal");
+
+    sim = new lb_sim();
+    sim->cfg = *cfg;
+    sim->elem = cfg->dtype == LB_F32 ? 4 : 8;
+    const int per512 = 512 / sim->elem;
+    sim->pitch = (cfg->nx + per512 - 1) / per512 * per512;
+    sim->plane = (long long)sim->pitch * cfg->ny;
+    sim->variant = default_variant(cfg->dtype, cfg->math);
+    auto bail = [&](int code, const std::string &m) { g_create_error = m; lb_destroy(sim); return code; };
+#define CUC(call)                                                                                  \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess) return bail(LB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
+    } while (0)
+    CUC(cudaSetDevice(cfg->device));
+    if (cfg->stream) sim->stream = (cudaStream_t)cfg->stream;
+    else { CUC(cudaStreamCreateWithFlags(&sim->stream, cudaStreamNonBlocking)); sim->own_stream = true; }
+    const size_t guard = (size_t)2 * sim->pitch * sim->elem;
+    sim->buf_bytes = guard * 2 + (size_t)9 * sim->plane * sim->elem;
+    for (int i = 0; i < 2; ++i) {
+        CUC(cudaMalloc((void **)&sim->buf_base[i], sim->buf_bytes));
+        CUC(cudaMemsetAsync(sim->buf_base[i], 0, sim->buf_bytes, sim->stream));
+        sim->buf[i] = sim->buf_base[i] + guard;
+    }
+    const size_t mom = (size_t)sim->plane * sim->elem;
+    CUC(cudaMalloc(&sim->rho, mom)); CUC(cudaMalloc(&sim->u, mom)); CUC(cudaMalloc(&sim->v, mom));
+    CUC(cudaMemsetAsync(sim->rho, 0, mom, sim->stream));
+    CUC(cudaMemsetAsync(sim->u, 0, mom, sim->stream));
+    CUC(cudaMemsetAsync(sim->v, 0, mom, sim->stream));
+    CUC(cudaMalloc((void **)&sim->mass_scratch, sizeof(double) * cfg->ny));
+    if (cfg->west_edge == LB_EDGE_HALO || cfg->east_edge == LB_EDGE_HALO) {
+        sim->hl = halo_layout(cfg->ny, sim->elem);
+        CUC(cudaMalloc((void **)&sim->halo, sim->hl.total));
+        CUC(cudaMemsetAsync(sim->halo, 0, sim->hl.total, sim->stream));
+    }
+    CUC(cudaStreamSynchronize(sim->stream));
+#undef CUC
+    *out = sim;
+    return LB_OK;
+}
+
+int lb_destroy(lb_sim *sim)
+{
+    if (!sim) return LB_OK;
+    cudaSetDevice(sim->cfg.device);
+    if (sim->stream) cudaStreamSynchronize(sim->stream);
+    drop_graphs(sim);
+    for (int side = 0; side < 2; ++side)
+        if (sim->peer[side] && sim->peer_ipc[side]) cudaIpcCloseMemHandle(sim->peer[side]);
+    for (int i = 0; i < 2; ++i) cudaFree(sim->buf_base[i]);
+    cudaFree(sim->rho); cudaFree(sim->u); cudaFree(sim->v); cudaFree(sim->feq);
+    cudaFree(sim->mask); cudaFree(sim->span_solid); cudaFree(sim->halo); cudaFree(sim->mass_scratch);
+    if (sim->own_stream && sim->stream) cudaStreamDestroy(sim->stream);
+    cudaGetLastError();
+    delete sim;
+    return LB_OK;
+}
+
+int lb_set_variant(lb_sim *sim, int variant)
+{
+    if (!sim) return LB_ERR_INVALID;
+    if (variant < 0) variant = default_variant(sim->cfg.dtype, sim->cfg.math);
+    if (variant >= g_nvariants || g_variants[variant].dtype != sim->cfg.dtype || g_variants[variant].math != sim->cfg.math)
+        return fail(sim, LB_ERR_INVALID, "lb_set_variant: variant does not match the handle's dtype/math");
+    sim->variant = variant;
+    return LB_OK;
+}
+
+int64_t lb_launch_count(const lb_sim *sim) { return sim ? sim->launches : 0; }
+
+int lb_set_mask(lb_sim *sim, const void *host_mask, int elem_bytes)
+{
+    if (!sim) return LB_ERR_INVALID;
+    CU(cudaSetDevice(sim->cfg.device));
+    drop_graphs(sim);
+    const int nx = sim->cfg.nx, ny = sim->cfg.ny;
+    if (!host_mask) {
+        CU(cudaStreamSynchronize(sim->stream));
+        cudaFree(sim->mask); cudaFree(sim->span_solid);
+        sim->mask = nullptr; sim->span_solid = nullptr;
+        return LB_OK;
+    }
+    if (elem_bytes != 1 && elem_bytes != 4) return fail(sim, LB_ERR_INVALID, "lb_set_mask: elem_bytes must be 1 or 4");
+    std::vector<uint8_t> packed((size_t)nx * ny);
+    if (elem_bytes == 1) {
+        const uint8_t *m = (const uint8_t *)host_mask;
+        for (size_t i = 0; i < packed.size(); ++i) packed[i] = (m[i] == 1) ? 1 : 0;
+    } else {
+        const int32_t *m = (const int32_t *)host_mask;
+        for (size_t i = 0; i < packed.size(); ++i) packed[i] = (m[i] == 1) ? 1 : 0;
+    }
+    if (!sim->mask) {
+        sim->mask_pitch = sim->pitch;
+        sim->nspans = sim->pitch / 32;
+        CU(cudaMalloc((void **)&sim->mask, (size_t)sim->mask_pitch * ny));
+        CU(cudaMalloc((void **)&sim->span_solid, (size_t)sim->nspans * ny));
+    }
+    CU(cudaMemsetAsync(sim->mask, 0, (size_t)sim->mask_pitch * ny, sim->stream));
+    CU(cudaMemcpy2DAsync(sim->mask, sim->mask_pitch, packed.data(), nx, nx, ny, cudaMemcpyHostToDevice, sim->stream));
+    k_span_solid<<<dim3((sim->nspans + 63) / 64, ny), 64, 0, sim->stream>>>(nx, ny, sim->mask, sim->mask_pitch,
+                                                                            sim->span_solid, sim->nspans);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(sim->stream));   // `packed` is about to go out of scope
+    return LB_OK;
+}
+
+int lb_set_mask_disk(lb_sim *sim, double cx, double cy, double r)
+{
+    if (!sim) return LB_ERR_INVALID;
+    CU(cudaSetDevice(sim->cfg.device));
+    drop_graphs(sim);
+    const int nx = sim->cfg.nx, ny = sim->cfg.ny;
+    if (!sim->mask) {
+        sim->mask_pitch = sim->pitch;
+        sim->nspans = sim->pitch / 32;
+        CU(cudaMalloc((void **)&sim->mask, (size_t)sim->mask_pitch * ny));
+        CU(cudaMalloc((void **)&sim->span_solid, (size_t)sim->nspans * ny));
+    }
+    CU(cudaMemsetAsync(sim->mask, 0, (size_t)sim->mask_pitch * ny, sim->stream));
+    k_mask_disk<<<grid2d(sim), 128, 0, sim->stream>>>(nx, ny, sim->cfg.x_offset, cx, cy, r * r, sim->mask, sim->mask_pitch);
+    k_span_solid<<<dim3((sim->nspans + 63) / 64, ny), 64, 0, sim->stream>>>(nx, ny, sim->mask, sim->mask_pitch,
+                                                                            sim->span_solid, sim->nspans);
+    CU(cudaGetLastError());
+    return LB_OK;
+}
+
+int lb_upload_f(lb_sim *sim, const void *host_f)
+{
+    if (!sim || !host_f) return fail(sim, LB_ERR_INVALID, "lb_upload_f: null argument");
+    CU(cudaSetDevice(sim->cfg.device));
+    const size_t w = (size_t)sim->cfg.nx * sim->elem, dp = (size_t)sim->pitch * sim->elem;
+    // planes are contiguous (plane = ny*pitch), so one 2-D copy of 9*ny rows does all nine
+    CU(cudaMemcpy2DAsync(sim->buf[sim->cur], dp, host_f, w, w, (size_t)9 * sim->cfg.ny, cudaMemcpyHostToDevice, sim->stream));
+    // the reference seeds f_streamed with the same data (opencl_dim.py:324-327)
+    CU(cudaMemcpyAsync(sim->buf_base[sim->cur ^ 1], sim->buf_base[sim->cur], sim->buf_bytes, cudaMemcpyDeviceToDevice, sim->stream));
+    CU(cudaStreamSynchronize(sim->stream));
+    return LB_OK;
+}
+
+int lb_upload_moments(lb_sim *sim, const void *host_rho, const void *host_u, const void *host_v)
+{
+    if (!sim) return LB_ERR_INVALID;
+    CU(cudaSetDevice(sim->cfg.device));
+    const size_t w = (size_t)sim->cfg.nx * sim->elem, dp = (size_t)sim->pitch * sim->elem;
+    const void *hs[3] = {host_rho, host_u, host_v};
+    void *ds[3] = {sim->rho, sim->u, sim->v};
+    for (int i = 0; i < 3; ++i)
+        if (hs[i]) CU(cudaMemcpy2DAsync(ds[i], dp, hs[i], w, w, sim->cfg.ny, cudaMemcpyHostToDevice, sim->stream));
+    CU(cudaStreamSynchronize(sim->stream));
+    return LB_OK;
+}
+
+static int ensure_feq(lb_sim *sim)
+{
+    if (!sim->feq) {
+        CU(cudaMalloc(&sim->feq, (size_t)9 * sim->plane * sim->elem));
+        CU(cudaMemsetAsync(sim->feq, 0, (size_t)9 * sim->plane * sim->elem, sim->stream));
+    }
+    return LB_OK;
+}
+
+static int compute_feq(lb_sim *sim)
+{
+    int rc = ensure_feq(sim);
+    if (rc) return rc;
+    const int nx = sim->cfg.nx, ny = sim->cfg.ny;
+    if (sim->cfg.dtype == LB_F32)
+        k_feq_from_moments<float><<<grid2d(sim), 128, 0, sim->stream>>>(nx, ny, sim->pitch, sim->plane, (const float *)sim->rho,
+            (const float *)sim->u, (const float *)sim->v, (float *)sim->feq, consts_of<float>(sim));
+    else
+        k_feq_from_moments<double><<<grid2d(sim), 128, 0, sim->stream>>>(nx, ny, sim->pitch, sim->plane, (const double *)sim->rho,
+            (const double *)sim->u, (const double *)sim->v, (double *)sim->feq, consts_of<double>(sim));
+    CU(cudaGetLastError());
+    return LB_OK;
+}
+
+// ---- the hot path ---------------------------------------------------------------------
+static const int GRAPH_MAX = 64;    // steps per captured graph
+
+int lb_step(lb_sim *sim, int n_steps)
+{
+    if (!sim) return LB_ERR_INVALID;
+    if (n_steps < 0) return fail(sim, LB_ERR_INVALID, "lb_step: negative step count");
+    if (n_steps == 0) return LB_OK;
+    CU(cudaSetDevice(sim->cfg.device));
+    if (uses_halo(sim)) {
+        for (int side = 0; side < 2; ++side) {
+            const int e = side == LB_WEST ? sim->cfg.west_edge : sim->cfg.east_edge;
+            if (e == LB_EDGE_HALO && !sim->peer[side]) return fail(sim, LB_ERR_STATE, "lb_step: halo edge not connected");
+        }
+    }
+    int remaining = n_steps - 1;            // all but the last step skip the moment stores
+    const bool graphs_ok = !uses_halo(sim); // halo launches carry a per-step flag value
+    while (remaining > 0) {
+        int chunk = remaining;
+        if (graphs_ok && chunk >= 4) {
+            if (chunk > GRAPH_MAX) chunk = GRAPH_MAX;
+            chunk &= ~1;                    // an even chunk returns to the same buffer
+            const int gi = sim->cur;
+            if (!sim->graph[gi] || sim->graph_len[gi] != chunk || sim->graph_variant[gi] != sim->variant) {
+                if (sim->graph[gi]) { cudaGraphExecDestroy(sim->graph[gi]); sim->graph[gi] = nullptr; }
+                cudaGraph_t g = nullptr;
+                CU(cudaStreamBeginCapture(sim->stream, cudaStreamCaptureModeThreadLocal));
+                int idx = sim->cur, rc = LB_OK;
+                const int64_t l0 = sim->launches;
+                for (int i = 0; i < chunk && rc == LB_OK; ++i) { rc = launch_step(sim, idx, 0, 0); idx ^= 1; }
+                sim->launches = l0;          // captured, not yet executed
+                cudaError_t ce = cudaStreamEndCapture(sim->stream, &g);
+                if (rc != LB_OK) { if (g) cudaGraphDestroy(g); return rc; }
+                CU(ce);
+                ce = cudaGraphInstantiate(&sim->graph[gi], g, 0);
+                cudaGraphDestroy(g);
+                CU(ce);
+                sim->graph_len[gi] = chunk; sim->graph_variant[gi] = sim->variant;
+            }
+            CU(cudaGraphLaunch(sim->graph[gi], sim->stream));
+            sim->launches += chunk;
+            sim->state_index += chunk;
+        } else {
+            for (int i = 0; i < chunk; ++i) {
+                int rc = launch_step(sim, sim->cur, 0, sim->state_index);
+                if (rc) return rc;
+                sim->cur ^= 1; sim->state_index++;
+            }
+        }
+        remaining -= chunk;
+    }
+    int rc = launch_step(sim, sim->cur, 1, sim->state_index);
+    if (rc) return rc;
+    sim->cur ^= 1; sim->state_index++;
+    return LB_OK;
+}
+
+int lb_sync(lb_sim *sim)
+{
+    if (!sim) return LB_ERR_INVALID;
+    CU(cudaSetDevice(sim->cfg.device));
+    CU(cudaStreamSynchronize(sim->stream));
+    if (sim->halo) {
+        unsigned int e = 0;
+        CU(cudaMemcpy(&e, sim->halo + sim->hl.off_error, sizeof(e), cudaMemcpyDeviceToHost));
+        if (e) return fail(sim, LB_ERR_HALO, "halo hand-shake timed out (neighbour slab did not publish its boundary column)");
+    }
+    return LB_OK;
+}
+
+int lb_download(lb_sim *sim, int field, void *host_out)
+{
+    if (!sim || !host_out) return fail(sim, LB_ERR_INVALID, "lb_download: null argument");
+    CU(cudaSetDevice(sim->cfg.device));
+    const size_t w = (size_t)sim->cfg.nx * sim->elem, dp = (size_t)sim->pitch * sim->elem;
+    const void *src = nullptr;
+    size_t rows = sim->cfg.ny;
+    switch (field) {
+    case LB_FIELD_F: src = sim->buf[sim->cur]; rows *= 9; break;
+    case LB_FIELD_FEQ: { int rc = compute_feq(sim); if (rc) return rc; src = sim->feq; rows *= 9; break; }
+    case LB_FIELD_RHO: src = sim->rho; break;
+    case LB_FIELD_U: src = sim->u; break;
+    case LB_FIELD_V: src = sim->v; break;
+    default: return fail(sim, LB_ERR_INVALID, "lb_download: unknown field");
+    }
+    CU(cudaMemcpy2DAsync(host_out, w, src, dp, w, rows, cudaMemcpyDeviceToHost, sim->stream));
+    return lb_sync(sim);
+}
+
+void *lb_stream(lb_sim *sim) { return sim ? (void *)sim->stream : nullptr; }
+
+int lb_device_ptr(lb_sim *sim, int field, void **ptr, int64_t *pitch_elems)
+{
+    if (!sim || !ptr) return LB_ERR_INVALID;
+    switch (field) {
+    case LB_FIELD_F: *ptr = sim->buf[sim->cur]; break;
+    case LB_FIELD_FEQ: *ptr = sim->feq; break;
+    case LB_FIELD_RHO: *ptr = sim->rho; break;
+    case LB_FIELD_U: *ptr = sim->u; break;
+    case LB_FIELD_V: *ptr = sim->v; break;
+    default: return fail(sim, LB_ERR_INVALID, "lb_device_ptr: unknown field");
+    }
+    if (pitch_elems) *pitch_elems = sim->pitch;
+    return LB_OK;
+}
+
+// ---- single stages --------------------------------------------------------------------
+#define DISPATCH(KERNEL, GRID, ...)                                                                 \
+    do {                                                                                           \
+        if (sim->cfg.dtype == LB_F32) { typedef float T; KERNEL<T><<<GRID, 128, 0, sim->stream>>>(__VA_ARGS__); } \
+        else { typedef double T; KERNEL<T><<<GRID, 128, 0, sim->stream>>>(__VA_ARGS__); }           \
+        CU(cudaGetLastError());                                                                    \
+    } while (0)
+
+int lb_stage_move(lb_sim *sim)
+{
+    if (!sim) return LB_ERR_INVALID;
+    if (uses_halo(sim)) return fail(sim, LB_ERR_STATE, "single stages are not available on halo-connected slabs");
+    CU(cudaSetDevice(sim->cfg.device));
+    DISPATCH(k_stage_move, grid2d(sim), sim->cfg.nx, sim->cfg.ny, sim->pitch, sim->plane, sim->cfg.bc == LB_BC_PERIODIC,
+             (const T *)sim->buf[sim->cur], (T *)sim->buf[sim->cur ^ 1]);
+    sim->cur ^= 1;
+    return LB_OK;
+}
+
+int lb_stage_move_bcs(lb_sim *sim)
+{
+    if (!sim) return LB_ERR_INVALID;
+    CU(cudaSetDevice(sim->cfg.device));
+    DISPATCH(k_stage_bcs, grid2d(sim), sim->cfg.nx, sim->cfg.ny, sim->pitch, sim->plane, sim->cfg.global_nx, sim->cfg.x_offset,
+             sim->cfg.bc == LB_BC_PIPE, sim->mask, sim->mask_pitch, (T *)sim->buf[sim->cur], consts_of<T>(sim));
+    return LB_OK;
+}
+
+int lb_stage_update_hydro(lb_sim *sim)
+{
+    if (!sim) return LB_ERR_INVALID;
+    CU(cudaSetDevice(sim->cfg.device));
+    DISPATCH(k_stage_hydro, grid2d(sim), sim->cfg.nx, sim->cfg.ny, sim->pitch, sim->plane, (const T *)sim->buf[sim->cur],
+             (T *)sim->rho, (T *)sim->u, (T *)sim->v);
+    if (sim->cfg.zero_obstacle_velocity && sim->mask) return lb_stage_zero_velocity(sim);
+    return LB_OK;
+}
+
+int lb_stage_zero_velocity(lb_sim *sim)
+{
+    if (!sim) return LB_ERR_INVALID;
+    if (!sim->mask) return LB_OK;
+    CU(cudaSetDevice(sim->cfg.device));
+    DISPATCH(k_zero_velocity, grid2d(sim), sim->cfg.nx, sim->cfg.ny, sim->pitch, sim->mask, sim->mask_pitch, (T *)sim->u, (T *)sim->v);
+    return LB_OK;
+}
+
+int lb_stage_update_feq(lb_sim *sim)
+{
+    if (!sim) return LB_ERR_INVALID;
+    CU(cudaSetDevice(sim->cfg.device));
+    return compute_feq(sim);
+}
+
+int lb_stage_collide(lb_sim *sim)
+{
+    if (!sim) return LB_ERR_INVALID;
+    CU(cudaSetDevice(sim->cfg.device));
+    if (!sim->feq) return fail(sim, LB_ERR_STATE, "lb_stage_collide: call lb_stage_update_feq first");
+    DISPATCH(k_stage_collide, grid2d(sim), sim->cfg.nx, sim->cfg.ny, sim->pitch, sim->plane, (T *)sim->buf[sim->cur],
+             (const T *)sim->feq, consts_of<T>(sim));
+    return LB_OK;
+}
+
+// ---- synthetic initialisers / diagnostics -----------------------------------------------
+int lb_init_synthetic(lb_sim *sim, int kind, double u0, double amplitude, uint64_t seed)
+{
+    if (!sim) return LB_ERR_INVALID;
+    if (kind != LB_SYNTH_PIPE_RAMP && kind != LB_SYNTH_SHEAR_LAYERS) return fail(sim, LB_ERR_INVALID, "lb_init_synthetic: bad kind");
+    CU(cudaSetDevice(sim->cfg.device));
+    DISPATCH(k_init_synth, grid2d(sim), sim->cfg.nx, sim->cfg.ny, sim->pitch, sim->plane, sim->cfg.global_nx, sim->cfg.x_offset, kind,
+             u0, amplitude, (unsigned long long)seed, sim->cfg.inlet_rho, sim->cfg.outlet_rho, sim->mask, sim->mask_pitch,
+             (T *)sim->buf[sim->cur], (T *)sim->buf[sim->cur ^ 1], (T *)sim->rho, (T *)sim->u, (T *)sim->v, consts_of<T>(sim));
+    return LB_OK;
+}
+
+int lb_total_mass(lb_sim *sim, double *out)
+{
+    if (!sim || !out) return LB_ERR_INVALID;
+    CU(cudaSetDevice(sim->cfg.device));
+    const int ny = sim->cfg.ny;
+    if (sim->cfg.dtype == LB_F32)
+        k_mass<float><<<ny, 256, 0, sim->stream>>>(sim->cfg.nx, ny, sim->pitch, sim->plane, (const float *)sim->buf[sim->cur], sim->mass_scratch);
+    else
+        k_mass<double><<<ny, 256, 0, sim->stream>>>(sim->cfg.nx, ny, sim->pitch, sim->plane, (const double *)sim->buf[sim->cur], sim->mass_scratch);
+    CU(cudaGetLastError());
+    std::vector<double> rows(ny);
+    CU(cudaMemcpyAsync(rows.data(), sim->mass_scratch, sizeof(double) * ny, cudaMemcpyDeviceToHost, sim->stream));
+    CU(cudaStreamSynchronize(sim->stream));
+    long double acc = 0;
+    for (double r : rows) acc += r;
+    *out = (double)acc;
+    return LB_OK;
+}
+
+// ---- halo -----------------------------------------------------------------------------
+int lb_halo_ipc_handle(lb_sim *sim, void *out_handle)
+{
+    if (!sim || !out_handle) return LB_ERR_INVALID;
+    if (!sim->halo) return fail(sim, LB_ERR_STATE, "lb_halo_ipc_handle: this slab has no halo edge");
+    static_assert(sizeof(cudaIpcMemHandle_t) == LB_IPC_HANDLE_BYTES, "IPC handle size");
+    CU(cudaSetDevice(sim->cfg.device));
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, sim->halo));
+    memcpy(out_handle, &h, sizeof(h));
+    return LB_OK;
+}
+
+int lb_halo_connect_ipc(lb_sim *sim, int side, const void *peer_handle, int peer_device)
+{
+    if (!sim || !peer_handle || (side != LB_WEST && side != LB_EAST)) return fail(sim, LB_ERR_INVALID, "lb_halo_connect_ipc: bad argument");
+    (void)peer_device;
+    CU(cudaSetDevice(sim->cfg.device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, peer_handle, sizeof(h));
+    void *p = nullptr;
+    CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    sim->peer[side] = (char *)p;
+    sim->peer_ipc[side] = true;
+    return LB_OK;
+}
+
+int lb_halo_connect_local(lb_sim *sim, int side, lb_sim *peer)
+{
+    if (!sim || !peer || (side != LB_WEST && side != LB_EAST)) return fail(sim, LB_ERR_INVALID, "lb_halo_connect_local: bad argument");
+    if (!peer->halo) return fail(sim, LB_ERR_STATE, "lb_halo_connect_local: peer has no halo arena");
+    if (peer->cfg.ny != sim->cfg.ny || peer->cfg.dtype != sim->cfg.dtype)
+        return fail(sim, LB_ERR_INVALID, "lb_halo_connect_local: neighbour slabs must share ny and dtype");
+    CU(cudaSetDevice(sim->cfg.device));
+    if (peer->cfg.device != sim->cfg.device) {
+        int can = 0;
+        CU(cudaDeviceCanAccessPeer(&can, sim->cfg.device, peer->cfg.device));
+        if (!can) return fail(sim, LB_ERR_CUDA, "lb_halo_connect_local: devices cannot access each other");
+        cudaError_t e = cudaDeviceEnablePeerAccess(peer->cfg.device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CU(e);
+        cudaGetLastError();
+    }
+    sim->peer[side] = peer->halo;
+    sim->peer_ipc[side] = false;
+    return LB_OK;
+}
+
+int lb_halo_prime(lb_sim *sim)
+{
+    if (!sim) return LB_ERR_INVALID;
+    if (!uses_halo(sim)) return LB_OK;
+    CU(cudaSetDevice(sim->cfg.device));
+    const HaloLayout &h = sim->hl;
+    const int par = sim->state_index & 1;
+    char *ow = (sim->cfg.west_edge == LB_EDGE_HALO && sim->peer[LB_WEST]) ? sim->peer[LB_WEST] + h.off_ghost_e[par] : nullptr;
+    char *oe = (sim->cfg.east_edge == LB_EDGE_HALO && sim->peer[LB_EAST]) ? sim->peer[LB_EAST] + h.off_ghost_w[par] : nullptr;
+    unsigned int *fw = ow ? (unsigned int *)(sim->peer[LB_WEST] + h.off_flag_e) : nullptr;
+    unsigned int *fe = oe ? (unsigned int *)(sim->peer[LB_EAST] + h.off_flag_w) : nullptr;
+    if ((sim->cfg.west_edge == LB_EDGE_HALO && !ow) || (sim->cfg.east_edge == LB_EDGE_HALO && !oe))
+        return fail(sim, LB_ERR_STATE, "lb_halo_prime: halo edge not connected");
+    if (sim->cfg.dtype == LB_F32)
+        k_halo_prime<float><<<1, 1024, 0, sim->stream>>>(sim->cfg.nx, sim->cfg.ny, sim->pitch, sim->plane, (const float *)sim->buf[sim->cur],
+                                                          (float *)ow, (float *)oe, fw, fe, sim->state_index + 1);
+    else
+        k_halo_prime<double><<<1, 1024, 0, sim->stream>>>(sim->cfg.nx, sim->cfg.ny, sim->pitch, sim->plane, (const double *)sim->buf[sim->cur],
+                                                           (double *)ow, (double *)oe, fw, fe, sim->state_index + 1);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(sim->stream));
+    return LB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,361 @@
+// The hot path: ONE kernel per lattice update.
+//
+// Replaces the reference's seven launches per step (opencl_dim.py:372-387, :510-518):
+//   move + copy_buffer (D2Q9.cl:139-171, :123-137)  -> pull-streaming from the `src` buffer
+//   move_bcs (D2Q9.cl:173-261)                      -> pipe_bc() on boundary threads only
+//   bounceback_in_obstacle (D2Q9.cl:398-433)        -> bounce_back() where the mask says solid
+//   update_hydro + update_feq + collide_particles   -> collide_node() in registers
+// and writes the post-collision populations into the `dst` buffer (ping-pong).
+//
+// Data layout: f[9][ny][pitch], x fastest, pitch a multiple of 512 B so
+// every warp-row is either fully inside or fully outside a row; two guard rows before and
+// after the 9 planes make every shifted vector / scalar access land in owned memory.
+//
+// Thread mapping: a warp owns SPAN = 32*V consecutive cells of a row (V = cells per thread,
+// 128-bit accesses for V*sizeof(T) == 16).  The +-1 x-shift of populations 1,5,8 / 3,6,7 is
+// resolved in registers: aligned vector load, one warp shuffle for the element that crosses
+// the thread boundary, one predicated scalar load on lane 0 / lane 31 for the element that
+// crosses the warp boundary.  A CTA is WX warps wide and WY warps tall; each warp walks R
+// rows.  Every plane element is read exactly once per step, so the algorithmic traffic is
+// 9 loads + 9 stores per cell: 72 B (fp32) / 144 B (fp64) per lattice update.
+#pragma once
+#include "lb_device.cuh"
+
+namespace lb {
+
+struct StepParams {
+    const void *src;          // plane 0, row 0 of the buffer being read
+    void *dst;                // plane 0, row 0 of the buffer being written
+    long long plane;          // elements between consecutive population planes
+    int nx, ny, pitch;        // slab extent and row pitch (elements)
+    int gnx, x_off;           // global width, global x of local column 0
+    int bc;                   // BC_PIPE / BC_PERIODIC
+    int west, east;           // EDGE_* beyond column 0 / column nx-1
+    int write_moments;        // store rho,u,v (last step of a run only)
+    int zero_obstacle_velocity;
+    const uint8_t *mask;      // [ny][mask_pitch], 1 = solid; nullptr = no obstacles
+    const uint8_t *span_solid;// [ny][nspans]: does this group of 32 cells of this row contain a solid node
+    int mask_pitch, nspans;
+    void *rho, *u, *v;        // [ny][pitch]
+    double omega, inlet_rho, outlet_rho, cs2, cs22, two_cs4;
+    // x-slab halo (EDGE_HALO): ghost columns are [3][ny+2] (slot, y+1)
+    const void *ghost_w;      // populations 1,5,8 of the west neighbour's last column (read)
+    const void *ghost_e;      // populations 3,6,7 of the east neighbour's first column (read)
+    void *out_w;              // west neighbour's east ghost column (write 3,6,7 of my column 0)
+    void *out_e;              // east neighbour's west ghost column (write 1,5,8 of my column nx-1)
+    unsigned int *flag_w_local, *flag_e_local;     // polled: neighbour's data for this step is in
+    unsigned int *flag_w_remote, *flag_e_remote;   // published: my data for the next step is out
+    unsigned int *done_w, *done_e;                 // edge-tile completion counters (local)
+    unsigned int *error_word;                      // set on hand-shake timeout
+    unsigned int step_id;                          // flag value that must be visible before reading ghosts
+    int tiles_x, tiles_y;
+    int edge_first;           // order edge tiles first (halo overlap)
+};
+
+// ---- vector access helpers ----------------------------------------------------------
+template <typename T, int V> struct VecOf;
+template <> struct VecOf<float, 4> { using type = float4; };
+template <> struct VecOf<float, 2> { using type = float2; };
+template <> struct VecOf<float, 1> { using type = float; };
+template <> struct VecOf<double, 2> { using type = double2; };
+template <> struct VecOf<double, 1> { using type = double; };
+
+template <typename T, int V> struct Pack { T v[V]; };
+
+__device__ __forceinline__ void unpack(const float4 &a, Pack<float, 4> &p) { p.v[0] = a.x; p.v[1] = a.y; p.v[2] = a.z; p.v[3] = a.w; }
+__device__ __forceinline__ void unpack(const float2 &a, Pack<float, 2> &p) { p.v[0] = a.x; p.v[1] = a.y; }
+__device__ __forceinline__ void unpack(const float &a, Pack<float, 1> &p) { p.v[0] = a; }
+__device__ __forceinline__ void unpack(const double2 &a, Pack<double, 2> &p) { p.v[0] = a.x; p.v[1] = a.y; }
+__device__ __forceinline__ void unpack(const double &a, Pack<double, 1> &p) { p.v[0] = a; }
+__device__ __forceinline__ float4 repack(const Pack<float, 4> &p) { return make_float4(p.v[0], p.v[1], p.v[2], p.v[3]); }
+__device__ __forceinline__ float2 repack(const Pack<float, 2> &p) { return make_float2(p.v[0], p.v[1]); }
+__device__ __forceinline__ float repack(const Pack<float, 1> &p) { return p.v[0]; }
+__device__ __forceinline__ double2 repack(const Pack<double, 2> &p) { return make_double2(p.v[0], p.v[1]); }
+__device__ __forceinline__ double repack(const Pack<double, 1> &p) { return p.v[0]; }
+
+// LDP: 0 = ld.global, 1 = ld.global.nc (read-only path), 2 = ld.global.cs (streaming / evict-first)
+template <int LDP, typename VT>
+__device__ __forceinline__ VT ld_vec(const VT *p)
+{
+    if (LDP == 1) return __ldg(p);
+    if (LDP == 2) return __ldcs(p);
+    return *p;
+}
+// STP: 0 = st.global, 1 = st.global.cs (streaming), 2 = st.global.wt
+template <int STP, typename VT>
+__device__ __forceinline__ void st_vec(VT *p, const VT &v)
+{
+    if (STP == 1) __stcs(p, v);
+    else if (STP == 2) __stwt(p, v);
+    else *p = v;
+}
+
+template <typename T, int V, int LDP>
+__device__ __forceinline__ Pack<T, V> load_pack(const T *p)
+{
+    using VT = typename VecOf<T, V>::type;
+    Pack<T, V> r;
+    unpack(ld_vec<LDP>(reinterpret_cast<const VT *>(p)), r);
+    return r;
+}
+template <typename T, int V, int STP>
+__device__ __forceinline__ void store_pack(T *p, const Pack<T, V> &r)
+{
+    using VT = typename VecOf<T, V>::type;
+    st_vec<STP>(reinterpret_cast<VT *>(p), repack(r));
+}
+
+// ---- halo hand-shake ----------------------------------------------------------------
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int *p)
+{
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned int *p, unsigned int v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// Wait (bounded: 2 s) until *flag >= want.  One thread polls, the CTA follows through a barrier.
+__device__ __forceinline__ void wait_flag(const unsigned int *flag, unsigned int want, unsigned int *error_word)
+{
+    if (threadIdx.x == 0) {
+        const unsigned long long t0 = globaltimer_ns();
+        while ((int)(ld_acquire_sys(flag) - want) < 0) {
+            if (globaltimer_ns() - t0 > 2000000000ull) { atomicExch(error_word, 1u); break; }
+            __nanosleep(64);
+        }
+    }
+    __syncthreads();
+}
+
+// ---- the fused kernel -----------------------------------------------------------------
+template <typename T, int V, int MATH, int WX, int WY, int R, int MINB, int LDP, int STP>
+__global__ void __launch_bounds__(32 * WX * WY, MINB) fused_step_kernel(const StepParams p)
+{
+    constexpr int SPAN = 32 * V;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int wx = warp % WX, wy = warp / WX;
+
+    // tile decode; with edge_first the two edge tile columns come first in launch order so that
+    // the neighbours' ghost data is published as early as possible in the step
+    int bx, by;
+    {
+        const int b = blockIdx.x;
+        if (p.edge_first && p.tiles_x >= 2) {
+            const int n_edge = 2 * p.tiles_y;
+            if (b < n_edge) { bx = (b & 1) ? p.tiles_x - 1 : 0; by = b >> 1; }
+            else { const int r = b - n_edge; bx = 1 + r % (p.tiles_x - 2); by = r / (p.tiles_x - 2); }
+        } else { bx = b % p.tiles_x; by = b / p.tiles_x; }
+    }
+    const bool halo_w = (p.west == EDGE_HALO) && (bx == 0);
+    const bool halo_e = (p.east == EDGE_HALO) && (bx == p.tiles_x - 1);
+    if (halo_w) wait_flag(p.flag_w_local, p.step_id, p.error_word);
+    if (halo_e) wait_flag(p.flag_e_local, p.step_id, p.error_word);
+
+    const int span0 = (bx * WX + wx) * SPAN;          // first cell of this warp's span
+    const int x0 = span0 + lane * V;                  // first cell of this thread
+    const int ybase = (by * WY + wy) * R;
+    const bool warp_active = span0 < p.pitch;         // warp-uniform (pitch is a multiple of SPAN)
+
+    const T *__restrict__ src = static_cast<const T *>(p.src);
+    T *__restrict__ dst = static_cast<T *>(p.dst);
+    const long long plane = p.plane;
+    const int nx = p.nx, ny = p.ny, pitch = p.pitch;
+    const Consts<T> c = make_consts<T>(p.omega, p.inlet_rho, p.outlet_rho, p.cs2, p.cs22, p.two_cs4);
+    const bool periodic = (p.bc == BC_PERIODIC);
+    const int el_east = (nx - 1) - x0;                // element index of column nx-1 in this thread, if in [0,V)
+    const bool has_west = (x0 == 0);
+    const bool has_east = (el_east >= 0 && el_east < V);
+
+    if (warp_active) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int y = ybase + r;
+            if (y >= ny) break;                       // warp-uniform
+            int ym = y - 1, yp = y + 1;               // source rows of the cy=+1 / cy=-1 populations
+            if (periodic) { if (ym < 0) ym = ny - 1; if (yp >= ny) yp = 0; }
+            const long long rc = (long long)y * pitch + x0;
+            const long long rm = (long long)ym * pitch + x0;
+            const long long rp = (long long)yp * pitch + x0;
+
+            // --- 9 aligned vector loads (guard rows make y=-1 / y=ny addresses valid) ---
+            Pack<T, V> q[9];
+            q[0] = load_pack<T, V, LDP>(src + 0 * plane + rc);
+            q[1] = load_pack<T, V, LDP>(src + 1 * plane + rc);
+            q[2] = load_pack<T, V, LDP>(src + 2 * plane + rm);
+            q[3] = load_pack<T, V, LDP>(src + 3 * plane + rc);
+            q[4] = load_pack<T, V, LDP>(src + 4 * plane + rp);
+            q[5] = load_pack<T, V, LDP>(src + 5 * plane + rm);
+            q[6] = load_pack<T, V, LDP>(src + 6 * plane + rm);
+            q[7] = load_pack<T, V, LDP>(src + 7 * plane + rp);
+            q[8] = load_pack<T, V, LDP>(src + 8 * plane + rp);
+            // --- elements that cross the warp boundary ---
+            T l1 = (T)0, l5 = (T)0, l8 = (T)0, r3 = (T)0, r6 = (T)0, r7 = (T)0;
+            if (lane == 0) {
+                l1 = src[1 * plane + rc - 1];
+                l5 = src[5 * plane + rm - 1];
+                l8 = src[8 * plane + rp - 1];
+            }
+            if (lane == 31) {
+                r3 = src[3 * plane + rc + V];
+                r6 = src[6 * plane + rm + V];
+                r7 = src[7 * plane + rp + V];
+            }
+            // --- elements that cross the thread boundary ---
+            {
+                const T s1 = __shfl_up_sync(0xffffffffu, q[1].v[V - 1], 1);
+                const T s5 = __shfl_up_sync(0xffffffffu, q[5].v[V - 1], 1);
+                const T s8 = __shfl_up_sync(0xffffffffu, q[8].v[V - 1], 1);
+                const T s3 = __shfl_down_sync(0xffffffffu, q[3].v[0], 1);
+                const T s6 = __shfl_down_sync(0xffffffffu, q[6].v[0], 1);
+                const T s7 = __shfl_down_sync(0xffffffffu, q[7].v[0], 1);
+                if (lane != 0) { l1 = s1; l5 = s5; l8 = s8; }
+                if (lane != 31) { r3 = s3; r6 = s6; r7 = s7; }
+            }
+            // shift: populations moving +x take the value of the cell to their left, and vice versa
+#pragma unroll
+            for (int e = V - 1; e > 0; --e) {
+                q[1].v[e] = q[1].v[e - 1]; q[5].v[e] = q[5].v[e - 1]; q[8].v[e] = q[8].v[e - 1];
+            }
+            q[1].v[0] = l1; q[5].v[0] = l5; q[8].v[0] = l8;
+#pragma unroll
+            for (int e = 0; e < V - 1; ++e) {
+                q[3].v[e] = q[3].v[e + 1]; q[6].v[e] = q[6].v[e + 1]; q[7].v[e] = q[7].v[e + 1];
+            }
+            q[3].v[V - 1] = r3; q[6].v[V - 1] = r6; q[7].v[V - 1] = r7;
+
+            // --- first / last column of the slab: wrap, ghost column, or domain boundary ---
+            if (has_west && p.west != EDGE_BOUNDARY) {
+                T a1, a5, a8;
+                if (p.west == EDGE_WRAP) {
+                    a1 = src[1 * plane + (long long)y * pitch + (nx - 1)];
+                    a5 = src[5 * plane + (long long)ym * pitch + (nx - 1)];
+                    a8 = src[8 * plane + (long long)yp * pitch + (nx - 1)];
+                } else {
+                    const T *gw = static_cast<const T *>(p.ghost_w);
+                    a1 = __ldcv(gw + 0 * (ny + 2) + (y + 1));
+                    a5 = __ldcv(gw + 1 * (ny + 2) + (ym + 1));
+                    a8 = __ldcv(gw + 2 * (ny + 2) + (yp + 1));
+                }
+                q[1].v[0] = a1; q[5].v[0] = a5; q[8].v[0] = a8;
+            }
+            if (has_east && p.east != EDGE_BOUNDARY) {
+                T a3, a6, a7;
+                if (p.east == EDGE_WRAP) {
+                    a3 = src[3 * plane + (long long)y * pitch];
+                    a6 = src[6 * plane + (long long)ym * pitch];
+                    a7 = src[7 * plane + (long long)yp * pitch];
+                } else {
+                    const T *ge = static_cast<const T *>(p.ghost_e);
+                    a3 = __ldcv(ge + 0 * (ny + 2) + (y + 1));
+                    a6 = __ldcv(ge + 1 * (ny + 2) + (ym + 1));
+                    a7 = __ldcv(ge + 2 * (ny + 2) + (yp + 1));
+                }
+#pragma unroll
+                for (int e = 0; e < V; ++e)
+                    if (e == el_east) { q[3].v[e] = a3; q[6].v[e] = a6; q[7].v[e] = a7; }
+            }
+
+            // --- obstacle mask: one flag byte per (row, span) says whether to look at all ---
+            uint32_t solid_bits = 0;
+            if (p.mask != nullptr) {
+                // flags have a fixed granularity of 32 cells: this warp's span covers SPAN/32 of them
+                const uint8_t *sf = p.span_solid + (long long)y * p.nspans + (span0 >> 5);
+                unsigned int any = 0;
+#pragma unroll
+                for (int k = 0; k < SPAN / 32; ++k) any |= sf[k];
+                if (any) {                                               // warp-uniform
+#pragma unroll
+                    for (int e = 0; e < V; ++e)
+                        if (x0 + e < nx && p.mask[(long long)y * p.mask_pitch + x0 + e] == 1) solid_bits |= (1u << e);
+                }
+            }
+
+            // --- per node: boundary closure, bounce-back, moments + feq + BGK ---
+            const bool row_is_wall = (!periodic) && (y == 0 || y == ny - 1);
+            const bool bc_thread = (!periodic) && (row_is_wall || (has_west && p.west == EDGE_BOUNDARY) ||
+                                                  (has_east && p.east == EDGE_BOUNDARY));
+            Pack<T, V> mrho, mu, mv;
+#pragma unroll
+            for (int e = 0; e < V; ++e) {
+                T g[9];
+#pragma unroll
+                for (int j = 0; j < 9; ++j) g[j] = q[j].v[e];
+                if (bc_thread) pipe_bc<T>(c, p.x_off + x0 + e, y, p.gnx, ny, g);
+                const bool solid = (solid_bits >> e) & 1u;
+                if (solid) bounce_back<T>(g);
+                collide_node<T, MATH>(c, g, mrho.v[e], mu.v[e], mv.v[e], solid && p.zero_obstacle_velocity);
+#pragma unroll
+                for (int j = 0; j < 9; ++j) q[j].v[e] = g[j];
+            }
+
+            // --- stores: aligned vectors; the one thread straddling column nx-1 goes scalar ---
+            if (x0 + V <= nx) {
+#pragma unroll
+                for (int j = 0; j < 9; ++j) store_pack<T, V, STP>(dst + j * plane + rc, q[j]);
+                if (p.write_moments) {
+                    store_pack<T, V, 0>(static_cast<T *>(p.rho) + rc, mrho);
+                    store_pack<T, V, 0>(static_cast<T *>(p.u) + rc, mu);
+                    store_pack<T, V, 0>(static_cast<T *>(p.v) + rc, mv);
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < V; ++e) {
+                    if (x0 + e < nx) {
+#pragma unroll
+                        for (int j = 0; j < 9; ++j) dst[j * plane + rc + e] = q[j].v[e];
+                        if (p.write_moments) {
+                            static_cast<T *>(p.rho)[rc + e] = mrho.v[e];
+                            static_cast<T *>(p.u)[rc + e] = mu.v[e];
+                            static_cast<T *>(p.v)[rc + e] = mv.v[e];
+                        }
+                    }
+                }
+            }
+
+            // --- publish my boundary columns into the neighbours' ghost columns ---
+            if (has_west && p.west == EDGE_HALO) {
+                T *ow = static_cast<T *>(p.out_w);
+                ow[0 * (ny + 2) + (y + 1)] = q[3].v[0];
+                ow[1 * (ny + 2) + (y + 1)] = q[6].v[0];
+                ow[2 * (ny + 2) + (y + 1)] = q[7].v[0];
+            }
+            if (has_east && p.east == EDGE_HALO) {
+                T *oe = static_cast<T *>(p.out_e);
+#pragma unroll
+                for (int e = 0; e < V; ++e)
+                    if (e == el_east) {
+                        oe[0 * (ny + 2) + (y + 1)] = q[1].v[e];
+                        oe[1 * (ny + 2) + (y + 1)] = q[5].v[e];
+                        oe[2 * (ny + 2) + (y + 1)] = q[8].v[e];
+                    }
+            }
+        }
+    }
+
+    // --- last edge tile of each side releases the neighbour for its next step ---
+    if (halo_w || halo_e) {
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            if (halo_w) {
+                const unsigned int old = atomicAdd(p.done_w, 1u);
+                if (old == (unsigned int)p.tiles_y - 1u) { *p.done_w = 0u; st_release_sys(p.flag_w_remote, p.step_id + 1u); }
+            }
+            if (halo_e) {
+                const unsigned int old = atomicAdd(p.done_e, 1u);
+                if (old == (unsigned int)p.tiles_y - 1u) { *p.done_e = 0u; st_release_sys(p.flag_e_remote, p.step_id + 1u); }
+            }
+        }
+    }
+}
+
+}  // namespace lb

@@ -1,0 +1,315 @@
+"""Low-level lattice object: one C-ABI handle (= one slab on one GPU).
+
+Arrays exchanged with this class use the DEVICE layout of the reference:
+f[9][ny][nx] / rho[ny][nx], x fastest (D2Q9.cl:24-25).  The reference's host arrays are
+Fortran-order (nx, ny, 9) / (nx, ny) (opencl_dim.py:165), which is the same memory: `a.T` of
+such an array is a C-contiguous view in device layout, no copy.
+"""
+import ctypes as ct
+
+import numpy as np
+
+from . import native as N
+
+# Lattice constants exactly as the reference computes them (opencl_dim.py:26-30); they are
+# handed to the library as doubles so both sides use the very same bits.
+cs = 1. / np.sqrt(3)
+cs2 = cs ** 2
+cs22 = 2 * cs2
+two_cs4 = 2 * cs ** 4
+
+_BC = {"pipe": N.BC_PIPE, "periodic": N.BC_PERIODIC}
+_MATH = {"strict": N.MATH_STRICT, "fast": N.MATH_FAST}
+_EDGE = {"boundary": N.EDGE_BOUNDARY, "wrap": N.EDGE_WRAP, "halo": N.EDGE_HALO}
+_FIELD = {"f": N.FIELD_F, "feq": N.FIELD_FEQ, "rho": N.FIELD_RHO, "u": N.FIELD_U, "v": N.FIELD_V}
+
+
+def _ptr(a):
+    return ct.c_void_p(a.ctypes.data)
+
+
+class Lattice:
+    """D2Q9 BGK lattice on one CUDA device.
+
+    Parameters mirror what the reference's kernels take (omega, inlet/outlet density,
+    obstacle mask, populations) rather than the physical parameters of the simulation
+    classes; `lb_b200.dimensionless` builds on this.
+
+    bc     'pipe' (pressure inlet/outlet + walls, D2Q9.cl:173-261) or 'periodic'
+    math   'strict' (bit-identical to the CPU oracle of D2Q9.cl) or 'fast' (FMA + reciprocals)
+    dtype  np.float32 (the reference's precision) or np.float64
+    """
+
+    def __init__(self, nx, ny, omega, inlet_rho=1.0, outlet_rho=1.0, mask=None, f0=None, bc="pipe",
+                 dtype=np.float32, math="fast", device=0, zero_obstacle_velocity=False,
+                 global_nx=None, x_offset=0, west_edge=None, east_edge=None, stream=None):
+        self._h = None
+        self.nx, self.ny = int(nx), int(ny)
+        self.dtype = np.dtype(dtype)
+        if self.dtype not in (np.dtype(np.float32), np.dtype(np.float64)):
+            raise ValueError("dtype must be float32 or float64")
+        self.bc, self.math = bc, math
+        default_edge = "wrap" if bc == "periodic" else "boundary"
+        cfg = N.LBConfig()
+        cfg.struct_size = ct.sizeof(N.LBConfig)
+        cfg.device = int(device)
+        cfg.nx, cfg.ny = self.nx, self.ny
+        cfg.dtype = N.F32 if self.dtype == np.float32 else N.F64
+        cfg.bc = _BC[bc]
+        cfg.math = _MATH[math]
+        cfg.zero_obstacle_velocity = int(bool(zero_obstacle_velocity))
+        cfg.global_nx = int(global_nx if global_nx is not None else nx)
+        cfg.x_offset = int(x_offset)
+        cfg.west_edge = _EDGE[west_edge or default_edge]
+        cfg.east_edge = _EDGE[east_edge or default_edge]
+        cfg.omega, cfg.inlet_rho, cfg.outlet_rho = float(omega), float(inlet_rho), float(outlet_rho)
+        cfg.cs2, cfg.cs22, cfg.two_cs4 = float(cs2), float(cs22), float(two_cs4)
+        cfg.stream = ct.c_void_p(stream) if stream else None
+        self.cfg = cfg
+        self.omega, self.inlet_rho, self.outlet_rho = cfg.omega, cfg.inlet_rho, cfg.outlet_rho
+        self.device = cfg.device
+        h = ct.c_void_p()
+        N.check(N.lib().lb_create(ct.byref(cfg), ct.byref(h)))
+        self._h = h
+        if mask is not None:
+            self.set_mask(mask)
+        if f0 is not None:
+            self.upload_f(f0)
+
+    from_lattice = classmethod(lambda cls, *a, **k: cls(*a, **k))
+
+    # -- lifetime ---------------------------------------------------------------------
+    def close(self):
+        if self._h is not None:
+            N.lib().lb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _call(self, fn, *args):
+        if self._h is None:
+            raise N.LBError(-3, "lattice is closed")
+        N.check(getattr(N.lib(), fn)(self._h, *args), self._h)
+
+    # -- uploads ----------------------------------------------------------------------
+    def set_mask(self, mask):
+        """mask: (ny, nx); entries equal to 1 are solid (D2Q9.cl:410).  None removes it."""
+        if mask is None:
+            self._call("lb_set_mask", None, 1)
+            return
+        m = np.asarray(mask)
+        if m.shape != (self.ny, self.nx):
+            raise ValueError(f"mask must have shape (ny, nx) = {(self.ny, self.nx)}, got {m.shape}")
+        m = np.ascontiguousarray(m, dtype=np.uint8)
+        self._call("lb_set_mask", _ptr(m), 1)
+
+    def upload_f(self, f):
+        """f: (9, ny, nx) populations; seeds both ping-pong buffers (opencl_dim.py:324-327)."""
+        a = np.ascontiguousarray(f, dtype=self.dtype)
+        if a.shape != (9, self.ny, self.nx):
+            raise ValueError(f"f must have shape (9, ny, nx) = {(9, self.ny, self.nx)}, got {a.shape}")
+        self._call("lb_upload_f", _ptr(a))
+
+    def upload_moments(self, rho=None, u=None, v=None):
+        arrs = []
+        for a in (rho, u, v):
+            if a is None:
+                arrs.append(None)
+                continue
+            b = np.ascontiguousarray(a, dtype=self.dtype)
+            if b.shape != (self.ny, self.nx):
+                raise ValueError("moment fields must have shape (ny, nx)")
+            arrs.append(b)
+        self._call("lb_upload_moments", *[(_ptr(a) if a is not None else None) for a in arrs])
+
+    # -- the hot path -----------------------------------------------------------------
+    def run(self, n, sync=True):
+        """n fused collide-and-stream steps (opencl_dim.Pipe_Flow.run); one sync at the end."""
+        self._call("lb_step", int(n))
+        if sync:
+            self.sync()
+
+    def sync(self):
+        self._call("lb_sync")
+
+    # -- readback ---------------------------------------------------------------------
+    def download(self, field, out=None):
+        """Device layout array of `field` in {'f','feq','rho','u','v'}."""
+        shape = (9, self.ny, self.nx) if field in ("f", "feq") else (self.ny, self.nx)
+        if out is None:
+            out = np.empty(shape, dtype=self.dtype)
+        else:
+            if out.shape != shape or out.dtype != self.dtype or not out.flags.c_contiguous:
+                raise ValueError("out must be a C-contiguous array of the field's shape and dtype")
+        self._call("lb_download", _FIELD[field], _ptr(out))
+        return out
+
+    def fields(self):
+        return {k: self.download(k) for k in ("f", "feq", "rho", "u", "v")}
+
+    # -- single stages (D2Q9.cl kernel by kernel) --------------------------------------
+    def move(self):
+        self._call("lb_stage_move")
+
+    def move_bcs(self):
+        self._call("lb_stage_move_bcs")
+
+    def update_hydro(self):
+        self._call("lb_stage_update_hydro")
+
+    def update_feq(self):
+        self._call("lb_stage_update_feq")
+
+    def collide_particles(self):
+        self._call("lb_stage_collide")
+
+    def zero_velocity_in_obstacle(self):
+        self._call("lb_stage_zero_velocity")
+
+    # -- synthetic initialisers / diagnostics -------------------------------------------
+    def init_synthetic(self, kind="pipe_ramp", u0=0.0, amplitude=0.0, seed=0):
+        k = {"pipe_ramp": N.SYNTH_PIPE_RAMP, "shear_layers": N.SYNTH_SHEAR_LAYERS}[kind]
+        self._call("lb_init_synthetic", k, float(u0), float(amplitude), ct.c_uint64(int(seed)))
+
+    def set_mask_disk(self, cx, cy, r):
+        self._call("lb_set_mask_disk", float(cx), float(cy), float(r))
+
+    def total_mass(self):
+        out = ct.c_double()
+        self._call("lb_total_mass", ct.byref(out))
+        return out.value
+
+    @property
+    def launch_count(self):
+        return int(N.lib().lb_launch_count(self._h))
+
+    def set_variant(self, variant):
+        """variant: index or name from `native.variants()`; -1 restores the default."""
+        if isinstance(variant, str):
+            variant = N.variants().index(variant)
+        self._call("lb_set_variant", int(variant))
+
+    @property
+    def stream_ptr(self):
+        """cudaStream_t (as int) this lattice enqueues on."""
+        return N.lib().lb_stream(self._h)
+
+    def device_ptr(self, field):
+        p, pitch = ct.c_void_p(), ct.c_int64()
+        self._call("lb_device_ptr", _FIELD[field], ct.byref(p), ct.byref(pitch))
+        return p.value, pitch.value
+
+    # -- halo ---------------------------------------------------------------------------
+    def halo_ipc_handle(self):
+        buf = ct.create_string_buffer(N.IPC_HANDLE_BYTES)
+        self._call("lb_halo_ipc_handle", buf)
+        return buf.raw
+
+    def halo_connect_ipc(self, side, handle_bytes, peer_device=0):
+        buf = ct.create_string_buffer(handle_bytes, N.IPC_HANDLE_BYTES)
+        self._call("lb_halo_connect_ipc", {"west": N.WEST, "east": N.EAST}[side], buf, int(peer_device))
+
+    def halo_connect_local(self, side, peer):
+        self._call("lb_halo_connect_local", {"west": N.WEST, "east": N.EAST}[side], peer._h)
+
+    def halo_prime(self):
+        self._call("lb_halo_prime")
+
+
+def split_slabs(global_nx, parts):
+    """Column ranges [(x_offset, nx), ...] of an x-slab decomposition into `parts` slabs.
+
+    Remainder columns go to the first slabs, so widths differ by at most one.
+    """
+    base, rem = divmod(int(global_nx), int(parts))
+    if base < 2:
+        raise ValueError("each slab needs at least 2 columns")
+    out, x = [], 0
+    for r in range(parts):
+        w = base + (1 if r < rem else 0)
+        out.append((x, w))
+        x += w
+    return out
+
+
+def slab_edges(rank, parts, bc):
+    """(west_edge, east_edge) names of slab `rank` of `parts` for boundary family `bc`."""
+    if parts == 1:
+        e = "wrap" if bc == "periodic" else "boundary"
+        return e, e
+    if bc == "periodic":
+        return "halo", "halo"
+    return ("boundary" if rank == 0 else "halo"), ("boundary" if rank == parts - 1 else "halo")
+
+
+class LocalSlabs:
+    """`parts` x-slabs of one lattice living in ONE process (virtual ranks).
+
+    Slabs on the same device share one stream and advance in lock-step, one step at a time, so the flag
+    hand-shake of the fused kernel is always already satisfied when a kernel starts.  Used to
+    prove that the decomposition is arithmetic-neutral (bit-identical to a single slab) and as
+    the single-process multi-device path when `devices` lists several GPUs.
+    """
+
+    def __init__(self, global_nx, ny, parts, devices=None, **kw):
+        self.global_nx, self.ny, self.parts = int(global_nx), int(ny), int(parts)
+        self.bc = kw.get("bc", "pipe")
+        self.ranges = split_slabs(global_nx, parts)
+        devices = devices or [kw.pop("device", 0)] * parts
+        kw.pop("device", None)
+        self.slabs = []
+        streams = {}          # one stream per device, shared by the slabs that live there
+        for r, (x0, w) in enumerate(self.ranges):
+            we, ee = slab_edges(r, parts, self.bc)
+            s = Lattice(w, ny, global_nx=global_nx, x_offset=x0, west_edge=we, east_edge=ee,
+                        device=devices[r], stream=streams.get(devices[r]), **kw)
+            streams.setdefault(devices[r], s.stream_ptr)
+            self.slabs.append(s)
+        if parts > 1:
+            for r, s in enumerate(self.slabs):
+                if s.cfg.west_edge == N.EDGE_HALO:
+                    s.halo_connect_local("west", self.slabs[(r - 1) % parts])
+                if s.cfg.east_edge == N.EDGE_HALO:
+                    s.halo_connect_local("east", self.slabs[(r + 1) % parts])
+
+    def close(self):
+        for s in self.slabs:
+            s.close()
+
+    def set_mask(self, mask):
+        for s, (x0, w) in zip(self.slabs, self.ranges):
+            s.set_mask(np.ascontiguousarray(mask[:, x0:x0 + w]))
+
+    def upload_f(self, f):
+        for s, (x0, w) in zip(self.slabs, self.ranges):
+            s.upload_f(np.ascontiguousarray(f[:, :, x0:x0 + w]))
+        self.prime()
+
+    def prime(self):
+        for s in self.slabs:
+            s.sync()
+        for s in self.slabs:
+            s.halo_prime()
+
+    def run(self, n):
+        for _ in range(int(n)):
+            for s in self.slabs:
+                s.run(1, sync=False)
+        for s in self.slabs:
+            s.sync()
+
+    def download(self, field):
+        return np.concatenate([s.download(field) for s in self.slabs], axis=-1)
+
+    def total_mass(self):
+        return sum(s.total_mass() for s in self.slabs)

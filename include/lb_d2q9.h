@@ -1,0 +1,189 @@
+/*
+ * lb_d2q9.h -- C ABI of the B200-native D2Q9 collide-and-stream engine.
+ *
+ * This is the drop-in boundary.  The reference
+ * (latticeboltzmann/2d-lb) has no FFI of its own: its seam is the pyopencl
+ * layer underneath LB_D2Q9/dimensionless/opencl_dim.py.  Each entry point
+ * below names the reference call site(s) it replaces (paths relative to the
+ * reference root).  Plain pointers and sizes only; no torch / numpy types.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative lb_status otherwise, and
+ *     never throws; lb_last_error() gives the message.
+ *   - one host thread per handle; the handle owns its device memory, stream,
+ *     CUDA graphs and peer mappings.
+ *   - host arrays use the reference's device layout: f[9][ny][nx], x fastest,
+ *     no padding (D2Q9.cl:24-25; == the bytes of opencl_dim's Fortran-order
+ *     (nx,ny,9) host arrays, opencl_dim.py:165).  Element type = the handle's
+ *     dtype (float for LB_F32, double for LB_F64).
+ *   - there is NO CPU fallback: without a CUDA device lb_create fails.
+ */
+#ifndef LB_D2Q9_H
+#define LB_D2Q9_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LB_ABI_VERSION 1
+
+typedef struct lb_sim lb_sim; /* opaque */
+
+enum lb_status {
+    LB_OK = 0,
+    LB_ERR_INVALID = -1,   /* bad argument / configuration */
+    LB_ERR_CUDA = -2,      /* a CUDA runtime call failed */
+    LB_ERR_STATE = -3,     /* call not valid in the handle's current state */
+    LB_ERR_HALO = -4       /* halo hand-shake with a neighbour slab timed out */
+};
+
+enum lb_dtype { LB_F32 = 0, LB_F64 = 1 };
+
+/* Boundary family.
+ *   LB_BC_PIPE      pressure (Zou-He) inlet x=0 / outlet x=nx-1, walls y=0 / y=ny-1,
+ *                   four corner closures -- D2Q9.cl:173-261 (`move_bcs`).
+ *   LB_BC_PERIODIC  doubly periodic box -- rocket_yeast.cl:152-191 /
+ *                   multi.cl:330-369 (`move_periodic`). */
+enum lb_bc { LB_BC_PIPE = 0, LB_BC_PERIODIC = 1 };
+
+/* Arithmetic contract of the fused kernel.
+ *   LB_MATH_STRICT  mirrors D2Q9.cl operation by operation (association order,
+ *                   IEEE division, no FMA contraction): bit-identical to the
+ *                   CPU oracle.
+ *   LB_MATH_FAST    same formulas with reciprocal constants and FMA; agrees
+ *                   with STRICT to rounding (tolerances in tests/). */
+enum lb_math { LB_MATH_STRICT = 0, LB_MATH_FAST = 1 };
+
+enum lb_field {
+    LB_FIELD_F = 0,    /* [9][ny][nx] post-collision populations (opencl_dim.py:394-395) */
+    LB_FIELD_FEQ = 1,  /* [9][ny][nx] equilibrium of the last moments (opencl_dim.py:397-398) */
+    LB_FIELD_RHO = 2,  /* [ny][nx] */
+    LB_FIELD_U = 3,    /* [ny][nx] */
+    LB_FIELD_V = 4     /* [ny][nx] */
+};
+
+enum lb_side { LB_WEST = 0, LB_EAST = 1 };
+
+/* What lies beyond the slab's first / last column. */
+enum lb_edge {
+    LB_EDGE_BOUNDARY = 0, /* the domain boundary (inlet / outlet for LB_BC_PIPE)      */
+    LB_EDGE_WRAP = 1,     /* periodic wrap inside this slab (single-slab periodic box) */
+    LB_EDGE_HALO = 2      /* a neighbour slab: ghost column filled through lb_halo_*    */
+};
+
+typedef struct lb_config {
+    int32_t struct_size;   /* = sizeof(lb_config), ABI guard */
+    int32_t device;        /* CUDA device ordinal */
+    int32_t nx, ny;        /* extent of THIS slab */
+    int32_t dtype;         /* lb_dtype */
+    int32_t bc;            /* lb_bc */
+    int32_t math;          /* lb_math */
+    int32_t zero_obstacle_velocity; /* 1: u=v=0 on solid nodes after every moment update
+                                       (opencl_dim_D2Q9i.py / cython_dim.pyx:459-466); 0: shipped
+                                       opencl_dim behaviour (moments of solid nodes kept) */
+    /* x-slab decomposition (single slab: global_nx = nx, x_offset = 0, edges per bc) */
+    int32_t global_nx;     /* columns of the whole lattice */
+    int32_t x_offset;      /* global x of local column 0 */
+    int32_t west_edge;     /* lb_edge */
+    int32_t east_edge;     /* lb_edge */
+    /* physics: opencl_dim.py:118 (omega), :273-274 (inlet/outlet rho), :26-30 (lattice constants,
+       passed in so that they are the very doubles the host computed) */
+    double omega, inlet_rho, outlet_rho;
+    double cs2, cs22, two_cs4;
+    void *stream;          /* cudaStream_t to enqueue on; NULL = the handle creates its own */
+} lb_config;
+
+/* -- lifetime: replaces cl.Context/CommandQueue/Program.build and the cl.Buffer
+ *    allocations of opencl_dim.py:203-255,165-176 ------------------------------ */
+int lb_abi_version(void);
+int lb_device_count(void);
+int lb_create(const lb_config *cfg, lb_sim **out);
+int lb_destroy(lb_sim *sim);
+/* message of the last failure on this handle (or of the last failed lb_create when sim == NULL) */
+const char *lb_last_error(const lb_sim *sim);
+
+/* -- uploads ------------------------------------------------------------------
+ * lb_set_mask: cl.Buffer(..., hostbuf=obstacle_mask_host), opencl_dim.py:502-503.
+ *   host_mask[ny][nx], elem_bytes 1 (uint8) or 4 (int32); value 1 = solid
+ *   (D2Q9.cl:410 tests `== 1`).  NULL removes the mask.
+ * lb_upload_f: init_pop's two cl.Buffer(COPY_HOST_PTR) of f and f_streamed, opencl_dim.py:324-327.
+ * lb_upload_moments: init_hydro's rho/u/v buffers, opencl_dim.py:291-293.  Any pointer may be NULL. */
+int lb_set_mask(lb_sim *sim, const void *host_mask, int elem_bytes);
+int lb_upload_f(lb_sim *sim, const void *host_f);
+int lb_upload_moments(lb_sim *sim, const void *host_rho, const void *host_u, const void *host_v);
+
+/* -- the hot path: Pipe_Flow.run, opencl_dim.py:372-387 (+ :510-518 with a mask).
+ *    Enqueues n_steps fused stream+BC+bounce-back+moments+feq+collide launches
+ *    (CUDA-graph batched); no host synchronisation inside.  After the call
+ *    completes, rho/u/v hold the moments of the last step (pre-collision), f is
+ *    post-collision -- the reference's get_fields semantics. */
+int lb_step(lb_sim *sim, int n_steps);
+int lb_sync(lb_sim *sim);
+
+/* -- readback: cl.enqueue_copy(queue, host, dev, is_blocking=True), opencl_dim.py:394-407.
+ *    Blocking.  host_out has the layout stated at the top of this file. */
+int lb_download(lb_sim *sim, int field, void *host_out);
+
+/* -- single stages, for the kernel-by-kernel checks the reference's notebooks do
+ *    (testing/Bryan/opencl_check_03.ipynb).  Each is one non-fused launch operating on the
+ *    handle's current f / rho,u,v / feq and is equivalent to the reference kernel named:
+ *    move            = D2Q9.cl `move` + `copy_buffer`        (opencl_dim.py:339-353)
+ *    move_bcs        = `move_bcs` (+ `bounceback_in_obstacle`) (:329-337, :510-518)
+ *    update_hydro    = `update_hydro`                          (:355-362)
+ *    update_feq      = `update_feq`                            (:295-306)
+ *    collide         = `collide_particles`                     (:364-370)
+ *    zero_velocity   = `set_zero_velocity_in_obstacle`         (:506-508) */
+int lb_stage_move(lb_sim *sim);
+int lb_stage_move_bcs(lb_sim *sim);
+int lb_stage_update_hydro(lb_sim *sim);
+int lb_stage_update_feq(lb_sim *sim);
+int lb_stage_collide(lb_sim *sim);
+int lb_stage_zero_velocity(lb_sim *sim);
+/* -- device-side initialisers for grids too large for host init (synthetic benchmark inputs) */
+enum lb_synth { LB_SYNTH_PIPE_RAMP = 0, LB_SYNTH_SHEAR_LAYERS = 1 };
+/* rho/u/v from an analytic profile in GLOBAL coordinates, f = feq*(1+amplitude*N(0,1)) with a
+ * counter-based generator keyed on (seed, global cell, population): slab-decomposition invariant.
+ *   PIPE_RAMP:    rho = inlet - gx*(inlet-outlet)/global_nx, u=v=0          (opencl_dim.py:279-288)
+ *   SHEAR_LAYERS: rho=1, u=U0*tanh(80(y/ny-1/4)) | U0*tanh(80(3/4-y/ny)), v=0.05*U0*sin(2pi(gx/gnx+1/4)) */
+int lb_init_synthetic(lb_sim *sim, int kind, double u0, double amplitude, uint64_t seed);
+/* solid disk in GLOBAL coordinates (centre cx,cy, radius r): mask = (gx-cx)^2+(y-cy)^2 < r^2 */
+int lb_set_mask_disk(lb_sim *sim, double cx, double cy, double r);
+
+/* -- diagnostics */
+/* sum over all populations and cells of this slab, accumulated in double (mass check) */
+int lb_total_mass(lb_sim *sim, double *out);
+/* number of fused-kernel launches issued by this handle since creation */
+int64_t lb_launch_count(const lb_sim *sim);
+/* choose one of the compiled tile configurations of the fused kernel (-1 = default);
+ * lb_variant_count/lb_variant_name enumerate them.  Tuning only: results do not change. */
+int lb_set_variant(lb_sim *sim, int variant);
+int lb_variant_count(void);
+const char *lb_variant_name(int variant);
+/* device pointers, for zero-copy consumers (torch tensors as buffers) */
+int lb_device_ptr(lb_sim *sim, int field, void **ptr, int64_t *pitch_elems);
+/* the cudaStream_t this handle enqueues on (so that several handles can share one stream) */
+void *lb_stream(lb_sim *sim);
+
+/* -- x-slab halo exchange over NVLink peer memory (new design; the reference is single-device).
+ *    Each slab owns a halo arena: two ghost columns x two parities x the 3 incoming
+ *    populations, plus step flags.  A slab's boundary threads store their outgoing
+ *    populations (1,5,8 eastward; 3,6,7 westward) straight into the NEIGHBOUR's arena
+ *    inside the fused kernel and then publish a step flag there; the neighbour's
+ *    boundary tiles poll their local flag before reading the ghost column. */
+#define LB_IPC_HANDLE_BYTES 64
+int lb_halo_ipc_handle(lb_sim *sim, void *out_handle /* LB_IPC_HANDLE_BYTES */);
+/* connect `side` to a neighbour slab living in another process (CUDA IPC) ... */
+int lb_halo_connect_ipc(lb_sim *sim, int side, const void *peer_handle, int peer_device);
+/* ... or in this process (virtual ranks on one device / several devices of one process) */
+int lb_halo_connect_local(lb_sim *sim, int side, lb_sim *peer);
+/* push the current state's boundary columns to the neighbours (call on every slab after
+ * uploads / initialisers and before the first lb_step; callers barrier in between) */
+int lb_halo_prime(lb_sim *sim);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LB_D2Q9_H */

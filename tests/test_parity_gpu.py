@@ -1,0 +1,259 @@
+"""Parity of the CUDA path (through the C-ABI) against the CPU oracle.  `-m gpu`.
+
+STRICT math: bit-exact for fp32 and fp64, any step count, any grid shape.
+FAST math:   tolerance stated per test (max relative error in rho and u, north_star).
+"""
+import numpy as np
+import pytest
+
+from util import periodic_case, pipe_case, rel_err
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = [(97, 41), (256, 128), (130, 67), (5, 4), (33, 3), (128, 9), (129, 9), (127, 9), (2, 2)]
+
+
+def _run_both(orc, Lattice, f0, mask, steps, dtype, math, bc="pipe", omega=1.3, rin=1.01, rout=1.0,
+              zero_vel=False, variant=None):
+    _, ny, nx = f0.shape
+    ref = orc.OpenCLSchemeOracle(f0, omega, rin, rout, mask=mask, bc=orc.BC_PERIODIC if bc == "periodic" else orc.BC_PIPE,
+                                 dtype=dtype, zero_obstacle_velocity=zero_vel)
+    ref.run(steps)
+    with Lattice(nx, ny, omega, rin, rout, mask=mask, f0=f0, bc=bc, dtype=dtype, math=math,
+                 zero_obstacle_velocity=zero_vel) as sim:
+        if variant is not None:
+            sim.set_variant(variant)
+        sim.run(steps)
+        got = sim.fields()
+    return ref, got
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("shape", SHAPES)
+def test_strict_pipe_bitexact(gpu, orc, shape, dtype):
+    from lb_b200 import Lattice
+    nx, ny = shape
+    f0, mask = pipe_case(orc, nx, ny, dtype, mask="blocks" if min(nx, ny) >= 9 else "none")
+    for steps in (1, 10):
+        ref, got = _run_both(orc, Lattice, f0, mask, steps, dtype, "strict")
+        for k in ("f", "rho", "u", "v", "feq"):
+            assert np.array_equal(got[k], getattr(ref, k)), f"{k} differs after {steps} steps on {shape}"
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("mask", ["random", "touching"])
+@pytest.mark.parametrize("zero_vel", [False, True])
+def test_strict_obstacles_bitexact(gpu, orc, dtype, mask, zero_vel):
+    from lb_b200 import Lattice
+    f0, m = pipe_case(orc, 201, 77, dtype, mask=mask, seed=3)
+    ref, got = _run_both(orc, Lattice, f0, m, 100, dtype, "strict", zero_vel=zero_vel, omega=1.1)
+    for k in ("f", "rho", "u", "v"):
+        assert np.array_equal(got[k], getattr(ref, k)), k
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("shape", [(96, 40), (130, 67), (7, 5), (128, 128)])
+def test_strict_periodic_bitexact_and_mass(gpu, orc, shape, dtype):
+    from lb_b200 import Lattice
+    nx, ny = shape
+    f0 = periodic_case(orc, nx, ny, dtype, amplitude=1e-3)
+    ref, got = _run_both(orc, Lattice, f0, None, 50, dtype, "strict", bc="periodic", omega=1.7)
+    for k in ("f", "rho", "u", "v"):
+        assert np.array_equal(got[k], getattr(ref, k)), k
+    m0, m1 = f0.astype(np.float64).sum(), got["f"].astype(np.float64).sum()
+    assert abs(m1 - m0) / m0 < (1e-6 if dtype == np.float32 else 1e-13)
+
+
+def test_c1_fp64_2000_steps(gpu, orc):
+    """BASELINE config 1: 256x128 fp64, 2000 steps.  Gate: max relative error in rho and u
+    <= 1e-12 for FAST math (STRICT is bit-exact)."""
+    from lb_b200 import Lattice
+    f0, _ = pipe_case(orc, 256, 128, np.float64, inlet_rho=1.00495022, seed=0)
+    omega = 1.000265
+    ref = orc.OpenCLSchemeOracle(f0, omega, 1.00495022, 1.0, dtype=np.float64)
+    ref.run(2000)
+    with Lattice(256, 128, omega, 1.00495022, 1.0, f0=f0, dtype=np.float64, math="strict") as sim:
+        sim.run(2000)
+        assert np.array_equal(sim.download("f"), ref.f)
+    with Lattice(256, 128, omega, 1.00495022, 1.0, f0=f0, dtype=np.float64, math="fast") as sim:
+        sim.run(2000)
+        rho, u, v = sim.download("rho"), sim.download("u"), sim.download("v")
+    assert rel_err(rho, ref.rho) <= 1e-12
+    assert rel_err(u, ref.u) <= 1e-12
+    assert np.abs(v - ref.v).max() <= 1e-12 * np.abs(ref.u).max()
+
+
+@pytest.mark.parametrize("steps", [1, 10, 100])
+def test_fast_fp32_tolerance(gpu, orc, steps):
+    """FAST fp32 vs the fp32 oracle, 256x128 pipe with obstacles: rho within 1e-5 relative and
+    u within 1e-5 of max(|u|, 1e-2) after <= 100 steps (u itself is O(1e-2))."""
+    from lb_b200 import Lattice
+    f0, m = pipe_case(orc, 256, 128, np.float32, mask="blocks")
+    ref, got = _run_both(orc, Lattice, f0, m, steps, np.float32, "fast")
+    assert rel_err(got["rho"], ref.rho) <= 1e-5
+    scale = max(np.abs(ref.u).max(), 1e-2)
+    assert np.abs(got["u"] - ref.u).max() <= 1e-5 * scale
+    assert np.abs(got["v"] - ref.v).max() <= 1e-5 * scale
+    assert np.abs(got["f"] - ref.f).max() <= 2e-6
+
+
+def test_all_variants_identical(gpu, orc):
+    """Tile shape / vector width / cache hints must not change a single bit."""
+    from lb_b200 import Lattice, native
+    for dtype, tn in ((np.float32, "f32"), (np.float64, "f64")):
+        f0, m = pipe_case(orc, 300, 70, dtype, mask="touching", seed=5)
+        base = {}
+        for name in native.variants():
+            if not name.startswith(tn + "."):
+                continue
+            math = name.split(".")[1]
+            with Lattice(300, 70, 1.2, 1.01, 1.0, mask=m, f0=f0, dtype=dtype, math=math) as sim:
+                sim.set_variant(name)
+                sim.run(7)
+                f = sim.download("f")
+            if math not in base:
+                base[math] = (name, f)
+            else:
+                assert np.array_equal(f, base[math][1]), f"{name} differs from {base[math][0]}"
+
+
+def test_stages_equal_fused_and_oracle(gpu, orc):
+    """The single-stage entry points (one D2Q9.cl kernel each) reproduce the oracle stage by stage,
+    and a stage sequence equals one fused step."""
+    from lb_b200 import Lattice
+    f0, m = pipe_case(orc, 97, 41, np.float32, mask="blocks")
+    ref = orc.OpenCLSchemeOracle(f0, 1.3, 1.01, 1.0, mask=m)
+    with Lattice(97, 41, 1.3, 1.01, 1.0, mask=m, f0=f0, math="strict") as sim, \
+            Lattice(97, 41, 1.3, 1.01, 1.0, mask=m, f0=f0, math="strict") as fused:
+        for _ in range(3):
+            for stage in ("move", "move_bcs", "update_hydro", "update_feq", "collide_particles"):
+                getattr(ref, stage)()
+                getattr(sim, stage)()
+                assert np.array_equal(sim.download("f"), ref.f), stage
+            assert np.array_equal(sim.download("rho"), ref.rho)
+            assert np.array_equal(sim.download("feq"), ref.feq)
+            fused.run(1)
+            assert np.array_equal(fused.download("f"), ref.f)
+            assert np.array_equal(fused.download("u"), ref.u)
+
+
+@pytest.mark.parametrize("bc", ["pipe", "periodic"])
+@pytest.mark.parametrize("parts", [2, 3, 5])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_slab_decomposition_is_arithmetic_neutral(gpu, orc, bc, parts, dtype):
+    """x-slabs with peer-memory halos (virtual ranks on one GPU) == single slab, bit for bit."""
+    from lb_b200 import Lattice
+    from lb_b200.lattice import LocalSlabs
+    nx, ny = 203, 45
+    if bc == "pipe":
+        f0, m = pipe_case(orc, nx, ny, dtype, mask="touching", seed=7)
+    else:
+        f0, m = periodic_case(orc, nx, ny, dtype, amplitude=1e-3), None
+    with Lattice(nx, ny, 1.4, 1.01, 1.0, mask=m, f0=f0, bc=bc, dtype=dtype, math="fast") as one:
+        one.run(25)
+        want = one.fields()
+    slabs = LocalSlabs(nx, ny, parts, omega=1.4, inlet_rho=1.01, outlet_rho=1.0, bc=bc, dtype=dtype, math="fast")
+    try:
+        if m is not None:
+            slabs.set_mask(m)
+        slabs.upload_f(f0)
+        slabs.run(25)
+        for k in ("f", "rho", "u", "v"):
+            assert np.array_equal(slabs.download(k), want[k]), k
+    finally:
+        slabs.close()
+
+
+def test_self_ring_halo_equals_wrap(gpu, orc):
+    """A periodic slab whose halo edges are connected to itself must equal in-kernel wrap."""
+    from lb_b200 import Lattice
+    f0 = periodic_case(orc, 150, 33, np.float32, amplitude=1e-3)
+    with Lattice(150, 33, 1.6, bc="periodic", f0=f0) as a:
+        a.run(12)
+        want = a.download("f")
+    with Lattice(150, 33, 1.6, bc="periodic", west_edge="halo", east_edge="halo") as b:
+        b.halo_connect_local("west", b)
+        b.halo_connect_local("east", b)
+        b.upload_f(f0)
+        b.halo_prime()
+        for _ in range(12):
+            b.run(1)
+        assert np.array_equal(b.download("f"), want)
+
+
+def test_poiseuille_known_answer(gpu, orc):
+    """docs/opencl_dimensionless_verification.ipynb: D=1.5, rho=10, nu=5, grad p=-100, L=2D, N=10,
+    999 steps (dimensionless time 10).  Constructor printouts and the analytic profile
+    u(y) = (1/(2 rho nu)) grad_p y (y - D)."""
+    import lb_b200.dimensionless as lb
+    np.random.seed(0)
+    sim = lb.Pipe_Flow(diameter=1.5, rho=10., viscosity=5., pressure_grad=-100., pipe_length=3., N=10,
+                       time_prefactor=1., verbose=False)
+    assert abs(sim.omega - 0.324465802203) < 1e-11
+    assert abs(sim.inlet_rho - 1.063) < 1e-12
+    assert (sim.nx, sim.ny) == (21, 11)
+    steps = int(10. / sim.delta_t)
+    f_init = sim.get_fields()["f"]
+    sim.run(steps)
+    fields = sim.get_physical_fields()
+    u_mean = fields["u"].mean(axis=0)
+    y = np.linspace(0, 1.5, sim.ny)
+    theory = (1. / (2 * 10. * 5.)) * (-100.) * y * (y - 1.5)
+    rms = np.sqrt(np.mean((u_mean - theory) ** 2))
+    assert abs(u_mean.max() - 0.5625) < 0.02          # N=10 overshoots slightly
+    assert rms < 0.01
+    # and the same run on the oracle, from the same initial populations
+    ref = orc.OpenCLSchemeOracle(np.ascontiguousarray(f_init.T), sim.omega, sim.inlet_rho, sim.outlet_rho)
+    ref.run(steps)
+    got = sim.get_fields()
+    assert np.abs(got["rho"].T - ref.rho).max() <= 1e-5
+    assert np.abs(got["u"].T - ref.u).max() <= 1e-5 * max(np.abs(ref.u).max(), 1e-2)
+
+
+def test_dimensionless_classes_match_oracle(gpu, orc):
+    """Pipe_Flow_Cylinder / Pipe_Flow_Obstacles through the drop-in API, STRICT math, bit-exact."""
+    import lb_b200.dimensionless as lb
+    np.random.seed(4)
+    sim = lb.Pipe_Flow_Cylinder(cylinder_center=[0.75, 0.5], cylinder_radius=0.1, diameter=1., rho=1., viscosity=1.,
+                                pressure_grad=-10., pipe_length=3., N=4, math="strict", verbose=False)
+    assert (sim.nx, sim.ny) == (121, 41)
+    f0 = sim.get_fields()["f"]
+    ref = orc.OpenCLSchemeOracle(np.ascontiguousarray(f0.T), sim.omega, sim.inlet_rho, sim.outlet_rho,
+                                 mask=np.ascontiguousarray(sim.obstacle_mask_host.T))
+    sim.run(40)
+    ref.run(40)
+    got = sim.get_fields()
+    assert got["f"].flags.f_contiguous and got["f"].shape == (121, 41, 9) and got["f"].dtype == np.float32
+    for k in ("f", "feq", "rho", "u", "v"):
+        assert np.array_equal(np.ascontiguousarray(got[k].T), getattr(ref, k)), k
+
+    mask = np.zeros((sim.nx, sim.ny), dtype=bool)
+    mask[30:40, 10:20] = True
+    np.random.seed(5)
+    obs = lb.Pipe_Flow_Obstacles(obstacle_mask=mask, diameter=1., rho=1., viscosity=1., pressure_grad=-10.,
+                                 pipe_length=3., N=40, time_prefactor=4., math="strict", verbose=False)
+    f0 = obs.get_fields()["f"]
+    ref = orc.OpenCLSchemeOracle(np.ascontiguousarray(f0.T), obs.omega, obs.inlet_rho, obs.outlet_rho,
+                                 mask=np.ascontiguousarray(mask.T), zero_obstacle_velocity=True)
+    obs.run(25)
+    ref.run(25)
+    got = obs.get_fields()
+    for k in ("f", "rho", "u", "v"):
+        assert np.array_equal(np.ascontiguousarray(got[k].T), getattr(ref, k)), k
+    assert (got["u"][mask] == 0).all()
+
+
+def test_c2_obstacles_4096x1024(gpu, orc):
+    """BASELINE config 2 shape (4096x1024 fp32 with an obstacle mask): 3 steps bit-exact in STRICT,
+    FAST within tolerance."""
+    from lb_b200 import Lattice
+    f0, m = pipe_case(orc, 4096, 1024, np.float32, mask="random", seed=11)
+    ref = orc.OpenCLSchemeOracle(f0, 1.0, 1.01, 1.0, mask=m, zero_obstacle_velocity=True)
+    ref.run(3)
+    with Lattice(4096, 1024, 1.0, 1.01, 1.0, mask=m, f0=f0, math="strict", zero_obstacle_velocity=True) as sim:
+        sim.run(3)
+        assert np.array_equal(sim.download("f"), ref.f)
+    with Lattice(4096, 1024, 1.0, 1.01, 1.0, mask=m, f0=f0, math="fast", zero_obstacle_velocity=True) as sim:
+        sim.run(3)
+        assert np.abs(sim.download("f") - ref.f).max() <= 1e-6
+        assert rel_err(sim.download("rho"), ref.rho) <= 1e-5
