@@ -649,7 +649,30 @@ static int compute_feq(lb_sim *sim)
 }
 
 // ---- the hot path ---------------------------------------------------------------------
-static const int GRAPH_MAX = 64;    // steps per captured graph
+static const int GRAPH_LEN = 32;    // steps per captured graph (even: a graph returns to its start buffer)
+
+// (re)build the graph of GRAPH_LEN moment-free steps that starts from buffer `sim->cur`
+static int ensure_graph(lb_sim *sim)
+{
+    const int gi = sim->cur;
+    if (sim->graph[gi] && sim->graph_variant[gi] == sim->variant) return LB_OK;
+    if (sim->graph[gi]) { cudaGraphExecDestroy(sim->graph[gi]); sim->graph[gi] = nullptr; }
+    cudaGraph_t g = nullptr;
+    CU(cudaStreamBeginCapture(sim->stream, cudaStreamCaptureModeThreadLocal));
+    int idx = sim->cur, rc = LB_OK;
+    const int64_t l0 = sim->launches;
+    for (int i = 0; i < GRAPH_LEN && rc == LB_OK; ++i) { rc = launch_step(sim, idx, 0, 0); idx ^= 1; }
+    sim->launches = l0;                  // captured, not executed
+    cudaError_t ce = cudaStreamEndCapture(sim->stream, &g);
+    if (rc != LB_OK) { if (g) cudaGraphDestroy(g); return rc; }
+    CU(ce);
+    ce = cudaGraphInstantiate(&sim->graph[gi], g, 0);
+    cudaGraphDestroy(g);
+    CU(ce);
+    sim->graph_len[gi] = GRAPH_LEN;
+    sim->graph_variant[gi] = sim->variant;
+    return LB_OK;
+}
 
 int lb_step(lb_sim *sim, int n_steps)
 {
@@ -665,39 +688,18 @@ int lb_step(lb_sim *sim, int n_steps)
     }
     int remaining = n_steps - 1;            // all but the last step skip the moment stores
     const bool graphs_ok = !uses_halo(sim); // halo launches carry a per-step flag value
-    while (remaining > 0) {
-        int chunk = remaining;
-        if (graphs_ok && chunk >= 4) {
-            if (chunk > GRAPH_MAX) chunk = GRAPH_MAX;
-            chunk &= ~1;                    // an even chunk returns to the same buffer
-            const int gi = sim->cur;
-            if (!sim->graph[gi] || sim->graph_len[gi] != chunk || sim->graph_variant[gi] != sim->variant) {
-                if (sim->graph[gi]) { cudaGraphExecDestroy(sim->graph[gi]); sim->graph[gi] = nullptr; }
-                cudaGraph_t g = nullptr;
-                CU(cudaStreamBeginCapture(sim->stream, cudaStreamCaptureModeThreadLocal));
-                int idx = sim->cur, rc = LB_OK;
-                const int64_t l0 = sim->launches;
-                for (int i = 0; i < chunk && rc == LB_OK; ++i) { rc = launch_step(sim, idx, 0, 0); idx ^= 1; }
-                sim->launches = l0;          // captured, not yet executed
-                cudaError_t ce = cudaStreamEndCapture(sim->stream, &g);
-                if (rc != LB_OK) { if (g) cudaGraphDestroy(g); return rc; }
-                CU(ce);
-                ce = cudaGraphInstantiate(&sim->graph[gi], g, 0);
-                cudaGraphDestroy(g);
-                CU(ce);
-                sim->graph_len[gi] = chunk; sim->graph_variant[gi] = sim->variant;
-            }
-            CU(cudaGraphLaunch(sim->graph[gi], sim->stream));
-            sim->launches += chunk;
-            sim->state_index += chunk;
-        } else {
-            for (int i = 0; i < chunk; ++i) {
-                int rc = launch_step(sim, sim->cur, 0, sim->state_index);
-                if (rc) return rc;
-                sim->cur ^= 1; sim->state_index++;
-            }
-        }
-        remaining -= chunk;
+    while (graphs_ok && remaining >= GRAPH_LEN) {
+        int rc = ensure_graph(sim);
+        if (rc) return rc;
+        CU(cudaGraphLaunch(sim->graph[sim->cur], sim->stream));
+        sim->launches += GRAPH_LEN;
+        sim->state_index += GRAPH_LEN;
+        remaining -= GRAPH_LEN;
+    }
+    for (; remaining > 0; --remaining) {
+        int rc = launch_step(sim, sim->cur, 0, sim->state_index);
+        if (rc) return rc;
+        sim->cur ^= 1; sim->state_index++;
     }
     int rc = launch_step(sim, sim->cur, 1, sim->state_index);
     if (rc) return rc;

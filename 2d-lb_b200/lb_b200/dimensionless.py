@@ -13,7 +13,11 @@ follow the reference line by line so that the same seed gives the same initial p
   Pipe_Flow_Cylinder            :441-518                 Pipe_Flow_Obstacles (template) :616-657
 
 Extensions (keyword-only, defaults reproduce the reference): dtype, math, device, verbose,
-zero_obstacle_velocity_each_step.
+zero_obstacle_velocity_each_step, and units='opencl' | 'cython'.  The reference's OpenCL and
+Cython modules map the same physical inputs to different lattice parameters:
+units='cython' selects cython_dim.pyx's algebra (T = 8 rho nu/(|grad p| L), Reynolds-number based
+omega, pressure drop scaled by the non-dimensional gradient; cython_dim.pyx:70,85-88,115-116,
+139-144,407-408) -- the one the published benchmark notebook's printouts were made with.
 """
 import numpy as np
 
@@ -42,7 +46,10 @@ class Pipe_Flow(object):
                  N=200, time_prefactor=1.,
                  two_d_local_size=(32, 32), three_d_local_size=(32, 32, 1), use_interop=False,
                  dtype=np.float32, math="fast", device=0, verbose=True,
-                 zero_obstacle_velocity_each_step=None):
+                 zero_obstacle_velocity_each_step=None, units="opencl"):
+        if units not in ("opencl", "cython"):
+            raise ValueError("units must be 'opencl' or 'cython'")
+        self._units = units
         self._verbose = verbose
         self.dtype = np.dtype(dtype)
         self._math = math
@@ -67,8 +74,12 @@ class Pipe_Flow(object):
         self._say('Characteristic L:', self.L)
         self._say('Characteristic T:', self.T)
 
-        self.W = (np.abs(self.phys_pressure_grad_div_rho) * self.L * self.T) / self.phys_visc
-        self._say('Weinstein number:', self.W)
+        if self._units == "opencl":
+            self.W = (np.abs(self.phys_pressure_grad_div_rho) * self.L * self.T) / self.phys_visc
+            self._say('Weinstein number:', self.W)
+        else:
+            self.Re = self.L ** 2 / (self.phys_visc * self.T ** 2)        # cython_dim.pyx:70
+            self._say('Reynolds number:', self.Re)
 
         self.N = N
         self.delta_x = 1. / N
@@ -76,8 +87,12 @@ class Pipe_Flow(object):
         self.ulb = self.delta_t / self.delta_x
         self._say('u_lb:', self.ulb)
 
-        self.lb_viscosity = (self.delta_t / self.delta_x ** 2) * (1. / self.W)
-        self.omega = (3 * self.lb_viscosity + 0.5) ** -1.
+        if self._units == "opencl":
+            self.lb_viscosity = (self.delta_t / self.delta_x ** 2) * (1. / self.W)
+            self.omega = (3 * self.lb_viscosity + 0.5) ** -1.
+        else:                                                             # cython_dim.pyx:85-88
+            self.lb_viscosity = (self.delta_t / self.delta_x ** 2) * (1. / self.Re)
+            self.omega = (self.lb_viscosity / cs2 + 0.5) ** -1.
         self._say('omega', self.omega)
         assert self.omega < 2.
 
@@ -115,8 +130,11 @@ class Pipe_Flow(object):
             print(*args)
 
     def set_characteristic_length_time(self):
-        """opencl_dim.py:180-189"""
+        """opencl_dim.py:180-189 (units='cython': cython_dim.pyx:115-116)"""
         self.L = self.phys_diameter
+        if self._units == "cython":
+            self.T = (8 * self.phys_rho * self.phys_visc) / (np.abs(self.phys_pressure_grad) * self.L)
+            return
         zeta = np.abs(self.phys_pressure_grad) / self.phys_rho
         self.T = np.sqrt(self.phys_diameter / zeta)
 
@@ -128,8 +146,10 @@ class Pipe_Flow(object):
         self.ny = self.ly + 1
 
     def _set_boundary_densities(self):
-        """opencl_dim.py:268-274"""
+        """opencl_dim.py:268-274 (units='cython': cython_dim.pyx:139-144)"""
         nondim_gradP = 1.
+        if self._units == "cython":
+            nondim_gradP = (self.T ** 2 / (self.phys_rho * self.L)) * self.phys_pressure_grad
         delta_rho = self.nx * (self.delta_t ** 2 / self.delta_x) * (1. / cs2) * nondim_gradP
         self.outlet_rho = 1.
         self.inlet_rho = 1. + np.abs(delta_rho)
@@ -241,8 +261,11 @@ class Pipe_Flow_Cylinder(Pipe_Flow):
         super(Pipe_Flow_Cylinder, self).__init__(**kwargs)
 
     def set_characteristic_length_time(self):
-        """opencl_dim.py:448-457"""
+        """opencl_dim.py:448-457 (units='cython': cython_dim.pyx:407-408)"""
         self.L = self.phys_cylinder_radius
+        if self._units == "cython":
+            self.T = (8 * self.phys_rho * self.phys_visc * self.L) / (np.abs(self.phys_pressure_grad) * self.phys_diameter ** 2)
+            return
         zeta = np.abs(self.phys_pressure_grad) / self.phys_rho
         self.T = np.sqrt(self.phys_cylinder_radius / zeta)
 

@@ -63,6 +63,10 @@ typedef struct {
     int nx, ny;
     double omega, inlet_rho, outlet_rho;
     double cs2, cs22, cssq;      /* cs**2, 2*cs2, 2.0/9.0  (cython_dim.pyx:20-23) */
+    int old_api;                 /* 1: LB_D2Q9/OLD/cython.pyx flavour -- no wall zeroing in update_hydro
+                                    (OLD/cython.pyx:126-149), and omega / inlet_rho are plain Python floats
+                                    there ("weak" under NEP 50), so the inlet velocity and the relaxation
+                                    are evaluated in float32 instead of float64 */
 } cy_params;
 
 #define IDX(j, x, y) ((size_t)(j) * plane + (size_t)(y) * nx + (size_t)(x))
@@ -209,22 +213,29 @@ void oracle_cy_update_hydro(const cy_params *p, const float *f, float *rho, doub
         u[c] = (double)((((((g[1] - g[3]) + g[5]) - g[6]) - g[7]) + g[8]) * inv);
         v[c] = (double)((((((g[5] + g[2]) + g[6]) - g[7]) - g[4]) - g[8]) * inv);
     }
-    for (int x = 0; x < nx; ++x) {                             /* :317-320 */
-        u[(size_t)0 * nx + x] = 0; u[(size_t)ly * nx + x] = 0;
-        v[(size_t)0 * nx + x] = 0; v[(size_t)ly * nx + x] = 0;
-    }
+    if (!p->old_api)
+        for (int x = 0; x < nx; ++x) {                         /* :317-320 */
+            u[(size_t)0 * nx + x] = 0; u[(size_t)ly * nx + x] = 0;
+            v[(size_t)0 * nx + x] = 0; v[(size_t)ly * nx + x] = 0;
+        }
     for (int y = 0; y < ny; ++y) {                             /* :325-333 */
         rho[(size_t)y * nx + 0] = (float)p->inlet_rho;
         rho[(size_t)y * nx + lx] = (float)p->outlet_rho;
         {
             const float a = (f[IDX(0, 0, y)] + f[IDX(2, 0, y)]) + f[IDX(4, 0, y)];
             const float b = 2 * ((f[IDX(3, 0, y)] + f[IDX(6, 0, y)]) + f[IDX(7, 0, y)]);
-            u[(size_t)y * nx + 0] = 1 - (double)(a + b) / p->inlet_rho;
+            /* cython_dim: inlet_rho = 1. + np.abs(...) is np.float64 -> float64 arithmetic;
+             * OLD: inlet_rho is the Python float 1. -> float32 arithmetic */
+            if (p->old_api) u[(size_t)y * nx + 0] = (double)(1.0f - (a + b) / (float)p->inlet_rho);
+            else u[(size_t)y * nx + 0] = 1 - (double)(a + b) / p->inlet_rho;
         }
         {
             const float a = (f[IDX(0, lx, y)] + f[IDX(2, lx, y)]) + f[IDX(4, lx, y)];
             const float b = 2 * ((f[IDX(1, lx, y)] + f[IDX(5, lx, y)]) + f[IDX(8, lx, y)]);
-            u[(size_t)y * nx + lx] = -1 + (double)(a + b) / p->outlet_rho;
+            /* cython_dim: outlet_rho is the Python float 1. ("weak"), so this line is float32 arithmetic;
+             * OLD: outlet_rho = deltaP/cs2 + 1 is np.float64, float64 arithmetic */
+            if (p->old_api) u[(size_t)y * nx + lx] = -1 + (double)(a + b) / p->outlet_rho;
+            else u[(size_t)y * nx + lx] = (double)(-1.0f + (a + b) / (float)p->outlet_rho);
         }
     }
     if (mask)
@@ -266,6 +277,11 @@ void oracle_cy_collide(const cy_params *p, float *f, const float *feq)
 {
     const size_t n = (size_t)9 * p->nx * p->ny;
     const double keep = 1. - p->omega, om = p->omega;
+    if (p->old_api) {
+        const float keep_f = (float)keep, om_f = (float)om;
+        for (size_t i = 0; i < n; ++i) f[i] = f[i] * keep_f + om_f * feq[i];
+        return;
+    }
     for (size_t i = 0; i < n; ++i) f[i] = (float)((double)f[i] * keep + om * (double)feq[i]);
 }
 

@@ -56,7 +56,7 @@ def _p(a):
 class CyParams(ct.Structure):
     _fields_ = [("nx", ct.c_int), ("ny", ct.c_int), ("omega", ct.c_double),
                 ("inlet_rho", ct.c_double), ("outlet_rho", ct.c_double),
-                ("cs2", ct.c_double), ("cs22", ct.c_double), ("cssq", ct.c_double)]
+                ("cs2", ct.c_double), ("cs22", ct.c_double), ("cssq", ct.c_double), ("old_api", ct.c_int)]
 
 
 def feq_of(rho, u, v, dtype):
@@ -136,10 +136,11 @@ class CythonSchemeOracle:
     """State + step of cython_dim.Pipe_Flow[_Cylinder] (cython_dim.pyx:204-359, :459-513).
 
     f: (9, ny, nx) float32; u, v: (ny, nx) float64 (the lagged velocity the
-    first move_bcs reads); mask: (ny, nx) bool or None.
+    first move_bcs reads); mask: (ny, nx) bool or None.  old_api=True selects the
+    LB_D2Q9/OLD/cython.pyx flavour (see cy_params.old_api in d2q9_oracle.c).
     """
 
-    def __init__(self, f0, u0, v0, omega, inlet_rho, outlet_rho, mask=None):
+    def __init__(self, f0, u0, v0, omega, inlet_rho, outlet_rho, mask=None, old_api=False):
         self.f = np.array(f0, dtype=np.float32, order="C", copy=True)
         _, self.ny, self.nx = self.f.shape
         self.u = np.array(u0, dtype=np.float64, order="C", copy=True)
@@ -149,7 +150,7 @@ class CythonSchemeOracle:
         self.scratch = np.zeros_like(self.f)
         self.mask = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
         self.p = CyParams(self.nx, self.ny, float(omega), float(inlet_rho), float(outlet_rho),
-                          float(cs2), float(cs22), float(cssq))
+                          float(cs2), float(cs22), float(cssq), int(bool(old_api)))
 
     def run(self, n):
         lib().oracle_cy_run(ct.byref(self.p), ct.c_int(int(n)), _p(self.f), _p(self.feq), _p(self.rho),

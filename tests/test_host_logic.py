@@ -1,0 +1,129 @@
+"""Host-side logic that needs no GPU: slab partitioning, the multi-process rendezvous under gloo
+(world_size 2), mask rasterisation, layout conventions."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_split_slabs_and_edges():
+    from lb_b200.lattice import slab_edges, split_slabs
+    assert split_slabs(32768, 8) == [(i * 4096, 4096) for i in range(8)]
+    r = split_slabs(203, 5)
+    assert sum(w for _, w in r) == 203 and r[0] == (0, 41) and r[-1] == (163, 40)
+    assert all(r[i][0] + r[i][1] == r[i + 1][0] for i in range(4))
+    with pytest.raises(ValueError):
+        split_slabs(7, 4)
+    assert slab_edges(0, 1, "pipe") == ("boundary", "boundary")
+    assert slab_edges(0, 1, "periodic") == ("wrap", "wrap")
+    assert slab_edges(0, 4, "pipe") == ("boundary", "halo")
+    assert slab_edges(2, 4, "pipe") == ("halo", "halo")
+    assert slab_edges(3, 4, "pipe") == ("halo", "boundary")
+    assert slab_edges(3, 4, "periodic") == ("halo", "halo")
+
+
+def test_fortran_host_arrays_are_device_layout():
+    """opencl_dim's (nx,ny,9) Fortran-order arrays are byte-identical to f[9][ny][nx]."""
+    nx, ny = 5, 3
+    a = np.zeros((nx, ny, 9), dtype=np.float32, order="F")
+    for j in range(9):
+        for y in range(ny):
+            for x in range(nx):
+                a[x, y, j] = j * 100 + y * 10 + x
+    dev = a.T
+    assert dev.flags.c_contiguous and dev.shape == (9, ny, nx)
+    assert np.shares_memory(dev, a)
+    assert dev[4, 2, 3] == 423
+    flat = np.frombuffer(a.tobytes(order="A"), dtype=np.float32)
+    assert flat[4 * nx * ny + 2 * nx + 3] == 423          # jump_id*nx*ny + y*nx + x  (D2Q9.cl:24-25)
+
+
+def test_circle_matches_skimage_contract():
+    from lb_b200 import draw
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "shims"))
+    from skimage.draw import circle as shim_circle          # independent statement of the contract
+    for (r, c, R) in ((30.0, 20.0, 4), (193.75, 162.5, 125), (40.5, 33.25, 10)):
+        a = draw.circle(r, c, R)
+        b = shim_circle(r, c, R)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+        m = np.zeros((int(r + R + 2), int(c + R + 2)), bool)
+        m[a[0], a[1]] = True
+        assert abs(m.sum() - np.pi * R * R) / (np.pi * R * R) < 0.12
+
+
+class _FakeLattice:
+    """Records what SlabLattice asks of the per-rank lattice."""
+
+    def __init__(self, nx, ny, omega, inlet_rho, outlet_rho, **kw):
+        self.nx, self.ny, self.kw = nx, ny, kw
+        self.connected = {}
+        self.primed = 0
+        self.f = None
+
+    def halo_ipc_handle(self):
+        return (b"H%03d" % self.kw["x_offset"]).ljust(64, b"\0")
+
+    def halo_connect_ipc(self, side, handle, device):
+        self.connected[side] = (handle.rstrip(b"\0"), device)
+
+    def halo_prime(self):
+        self.primed += 1
+
+    def sync(self):
+        pass
+
+    def upload_f(self, f):
+        self.f = f
+
+    def download(self, field):
+        return self.f
+
+    def close(self):
+        pass
+
+
+def _worker(rank, world, port, bc, out):
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.join(ROOT, "2d-lb_b200"))
+    from lb_b200.slab import SlabLattice
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        s = SlabLattice(37, 6, 1.0, bc=bc, lattice_factory=_FakeLattice, device=rank)
+        f = np.arange(9 * 6 * 37, dtype=np.float32).reshape(9, 6, 37)
+        s.upload_f(f)
+        whole = s.gather("f")
+        out.put((rank, s.x_offset, s.nx, s.west_edge, s.east_edge, dict(s.lat.connected), s.lat.primed,
+                 bool(np.array_equal(whole, f))))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("bc", ["pipe", "periodic"])
+def test_slab_rendezvous_gloo_world2(bc):
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, bc, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    r0, r1 = res
+    assert (r0[1], r0[2]) == (0, 19) and (r1[1], r1[2]) == (19, 18)
+    assert r0[7] and r1[7]                      # slab slices reassemble the global array
+    assert r0[6] == 1 and r1[6] == 1            # primed once after upload
+    if bc == "pipe":
+        assert (r0[3], r0[4]) == ("boundary", "halo") and (r1[3], r1[4]) == ("halo", "boundary")
+        assert r0[5] == {"east": (b"H019", 1)} and r1[5] == {"west": (b"H000", 0)}
+    else:
+        assert r0[5] == {"west": (b"H019", 1), "east": (b"H019", 1)}
+        assert r1[5] == {"west": (b"H000", 0), "east": (b"H000", 0)}
