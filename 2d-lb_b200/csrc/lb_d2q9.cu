@@ -99,7 +99,12 @@ static void launch_variant(const StepParams &p_in, cudaStream_t st)
     constexpr int SPAN = 32 * V;
     p.tiles_x = (p.pitch + SPAN * WX - 1) / (SPAN * WX);
     p.tiles_y = (p.ny + WY * R - 1) / (WY * R);
-    const unsigned grid = (unsigned)p.tiles_x * (unsigned)p.tiles_y;
+    dim3 grid;
+    if (p.edge_first) grid = dim3((unsigned)p.tiles_x * (unsigned)p.tiles_y, 1, 1);
+    else {
+        const unsigned gy = p.tiles_y < 65535 ? p.tiles_y : 65535;
+        grid = dim3((unsigned)p.tiles_x, gy, ((unsigned)p.tiles_y + gy - 1) / gy);
+    }
     fused_step_kernel<T, V, MATH, WX, WY, R, MINB, LDP, STP><<<grid, 32 * WX * WY, 0, st>>>(p);
 }
 
@@ -110,7 +115,10 @@ static void launch_variant(const StepParams &p_in, cudaStream_t st)
 #define VARS_FOR(T, TN, DT, VMAX, VHALF)                                                            \
     VAR(T, TN, DT, VMAX, MATH_FAST, "fast", 2, 2, 1, 6, 1, 0, true),                                \
     VAR(T, TN, DT, VMAX, MATH_FAST, "fast", 2, 2, 1, 4, 1, 0, false),                               \
+    VAR(T, TN, DT, VMAX, MATH_FAST, "fast", 2, 2, 1, 5, 1, 0, false),                               \
+    VAR(T, TN, DT, VMAX, MATH_FAST, "fast", 2, 2, 1, 7, 1, 0, false),                               \
     VAR(T, TN, DT, VMAX, MATH_FAST, "fast", 2, 2, 1, 8, 1, 0, false),                               \
+    VAR(T, TN, DT, VMAX, MATH_FAST, "fast", 4, 1, 1, 6, 1, 0, false),                               \
     VAR(T, TN, DT, VMAX, MATH_FAST, "fast", 2, 2, 2, 4, 1, 0, false),                               \
     VAR(T, TN, DT, VMAX, MATH_FAST, "fast", 2, 2, 2, 3, 1, 0, false),                               \
     VAR(T, TN, DT, VMAX, MATH_FAST, "fast", 2, 2, 2, 2, 1, 0, false),                               \
@@ -130,8 +138,11 @@ static void launch_variant(const StepParams &p_in, cudaStream_t st)
     VAR(T, TN, DT, VHALF, MATH_FAST, "fast", 2, 2, 2, 6, 1, 0, false),                              \
     VAR(T, TN, DT, VHALF, MATH_FAST, "fast", 4, 2, 1, 4, 1, 0, false),                              \
     VAR(T, TN, DT, VHALF, MATH_FAST, "fast", 2, 2, 4, 6, 1, 0, false),                              \
-    VAR(T, TN, DT, VMAX, MATH_STRICT, "strict", 2, 2, 1, 4, 1, 0, true),                            \
-    VAR(T, TN, DT, VMAX, MATH_STRICT, "strict", 2, 2, 1, 6, 1, 0, false),                           \
+    VAR(T, TN, DT, VMAX, MATH_STRICT, "strict", 2, 2, 1, 6, 1, 0, true),                            \
+    VAR(T, TN, DT, VMAX, MATH_STRICT, "strict", 2, 2, 1, 5, 1, 0, false),                           \
+    VAR(T, TN, DT, VMAX, MATH_STRICT, "strict", 2, 2, 1, 4, 1, 0, false),                           \
+    VAR(T, TN, DT, VMAX, MATH_STRICT, "strict", 2, 4, 1, 3, 1, 0, false),                           \
+    VAR(T, TN, DT, VMAX, MATH_STRICT, "strict", 4, 1, 1, 6, 1, 0, false),                           \
     VAR(T, TN, DT, VMAX, MATH_STRICT, "strict", 2, 2, 2, 3, 1, 0, false),                           \
     VAR(T, TN, DT, VHALF, MATH_STRICT, "strict", 2, 2, 1, 8, 1, 0, false),                          \
     VAR(T, TN, DT, VHALF, MATH_STRICT, "strict", 2, 2, 2, 6, 1, 0, false)
@@ -391,8 +402,8 @@ static void fill_params(lb_sim *s, StepParams &p, int src_idx, int write_moments
     p.zero_obstacle_velocity = s->cfg.zero_obstacle_velocity;
     p.mask = s->mask; p.span_solid = s->span_solid; p.mask_pitch = s->mask_pitch; p.nspans = s->nspans;
     p.rho = s->rho; p.u = s->u; p.v = s->v;
-    p.omega = s->cfg.omega; p.inlet_rho = s->cfg.inlet_rho; p.outlet_rho = s->cfg.outlet_rho;
-    p.cs2 = s->cfg.cs2; p.cs22 = s->cfg.cs22; p.two_cs4 = s->cfg.two_cs4;
+    p.cf = consts_of<float>(s);
+    p.cd = consts_of<double>(s);
     if (uses_halo(s)) {
         const int rp = state_index & 1, wp = (state_index + 1) & 1;
         const HaloLayout &h = s->hl;

@@ -37,7 +37,8 @@ struct StepParams {
     const uint8_t *span_solid;// [ny][nspans]: does this group of 32 cells of this row contain a solid node
     int mask_pitch, nspans;
     void *rho, *u, *v;        // [ny][pitch]
-    double omega, inlet_rho, outlet_rho, cs2, cs22, two_cs4;
+    Consts<float> cf;         // per-launch constants, precomputed on the host in both types
+    Consts<double> cd;
     // x-slab halo (EDGE_HALO): ghost columns are [3][ny+2] (slot, y+1)
     const void *ghost_w;      // populations 1,5,8 of the west neighbour's last column (read)
     const void *ghost_e;      // populations 3,6,7 of the east neighbour's first column (read)
@@ -49,8 +50,12 @@ struct StepParams {
     unsigned int *error_word;                      // set on hand-shake timeout
     unsigned int step_id;                          // flag value that must be visible before reading ghosts
     int tiles_x, tiles_y;
-    int edge_first;           // order edge tiles first (halo overlap)
+    int edge_first;           // 1-D grid with the two edge tile columns first (halo overlap); else 2-D/3-D grid
 };
+
+template <typename T> __device__ __forceinline__ const Consts<T> &consts_in(const StepParams &p);
+template <> __device__ __forceinline__ const Consts<float> &consts_in<float>(const StepParams &p) { return p.cf; }
+template <> __device__ __forceinline__ const Consts<double> &consts_in<double>(const StepParams &p) { return p.cd; }
 
 // ---- vector access helpers ----------------------------------------------------------
 template <typename T, int V> struct VecOf;
@@ -144,16 +149,19 @@ __global__ void __launch_bounds__(32 * WX * WY, MINB) fused_step_kernel(const St
     const int warp = threadIdx.x >> 5;
     const int wx = warp % WX, wy = warp / WX;
 
-    // tile decode; with edge_first the two edge tile columns come first in launch order so that
-    // the neighbours' ghost data is published as early as possible in the step
+    // tile decode.  Single-GPU launches use a (tiles_x, tiles_y) grid: no integer division.  Halo
+    // launches use a 1-D grid in which the two edge tile columns come first, so the neighbours'
+    // ghost data is published as early as possible in the step.
     int bx, by;
-    {
+    if (p.edge_first) {
         const int b = blockIdx.x;
-        if (p.edge_first && p.tiles_x >= 2) {
-            const int n_edge = 2 * p.tiles_y;
-            if (b < n_edge) { bx = (b & 1) ? p.tiles_x - 1 : 0; by = b >> 1; }
-            else { const int r = b - n_edge; bx = 1 + r % (p.tiles_x - 2); by = r / (p.tiles_x - 2); }
-        } else { bx = b % p.tiles_x; by = b / p.tiles_x; }
+        const int n_edge = 2 * p.tiles_y;
+        if (p.tiles_x < 2) { bx = 0; by = b; }
+        else if (b < n_edge) { bx = (b & 1) ? p.tiles_x - 1 : 0; by = b >> 1; }
+        else { const int r = b - n_edge; by = r / (p.tiles_x - 2); bx = 1 + (r - by * (p.tiles_x - 2)); }
+    } else {
+        bx = blockIdx.x;
+        by = blockIdx.z * gridDim.y + blockIdx.y;
     }
     const bool halo_w = (p.west == EDGE_HALO) && (bx == 0);
     const bool halo_e = (p.east == EDGE_HALO) && (bx == p.tiles_x - 1);
@@ -169,7 +177,7 @@ __global__ void __launch_bounds__(32 * WX * WY, MINB) fused_step_kernel(const St
     T *__restrict__ dst = static_cast<T *>(p.dst);
     const long long plane = p.plane;
     const int nx = p.nx, ny = p.ny, pitch = p.pitch;
-    const Consts<T> c = make_consts<T>(p.omega, p.inlet_rho, p.outlet_rho, p.cs2, p.cs22, p.two_cs4);
+    const Consts<T> &c = consts_in<T>(p);
     const bool periodic = (p.bc == BC_PERIODIC);
     const int el_east = (nx - 1) - x0;                // element index of column nx-1 in this thread, if in [0,V)
     const bool has_west = (x0 == 0);
@@ -179,35 +187,39 @@ __global__ void __launch_bounds__(32 * WX * WY, MINB) fused_step_kernel(const St
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const int y = ybase + r;
-            if (y >= ny) break;                       // warp-uniform
+            if (y >= ny) break;                       // warp-uniform (also guards by >= tiles_y)
             int ym = y - 1, yp = y + 1;               // source rows of the cy=+1 / cy=-1 populations
             if (periodic) { if (ym < 0) ym = ny - 1; if (yp >= ny) yp = 0; }
             const long long rc = (long long)y * pitch + x0;
             const long long rm = (long long)ym * pitch + x0;
             const long long rp = (long long)yp * pitch + x0;
 
-            // --- 9 aligned vector loads (guard rows make y=-1 / y=ny addresses valid) ---
+            // --- 9 aligned vector loads (guard rows make y=-1 / y=ny addresses valid).
+            //     Three row bases + uniform multiples of the plane stride: one 64-bit add per address.
+            const T *pc = src + rc;                   // planes 0,1,3 read row y
+            const T *pm = src + rm + 2 * plane;       // planes 2,5,6 read row y-1
+            const T *pp = src + rp + 4 * plane;       // planes 4,7,8 read row y+1
             Pack<T, V> q[9];
-            q[0] = load_pack<T, V, LDP>(src + 0 * plane + rc);
-            q[1] = load_pack<T, V, LDP>(src + 1 * plane + rc);
-            q[2] = load_pack<T, V, LDP>(src + 2 * plane + rm);
-            q[3] = load_pack<T, V, LDP>(src + 3 * plane + rc);
-            q[4] = load_pack<T, V, LDP>(src + 4 * plane + rp);
-            q[5] = load_pack<T, V, LDP>(src + 5 * plane + rm);
-            q[6] = load_pack<T, V, LDP>(src + 6 * plane + rm);
-            q[7] = load_pack<T, V, LDP>(src + 7 * plane + rp);
-            q[8] = load_pack<T, V, LDP>(src + 8 * plane + rp);
-            // --- elements that cross the warp boundary ---
+            q[0] = load_pack<T, V, LDP>(pc);
+            q[1] = load_pack<T, V, LDP>(pc + plane);
+            q[3] = load_pack<T, V, LDP>(pc + 3 * plane);
+            q[2] = load_pack<T, V, LDP>(pm);
+            q[5] = load_pack<T, V, LDP>(pm + 3 * plane);
+            q[6] = load_pack<T, V, LDP>(pm + 4 * plane);
+            q[4] = load_pack<T, V, LDP>(pp);
+            q[7] = load_pack<T, V, LDP>(pp + 3 * plane);
+            q[8] = load_pack<T, V, LDP>(pp + 4 * plane);
+            // --- elements that cross the warp boundary (same 32-B sector the neighbour warp loads) ---
             T l1 = (T)0, l5 = (T)0, l8 = (T)0, r3 = (T)0, r6 = (T)0, r7 = (T)0;
             if (lane == 0) {
-                l1 = src[1 * plane + rc - 1];
-                l5 = src[5 * plane + rm - 1];
-                l8 = src[8 * plane + rp - 1];
+                l1 = pc[plane - 1];
+                l5 = pm[3 * plane - 1];
+                l8 = pp[4 * plane - 1];
             }
             if (lane == 31) {
-                r3 = src[3 * plane + rc + V];
-                r6 = src[6 * plane + rm + V];
-                r7 = src[7 * plane + rp + V];
+                r3 = pc[3 * plane + V];
+                r6 = pm[4 * plane + V];
+                r7 = pp[3 * plane + V];
             }
             // --- elements that cross the thread boundary ---
             {
@@ -264,43 +276,66 @@ __global__ void __launch_bounds__(32 * WX * WY, MINB) fused_step_kernel(const St
                     if (e == el_east) { q[3].v[e] = a3; q[6].v[e] = a6; q[7].v[e] = a7; }
             }
 
-            // --- obstacle mask: one flag byte per (row, span) says whether to look at all ---
+            // --- boundary closure: only threads that own a wall / inlet / outlet node ---
+            const bool row_is_wall = (!periodic) && (y == 0 || y == ny - 1);
+            if ((!periodic) && (row_is_wall || (has_west && p.west == EDGE_BOUNDARY) ||
+                                (has_east && p.east == EDGE_BOUNDARY))) {
+#pragma unroll
+                for (int e = 0; e < V; ++e) {
+                    T g[9];
+#pragma unroll
+                    for (int j = 0; j < 9; ++j) g[j] = q[j].v[e];
+                    pipe_bc<T>(c, p.x_off + x0 + e, y, p.gnx, ny, g);
+#pragma unroll
+                    for (int j = 0; j < 9; ++j) q[j].v[e] = g[j];
+                }
+            }
+
+            // --- obstacles: one flag byte per (row, 32 cells) says whether to look at the mask at all.
+            //     The vote makes the branch warp-uniform, so warps without solids issue nothing here.
             uint32_t solid_bits = 0;
             if (p.mask != nullptr) {
-                // flags have a fixed granularity of 32 cells: this warp's span covers SPAN/32 of them
                 const uint8_t *sf = p.span_solid + (long long)y * p.nspans + (span0 >> 5);
                 unsigned int any = 0;
 #pragma unroll
                 for (int k = 0; k < SPAN / 32; ++k) any |= sf[k];
-                if (any) {                                               // warp-uniform
+                if (__any_sync(0xffffffffu, any != 0)) {
 #pragma unroll
                     for (int e = 0; e < V; ++e)
                         if (x0 + e < nx && p.mask[(long long)y * p.mask_pitch + x0 + e] == 1) solid_bits |= (1u << e);
+                    if (__any_sync(0xffffffffu, solid_bits != 0)) {
+#pragma unroll
+                        for (int e = 0; e < V; ++e) {
+                            if ((solid_bits >> e) & 1u) {         // D2Q9.cl:410-431
+                                T t;
+                                t = q[1].v[e]; q[1].v[e] = q[3].v[e]; q[3].v[e] = t;
+                                t = q[2].v[e]; q[2].v[e] = q[4].v[e]; q[4].v[e] = t;
+                                t = q[5].v[e]; q[5].v[e] = q[7].v[e]; q[7].v[e] = t;
+                                t = q[6].v[e]; q[6].v[e] = q[8].v[e]; q[8].v[e] = t;
+                            }
+                        }
+                    }
                 }
             }
+            const uint32_t zero_bits = p.zero_obstacle_velocity ? solid_bits : 0u;
 
-            // --- per node: boundary closure, bounce-back, moments + feq + BGK ---
-            const bool row_is_wall = (!periodic) && (y == 0 || y == ny - 1);
-            const bool bc_thread = (!periodic) && (row_is_wall || (has_west && p.west == EDGE_BOUNDARY) ||
-                                                  (has_east && p.east == EDGE_BOUNDARY));
+            // --- per node: moments + equilibrium + BGK relaxation, in registers ---
             Pack<T, V> mrho, mu, mv;
 #pragma unroll
             for (int e = 0; e < V; ++e) {
                 T g[9];
 #pragma unroll
                 for (int j = 0; j < 9; ++j) g[j] = q[j].v[e];
-                if (bc_thread) pipe_bc<T>(c, p.x_off + x0 + e, y, p.gnx, ny, g);
-                const bool solid = (solid_bits >> e) & 1u;
-                if (solid) bounce_back<T>(g);
-                collide_node<T, MATH>(c, g, mrho.v[e], mu.v[e], mv.v[e], solid && p.zero_obstacle_velocity);
+                collide_node<T, MATH>(c, g, mrho.v[e], mu.v[e], mv.v[e], (zero_bits >> e) & 1u);
 #pragma unroll
                 for (int j = 0; j < 9; ++j) q[j].v[e] = g[j];
             }
 
             // --- stores: aligned vectors; the one thread straddling column nx-1 goes scalar ---
             if (x0 + V <= nx) {
+                T *pd = dst + rc;
 #pragma unroll
-                for (int j = 0; j < 9; ++j) store_pack<T, V, STP>(dst + j * plane + rc, q[j]);
+                for (int j = 0; j < 9; ++j) store_pack<T, V, STP>(pd + j * plane, q[j]);
                 if (p.write_moments) {
                     store_pack<T, V, 0>(static_cast<T *>(p.rho) + rc, mrho);
                     store_pack<T, V, 0>(static_cast<T *>(p.u) + rc, mu);

@@ -68,6 +68,7 @@ class Lattice:
         self.cfg = cfg
         self.omega, self.inlet_rho, self.outlet_rho = cfg.omega, cfg.inlet_rho, cfg.outlet_rho
         self.device = cfg.device
+        self._stream_owner = None     # set by whoever lends this lattice a stream: keeps the lender alive
         h = ct.c_void_p()
         N.check(N.lib().lb_create(ct.byref(cfg), ct.byref(h)))
         self._h = h
@@ -271,9 +272,11 @@ class LocalSlabs:
         streams = {}          # one stream per device, shared by the slabs that live there
         for r, (x0, w) in enumerate(self.ranges):
             we, ee = slab_edges(r, parts, self.bc)
+            lender = streams.get(devices[r])
             s = Lattice(w, ny, global_nx=global_nx, x_offset=x0, west_edge=we, east_edge=ee,
-                        device=devices[r], stream=streams.get(devices[r]), **kw)
-            streams.setdefault(devices[r], s.stream_ptr)
+                        device=devices[r], stream=lender.stream_ptr if lender else None, **kw)
+            s._stream_owner = lender       # the lender (which owns the stream) must outlive the borrower
+            streams.setdefault(devices[r], s)
             self.slabs.append(s)
         if parts > 1:
             for r, s in enumerate(self.slabs):
@@ -283,7 +286,7 @@ class LocalSlabs:
                     s.halo_connect_local("east", self.slabs[(r + 1) % parts])
 
     def close(self):
-        for s in self.slabs:
+        for s in reversed(self.slabs):     # borrowers of a shared stream first, its owner last
             s.close()
 
     def set_mask(self, mask):
