@@ -383,11 +383,19 @@ __global__ void __launch_bounds__(32 * WX * WY, MINB) fused_step_kernel(const St
         if (threadIdx.x == 0) {
             if (halo_w) {
                 const unsigned int old = atomicAdd(p.done_w, 1u);
-                if (old == (unsigned int)p.tiles_y - 1u) { *p.done_w = 0u; st_release_sys(p.flag_w_remote, p.step_id + 1u); }
+                if (old == (unsigned int)p.tiles_y - 1u) {
+                    __threadfence_system();      // acquire side: every other edge tile's peer stores are ordered before the flag
+                    *p.done_w = 0u;
+                    st_release_sys(p.flag_w_remote, p.step_id + 1u);
+                }
             }
             if (halo_e) {
                 const unsigned int old = atomicAdd(p.done_e, 1u);
-                if (old == (unsigned int)p.tiles_y - 1u) { *p.done_e = 0u; st_release_sys(p.flag_e_remote, p.step_id + 1u); }
+                if (old == (unsigned int)p.tiles_y - 1u) {
+                    __threadfence_system();
+                    *p.done_e = 0u;
+                    st_release_sys(p.flag_e_remote, p.step_id + 1u);
+                }
             }
         }
     }

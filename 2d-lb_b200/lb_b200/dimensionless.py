@@ -45,7 +45,7 @@ class Pipe_Flow(object):
     def __init__(self, diameter=None, rho=None, viscosity=None, pressure_grad=None, pipe_length=None,
                  N=200, time_prefactor=1.,
                  two_d_local_size=(32, 32), three_d_local_size=(32, 32, 1), use_interop=False,
-                 dtype=np.float32, math="fast", device=0, verbose=True,
+                 dtype=np.float32, math="strict", device=0, verbose=True,
                  zero_obstacle_velocity_each_step=None, units="opencl"):
         if units not in ("opencl", "cython"):
             raise ValueError("units must be 'opencl' or 'cython'")

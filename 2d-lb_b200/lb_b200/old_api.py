@@ -17,7 +17,7 @@ NUM_JUMPERS = 9
 class Pipe_Flow(object):
     def __init__(self, omega=.99, lx=400, ly=400, dr=1., dt=1., deltaP=-.1,
                  two_d_local_size=(32, 32), three_d_local_size=(32, 32, 1),
-                 dtype=np.float32, math="fast", device=0):
+                 dtype=np.float32, math="strict", device=0):
         self.lx, self.ly = lx, ly
         self.omega = np.float32(omega)                       # OLD/opencl.py:50
         self.dr, self.dt, self.deltaP = np.float32(dr), np.float32(dt), np.float32(deltaP)

@@ -28,7 +28,7 @@ class SlabLattice:
     """
 
     def __init__(self, global_nx, ny, omega, inlet_rho=1.0, outlet_rho=1.0, bc="pipe", dtype=np.float32,
-                 math="fast", device=None, zero_obstacle_velocity=False, stream=None, dist=None,
+                 math="strict", device=None, zero_obstacle_velocity=False, stream=None, dist=None,
                  lattice_factory=Lattice):
         if dist is None:
             import torch.distributed as dist

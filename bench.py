@@ -225,7 +225,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--math", default="fast", choices=["fast", "strict"])
+    ap.add_argument("--math", default="strict", choices=["fast", "strict"])
     ap.add_argument("--variant", default="")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
