@@ -4,6 +4,7 @@
 // (see __graft_entry__.build()).
 #include "../../include/lb_d2q9.h"
 #include "lb_fused.cuh"
+#include "lb_cython.cuh"
 
 #include <cstdio>
 #include <cstring>
@@ -41,6 +42,8 @@ static HaloLayout halo_layout(int ny, int elem)
 struct lb_sim {
     lb_config cfg;
     int elem = 4;                 // bytes per population value
+    int uv_elem = 4;              // bytes per u / v value (8 for the cython schemes: float64 like the reference)
+    bool prestream_done = false;  // cython schemes: is the next step's BC + swap already applied to `cur`
     int pitch = 0;                // row pitch in elements (multiple of 512 B)
     long long plane = 0;          // elements per plane
     size_t buf_bytes = 0;         // bytes of one guarded 9-plane buffer
@@ -100,7 +103,13 @@ static void launch_variant(const StepParams &p_in, cudaStream_t st)
     p.tiles_x = (p.pitch + SPAN * WX - 1) / (SPAN * WX);
     p.tiles_y = (p.ny + WY * R - 1) / (WY * R);
     dim3 grid;
-    if (p.edge_first) grid = dim3((unsigned)p.tiles_x * (unsigned)p.tiles_y, 1, 1);
+    if (p.edge_first) {
+        p.edge_rows = 16;
+        p.edge_tiles_y = (p.ny + WY * p.edge_rows - 1) / (WY * p.edge_rows);
+        const unsigned n_edge = (p.tiles_x < 2 ? 1u : 2u) * (unsigned)p.edge_tiles_y;
+        const unsigned n_int = p.tiles_x > 2 ? (unsigned)(p.tiles_x - 2) * (unsigned)p.tiles_y : 0u;
+        grid = dim3(n_edge + n_int, 1, 1);
+    }
     else {
         const unsigned gy = p.tiles_y < 65535 ? p.tiles_y : 65535;
         grid = dim3((unsigned)p.tiles_x, gy, ((unsigned)p.tiles_y + gy - 1) / gy);
@@ -119,13 +128,7 @@ static void launch_variant(const StepParams &p_in, cudaStream_t st)
     VAR(T, TN, DT, VMAX, MATH_FAST, "fast", 2, 2, 1, 7, 1, 0, false),                               \
     VAR(T, TN, DT, VMAX, MATH_FAST, "fast", 2, 2, 1, 8, 1, 0, false),                               \
     VAR(T, TN, DT, VMAX, MATH_FAST, "fast", 4, 1, 1, 6, 1, 0, false),                               \
-    VAR(T, TN, DT, VMAX, MATH_FAST, "fast", 2, 2, 2, 4, 1, 0, false),                               \
-    VAR(T, TN, DT, VMAX, MATH_FAST, "fast", 2, 2, 2, 3, 1, 0, false),                               \
-    VAR(T, TN, DT, VMAX, MATH_FAST, "fast", 2, 2, 2, 2, 1, 0, false),                               \
-    VAR(T, TN, DT, VMAX, MATH_FAST, "fast", 2, 2, 4, 2, 1, 0, false),                               \
     VAR(T, TN, DT, VMAX, MATH_FAST, "fast", 4, 1, 1, 4, 1, 0, false),                               \
-    VAR(T, TN, DT, VMAX, MATH_FAST, "fast", 4, 1, 2, 4, 1, 0, false),                               \
-    VAR(T, TN, DT, VMAX, MATH_FAST, "fast", 1, 4, 2, 4, 1, 0, false),                               \
     VAR(T, TN, DT, VMAX, MATH_FAST, "fast", 2, 4, 1, 2, 1, 0, false),                               \
     VAR(T, TN, DT, VMAX, MATH_FAST, "fast", 2, 4, 1, 3, 1, 0, false),                               \
     VAR(T, TN, DT, VMAX, MATH_FAST, "fast", 2, 4, 1, 4, 1, 0, false),                               \
@@ -134,16 +137,12 @@ static void launch_variant(const StepParams &p_in, cudaStream_t st)
     VAR(T, TN, DT, VMAX, MATH_FAST, "fast", 2, 2, 1, 6, 2, 1, false),                               \
     VAR(T, TN, DT, VMAX, MATH_FAST, "fast", 2, 2, 1, 6, 1, 1, false),                               \
     VAR(T, TN, DT, VHALF, MATH_FAST, "fast", 2, 2, 1, 8, 1, 0, false),                              \
-    VAR(T, TN, DT, VHALF, MATH_FAST, "fast", 2, 2, 2, 8, 1, 0, false),                              \
-    VAR(T, TN, DT, VHALF, MATH_FAST, "fast", 2, 2, 2, 6, 1, 0, false),                              \
     VAR(T, TN, DT, VHALF, MATH_FAST, "fast", 4, 2, 1, 4, 1, 0, false),                              \
-    VAR(T, TN, DT, VHALF, MATH_FAST, "fast", 2, 2, 4, 6, 1, 0, false),                              \
     VAR(T, TN, DT, VMAX, MATH_STRICT, "strict", 2, 2, 1, 6, 1, 0, true),                            \
     VAR(T, TN, DT, VMAX, MATH_STRICT, "strict", 2, 2, 1, 5, 1, 0, false),                           \
     VAR(T, TN, DT, VMAX, MATH_STRICT, "strict", 2, 2, 1, 4, 1, 0, false),                           \
     VAR(T, TN, DT, VMAX, MATH_STRICT, "strict", 2, 4, 1, 3, 1, 0, false),                           \
     VAR(T, TN, DT, VMAX, MATH_STRICT, "strict", 4, 1, 1, 6, 1, 0, false),                           \
-    VAR(T, TN, DT, VMAX, MATH_STRICT, "strict", 2, 2, 2, 3, 1, 0, false),                           \
     VAR(T, TN, DT, VHALF, MATH_STRICT, "strict", 2, 2, 1, 8, 1, 0, false),                          \
     VAR(T, TN, DT, VHALF, MATH_STRICT, "strict", 2, 2, 2, 6, 1, 0, false)
 
@@ -379,6 +378,11 @@ static Consts<T> consts_of(const lb_sim *s)
     return make_consts<T>(s->cfg.omega, s->cfg.inlet_rho, s->cfg.outlet_rho, s->cfg.cs2, s->cfg.cs22, s->cfg.two_cs4);
 }
 
+static CyConsts cy_consts_of(const lb_sim *s)
+{
+    return make_cy_consts(s->cfg.omega, s->cfg.inlet_rho, s->cfg.outlet_rho, s->cfg.cs2, s->cfg.cs22);
+}
+
 static void drop_graphs(lb_sim *s)
 {
     for (int i = 0; i < 2; ++i) {
@@ -477,6 +481,12 @@ int lb_create(const lb_config *cfg, lb_sim **out)
     if (cfg->global_nx < cfg->nx || cfg->x_offset < 0 || cfg->x_offset + cfg->nx > cfg->global_nx)
         return fail(nullptr, LB_ERR_INVALID, "lb_create: slab does not fit the global lattice");
     if (!(cfg->omega > 0.0 && cfg->omega < 2.0)) return fail(nullptr, LB_ERR_INVALID, "lb_create: omega must be in (0,2)");
+    if (cfg->scheme < LB_SCHEME_OPENCL || cfg->scheme > LB_SCHEME_CYTHON_OLD || cfg->reserved0 != 0)
+        return fail(nullptr, LB_ERR_INVALID, "lb_create: bad scheme");
+    if (cfg->scheme != LB_SCHEME_OPENCL &&
+        (cfg->dtype != LB_F32 || cfg->bc != LB_BC_PIPE || cfg->west_edge != LB_EDGE_BOUNDARY ||
+         cfg->east_edge != LB_EDGE_BOUNDARY || cfg->global_nx != cfg->nx))
+        return fail(nullptr, LB_ERR_INVALID, "lb_create: the cython schemes need dtype F32, bc PIPE and a single slab");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         cudaGetLastError();
@@ -487,6 +497,7 @@ int lb_create(const lb_config *cfg, lb_sim **out)
     sim = new lb_sim();
     sim->cfg = *cfg;
     sim->elem = cfg->dtype == LB_F32 ? 4 : 8;
+    sim->uv_elem = cfg->scheme == LB_SCHEME_OPENCL ? sim->elem : 8;
     const int per512 = 512 / sim->elem;
     sim->pitch = (cfg->nx + per512 - 1) / per512 * per512;
     sim->plane = (long long)sim->pitch * cfg->ny;
@@ -507,11 +518,11 @@ int lb_create(const lb_config *cfg, lb_sim **out)
         CUC(cudaMemsetAsync(sim->buf_base[i], 0, sim->buf_bytes, sim->stream));
         sim->buf[i] = sim->buf_base[i] + guard;
     }
-    const size_t mom = (size_t)sim->plane * sim->elem;
-    CUC(cudaMalloc(&sim->rho, mom)); CUC(cudaMalloc(&sim->u, mom)); CUC(cudaMalloc(&sim->v, mom));
+    const size_t mom = (size_t)sim->plane * sim->elem, mom_uv = (size_t)sim->plane * sim->uv_elem;
+    CUC(cudaMalloc(&sim->rho, mom)); CUC(cudaMalloc(&sim->u, mom_uv)); CUC(cudaMalloc(&sim->v, mom_uv));
     CUC(cudaMemsetAsync(sim->rho, 0, mom, sim->stream));
-    CUC(cudaMemsetAsync(sim->u, 0, mom, sim->stream));
-    CUC(cudaMemsetAsync(sim->v, 0, mom, sim->stream));
+    CUC(cudaMemsetAsync(sim->u, 0, mom_uv, sim->stream));
+    CUC(cudaMemsetAsync(sim->v, 0, mom_uv, sim->stream));
     CUC(cudaMalloc((void **)&sim->mass_scratch, sizeof(double) * cfg->ny));
     if (cfg->west_edge == LB_EDGE_HALO || cfg->east_edge == LB_EDGE_HALO) {
         sim->hl = halo_layout(cfg->ny, sim->elem);
@@ -619,6 +630,7 @@ int lb_upload_f(lb_sim *sim, const void *host_f)
     // the reference seeds f_streamed with the same data (opencl_dim.py:324-327)
     CU(cudaMemcpyAsync(sim->buf_base[sim->cur ^ 1], sim->buf_base[sim->cur], sim->buf_bytes, cudaMemcpyDeviceToDevice, sim->stream));
     CU(cudaStreamSynchronize(sim->stream));
+    sim->prestream_done = false;
     return LB_OK;
 }
 
@@ -626,11 +638,13 @@ int lb_upload_moments(lb_sim *sim, const void *host_rho, const void *host_u, con
 {
     if (!sim) return LB_ERR_INVALID;
     CU(cudaSetDevice(sim->cfg.device));
-    const size_t w = (size_t)sim->cfg.nx * sim->elem, dp = (size_t)sim->pitch * sim->elem;
     const void *hs[3] = {host_rho, host_u, host_v};
     void *ds[3] = {sim->rho, sim->u, sim->v};
-    for (int i = 0; i < 3; ++i)
+    for (int i = 0; i < 3; ++i) {
+        const int eb = i == 0 ? sim->elem : sim->uv_elem;      // u, v are float64 for the cython schemes
+        const size_t w = (size_t)sim->cfg.nx * eb, dp = (size_t)sim->pitch * eb;
         if (hs[i]) CU(cudaMemcpy2DAsync(ds[i], dp, hs[i], w, w, sim->cfg.ny, cudaMemcpyHostToDevice, sim->stream));
+    }
     CU(cudaStreamSynchronize(sim->stream));
     return LB_OK;
 }
@@ -649,7 +663,10 @@ static int compute_feq(lb_sim *sim)
     int rc = ensure_feq(sim);
     if (rc) return rc;
     const int nx = sim->cfg.nx, ny = sim->cfg.ny;
-    if (sim->cfg.dtype == LB_F32)
+    if (sim->cfg.scheme != LB_SCHEME_OPENCL)
+        cy_feq_kernel<<<grid2d(sim), 128, 0, sim->stream>>>(nx, ny, sim->pitch, sim->plane, (const float *)sim->rho,
+            (const double *)sim->u, (const double *)sim->v, (float *)sim->feq, cy_consts_of(sim));
+    else if (sim->cfg.dtype == LB_F32)
         k_feq_from_moments<float><<<grid2d(sim), 128, 0, sim->stream>>>(nx, ny, sim->pitch, sim->plane, (const float *)sim->rho,
             (const float *)sim->u, (const float *)sim->v, (float *)sim->feq, consts_of<float>(sim));
     else
@@ -660,6 +677,40 @@ static int compute_feq(lb_sim *sim)
 }
 
 // ---- the hot path ---------------------------------------------------------------------
+// scheme "cython": see lb_cython.cuh for the fusion order
+static int cython_steps(lb_sim *sim, int n_steps)
+{
+    const int nx = sim->cfg.nx, ny = sim->cfg.ny;
+    const CyConsts c = cy_consts_of(sim);
+    if (!sim->prestream_done) {
+        cy_prestream_kernel<<<grid2d(sim), 128, 0, sim->stream>>>(nx, ny, sim->pitch, sim->plane, (float *)sim->buf[sim->cur],
+                                                                   (const double *)sim->u, sim->mask, sim->mask_pitch, c);
+        CU(cudaGetLastError());
+    }
+    constexpr int WX = 2, WY = 2;
+    const unsigned tiles_x = (sim->pitch + 128 * WX - 1) / (128 * WX), tiles_y = (ny + WY - 1) / WY;
+    const unsigned gy = tiles_y < 65535 ? tiles_y : 65535;
+    const dim3 grid(tiles_x, gy, (tiles_y + gy - 1) / gy);
+    for (int i = 0; i < n_steps; ++i) {
+        const bool last = (i == n_steps - 1);
+        CyParams p;
+        p.src = (const float *)sim->buf[sim->cur];
+        p.dst = (float *)sim->buf[sim->cur ^ 1];
+        p.plane = sim->plane; p.nx = nx; p.ny = ny; p.pitch = sim->pitch;
+        p.write_moments = last; p.apply_next_bc = !last;
+        p.mask = sim->mask; p.mask_pitch = sim->mask_pitch;
+        p.rho = (float *)sim->rho; p.u = (double *)sim->u; p.v = (double *)sim->v;
+        p.c = c;
+        if (sim->cfg.scheme == LB_SCHEME_CYTHON_OLD) fused_step_cython_kernel<true, WX, WY, 4><<<grid, 32 * WX * WY, 0, sim->stream>>>(p);
+        else fused_step_cython_kernel<false, WX, WY, 4><<<grid, 32 * WX * WY, 0, sim->stream>>>(p);
+        CU(cudaGetLastError());
+        sim->launches++;
+        sim->cur ^= 1; sim->state_index++;
+    }
+    sim->prestream_done = false;      // the last launch left plain post-collision populations
+    return LB_OK;
+}
+
 static const int GRAPH_LEN = 32;    // steps per captured graph (even: a graph returns to its start buffer)
 
 // (re)build the graph of GRAPH_LEN moment-free steps that starts from buffer `sim->cur`
@@ -697,6 +748,7 @@ int lb_step(lb_sim *sim, int n_steps)
             if (e == LB_EDGE_HALO && !sim->peer[side]) return fail(sim, LB_ERR_STATE, "lb_step: halo edge not connected");
         }
     }
+    if (sim->cfg.scheme != LB_SCHEME_OPENCL) return cython_steps(sim, n_steps);
     int remaining = n_steps - 1;            // all but the last step skip the moment stores
     const bool graphs_ok = !uses_halo(sim); // halo launches carry a per-step flag value
     while (graphs_ok && remaining >= GRAPH_LEN) {
@@ -735,7 +787,8 @@ int lb_download(lb_sim *sim, int field, void *host_out)
 {
     if (!sim || !host_out) return fail(sim, LB_ERR_INVALID, "lb_download: null argument");
     CU(cudaSetDevice(sim->cfg.device));
-    const size_t w = (size_t)sim->cfg.nx * sim->elem, dp = (size_t)sim->pitch * sim->elem;
+    size_t w = (size_t)sim->cfg.nx * sim->elem, dp = (size_t)sim->pitch * sim->elem;
+    if (field == LB_FIELD_U || field == LB_FIELD_V) { w = (size_t)sim->cfg.nx * sim->uv_elem; dp = (size_t)sim->pitch * sim->uv_elem; }
     const void *src = nullptr;
     size_t rows = sim->cfg.ny;
     switch (field) {
@@ -778,6 +831,7 @@ int lb_device_ptr(lb_sim *sim, int field, void **ptr, int64_t *pitch_elems)
 int lb_stage_move(lb_sim *sim)
 {
     if (!sim) return LB_ERR_INVALID;
+    if (sim->cfg.scheme != LB_SCHEME_OPENCL) return fail(sim, LB_ERR_STATE, "lb_stage_move: single stages exist for LB_SCHEME_OPENCL only");
     if (uses_halo(sim)) return fail(sim, LB_ERR_STATE, "single stages are not available on halo-connected slabs");
     CU(cudaSetDevice(sim->cfg.device));
     DISPATCH(k_stage_move, grid2d(sim), sim->cfg.nx, sim->cfg.ny, sim->pitch, sim->plane, sim->cfg.bc == LB_BC_PERIODIC,
@@ -789,6 +843,7 @@ int lb_stage_move(lb_sim *sim)
 int lb_stage_move_bcs(lb_sim *sim)
 {
     if (!sim) return LB_ERR_INVALID;
+    if (sim->cfg.scheme != LB_SCHEME_OPENCL) return fail(sim, LB_ERR_STATE, "lb_stage_move_bcs: single stages exist for LB_SCHEME_OPENCL only");
     CU(cudaSetDevice(sim->cfg.device));
     DISPATCH(k_stage_bcs, grid2d(sim), sim->cfg.nx, sim->cfg.ny, sim->pitch, sim->plane, sim->cfg.global_nx, sim->cfg.x_offset,
              sim->cfg.bc == LB_BC_PIPE, sim->mask, sim->mask_pitch, (T *)sim->buf[sim->cur], consts_of<T>(sim));
@@ -798,6 +853,7 @@ int lb_stage_move_bcs(lb_sim *sim)
 int lb_stage_update_hydro(lb_sim *sim)
 {
     if (!sim) return LB_ERR_INVALID;
+    if (sim->cfg.scheme != LB_SCHEME_OPENCL) return fail(sim, LB_ERR_STATE, "lb_stage_update_hydro: single stages exist for LB_SCHEME_OPENCL only");
     CU(cudaSetDevice(sim->cfg.device));
     DISPATCH(k_stage_hydro, grid2d(sim), sim->cfg.nx, sim->cfg.ny, sim->pitch, sim->plane, (const T *)sim->buf[sim->cur],
              (T *)sim->rho, (T *)sim->u, (T *)sim->v);
@@ -810,6 +866,12 @@ int lb_stage_zero_velocity(lb_sim *sim)
     if (!sim) return LB_ERR_INVALID;
     if (!sim->mask) return LB_OK;
     CU(cudaSetDevice(sim->cfg.device));
+    if (sim->cfg.scheme != LB_SCHEME_OPENCL) {
+        k_zero_velocity<double><<<grid2d(sim), 128, 0, sim->stream>>>(sim->cfg.nx, sim->cfg.ny, sim->pitch, sim->mask, sim->mask_pitch,
+                                                                       (double *)sim->u, (double *)sim->v);
+        CU(cudaGetLastError());
+        return LB_OK;
+    }
     DISPATCH(k_zero_velocity, grid2d(sim), sim->cfg.nx, sim->cfg.ny, sim->pitch, sim->mask, sim->mask_pitch, (T *)sim->u, (T *)sim->v);
     return LB_OK;
 }
@@ -824,6 +886,7 @@ int lb_stage_update_feq(lb_sim *sim)
 int lb_stage_collide(lb_sim *sim)
 {
     if (!sim) return LB_ERR_INVALID;
+    if (sim->cfg.scheme != LB_SCHEME_OPENCL) return fail(sim, LB_ERR_STATE, "lb_stage_collide: single stages exist for LB_SCHEME_OPENCL only");
     CU(cudaSetDevice(sim->cfg.device));
     if (!sim->feq) return fail(sim, LB_ERR_STATE, "lb_stage_collide: call lb_stage_update_feq first");
     DISPATCH(k_stage_collide, grid2d(sim), sim->cfg.nx, sim->cfg.ny, sim->pitch, sim->plane, (T *)sim->buf[sim->cur],
@@ -836,6 +899,7 @@ int lb_init_synthetic(lb_sim *sim, int kind, double u0, double amplitude, uint64
 {
     if (!sim) return LB_ERR_INVALID;
     if (kind != LB_SYNTH_PIPE_RAMP && kind != LB_SYNTH_SHEAR_LAYERS) return fail(sim, LB_ERR_INVALID, "lb_init_synthetic: bad kind");
+    if (sim->cfg.scheme != LB_SCHEME_OPENCL) return fail(sim, LB_ERR_STATE, "lb_init_synthetic: LB_SCHEME_OPENCL only");
     CU(cudaSetDevice(sim->cfg.device));
     DISPATCH(k_init_synth, grid2d(sim), sim->cfg.nx, sim->cfg.ny, sim->pitch, sim->plane, sim->cfg.global_nx, sim->cfg.x_offset, kind,
              u0, amplitude, (unsigned long long)seed, sim->cfg.inlet_rho, sim->cfg.outlet_rho, sim->mask, sim->mask_pitch,

@@ -16,7 +16,7 @@
 // resolved in registers: aligned vector load, one warp shuffle for the element that crosses
 // the thread boundary, one predicated scalar load on lane 0 / lane 31 for the element that
 // crosses the warp boundary.  A CTA is WX warps wide and WY warps tall; each warp walks R
-// rows.  Every plane element is read exactly once per step, so the algorithmic traffic is
+// rows (edge tiles of a halo-connected slab walk `edge_rows` rows instead).  Every plane element is read exactly once per step, so the algorithmic traffic is
 // 9 loads + 9 stores per cell: 72 B (fp32) / 144 B (fp64) per lattice update.
 #pragma once
 #include "lb_device.cuh"
@@ -51,6 +51,8 @@ struct StepParams {
     unsigned int step_id;                          // flag value that must be visible before reading ghosts
     int tiles_x, tiles_y;
     int edge_first;           // 1-D grid with the two edge tile columns first (halo overlap); else 2-D/3-D grid
+    int edge_rows;            // rows per warp in an edge tile (tall tiles: few participants in the hand-shake)
+    int edge_tiles_y;         // edge tiles per side
 };
 
 template <typename T> __device__ __forceinline__ const Consts<T> &consts_in(const StepParams &p);
@@ -153,12 +155,20 @@ __global__ void __launch_bounds__(32 * WX * WY, MINB) fused_step_kernel(const St
     // launches use a 1-D grid in which the two edge tile columns come first, so the neighbours'
     // ghost data is published as early as possible in the step.
     int bx, by;
+    int rows = R;                                     // rows each warp walks
     if (p.edge_first) {
+        // edge tiles are TALL (edge_rows rows per warp): few CTAs take part in the hand-shake
         const int b = blockIdx.x;
-        const int n_edge = 2 * p.tiles_y;
-        if (p.tiles_x < 2) { bx = 0; by = b; }
-        else if (b < n_edge) { bx = (b & 1) ? p.tiles_x - 1 : 0; by = b >> 1; }
-        else { const int r = b - n_edge; by = r / (p.tiles_x - 2); bx = 1 + (r - by * (p.tiles_x - 2)); }
+        const int n_edge = (p.tiles_x < 2 ? 1 : 2) * p.edge_tiles_y;
+        if (b < n_edge) {
+            rows = p.edge_rows;
+            if (p.tiles_x < 2) { bx = 0; by = b; }
+            else { bx = (b & 1) ? p.tiles_x - 1 : 0; by = b >> 1; }
+        } else {
+            const int r = b - n_edge;
+            by = r / (p.tiles_x - 2);
+            bx = 1 + (r - by * (p.tiles_x - 2));
+        }
     } else {
         bx = blockIdx.x;
         by = blockIdx.z * gridDim.y + blockIdx.y;
@@ -170,7 +180,7 @@ __global__ void __launch_bounds__(32 * WX * WY, MINB) fused_step_kernel(const St
 
     const int span0 = (bx * WX + wx) * SPAN;          // first cell of this warp's span
     const int x0 = span0 + lane * V;                  // first cell of this thread
-    const int ybase = (by * WY + wy) * R;
+    const int ybase = (by * WY + wy) * rows;
     const bool warp_active = span0 < p.pitch;         // warp-uniform (pitch is a multiple of SPAN)
 
     const T *__restrict__ src = static_cast<const T *>(p.src);
@@ -184,8 +194,7 @@ __global__ void __launch_bounds__(32 * WX * WY, MINB) fused_step_kernel(const St
     const bool has_east = (el_east >= 0 && el_east < V);
 
     if (warp_active) {
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
+        for (int r = 0; r < rows; ++r) {
             const int y = ybase + r;
             if (y >= ny) break;                       // warp-uniform (also guards by >= tiles_y)
             int ym = y - 1, yp = y + 1;               // source rows of the cy=+1 / cy=-1 populations
@@ -376,22 +385,24 @@ __global__ void __launch_bounds__(32 * WX * WY, MINB) fused_step_kernel(const St
         }
     }
 
-    // --- last edge tile of each side releases the neighbour for its next step ---
+    // --- last edge tile of each side releases the neighbour for its next step.  The barrier orders
+    //     every thread's peer stores before thread 0's system-scope fence (cumulativity), so one
+    //     thread fences for the CTA -- the cooperative-groups grid-sync pattern.
     if (halo_w || halo_e) {
-        __threadfence_system();
         __syncthreads();
         if (threadIdx.x == 0) {
+            __threadfence_system();
             if (halo_w) {
                 const unsigned int old = atomicAdd(p.done_w, 1u);
-                if (old == (unsigned int)p.tiles_y - 1u) {
-                    __threadfence_system();      // acquire side: every other edge tile's peer stores are ordered before the flag
+                if (old == (unsigned int)p.edge_tiles_y - 1u) {
+                    __threadfence_system();      // acquire side: the other edge tiles' peer stores precede the flag
                     *p.done_w = 0u;
                     st_release_sys(p.flag_w_remote, p.step_id + 1u);
                 }
             }
             if (halo_e) {
                 const unsigned int old = atomicAdd(p.done_e, 1u);
-                if (old == (unsigned int)p.tiles_y - 1u) {
+                if (old == (unsigned int)p.edge_tiles_y - 1u) {
                     __threadfence_system();
                     *p.done_e = 0u;
                     st_release_sys(p.flag_e_remote, p.step_id + 1u);

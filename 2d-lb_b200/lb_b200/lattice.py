@@ -21,6 +21,7 @@ two_cs4 = 2 * cs ** 4
 _BC = {"pipe": N.BC_PIPE, "periodic": N.BC_PERIODIC}
 _MATH = {"strict": N.MATH_STRICT, "fast": N.MATH_FAST}
 _EDGE = {"boundary": N.EDGE_BOUNDARY, "wrap": N.EDGE_WRAP, "halo": N.EDGE_HALO}
+_SCHEME = {"opencl": N.SCHEME_OPENCL, "cython": N.SCHEME_CYTHON, "cython_old": N.SCHEME_CYTHON_OLD}
 _FIELD = {"f": N.FIELD_F, "feq": N.FIELD_FEQ, "rho": N.FIELD_RHO, "u": N.FIELD_U, "v": N.FIELD_V}
 
 
@@ -40,12 +41,16 @@ class Lattice:
            oracle, and HBM-bound like 'fast') or 'fast' (FMA + reciprocal constants, ~30% fewer
            instructions, agrees to rounding)
     dtype  np.float32 (the reference's precision) or np.float64
+    scheme 'opencl' (default: the step order of opencl_dim.py), 'cython' or
+           'cython_old' (the reference's CPU classes, cython_dim.pyx / OLD/cython.pyx, including
+           their mixed-precision arithmetic; float32 populations, float64 u and v)
     """
 
     def __init__(self, nx, ny, omega, inlet_rho=1.0, outlet_rho=1.0, mask=None, f0=None, bc="pipe",
                  dtype=np.float32, math="strict", device=0, zero_obstacle_velocity=False,
-                 global_nx=None, x_offset=0, west_edge=None, east_edge=None, stream=None):
+                 global_nx=None, x_offset=0, west_edge=None, east_edge=None, stream=None, scheme="opencl"):
         self._h = None
+        self.scheme = scheme
         self.nx, self.ny = int(nx), int(ny)
         self.dtype = np.dtype(dtype)
         if self.dtype not in (np.dtype(np.float32), np.dtype(np.float64)):
@@ -64,6 +69,8 @@ class Lattice:
         cfg.x_offset = int(x_offset)
         cfg.west_edge = _EDGE[west_edge or default_edge]
         cfg.east_edge = _EDGE[east_edge or default_edge]
+        cfg.scheme = _SCHEME[scheme]
+        cfg.reserved0 = 0
         cfg.omega, cfg.inlet_rho, cfg.outlet_rho = float(omega), float(inlet_rho), float(outlet_rho)
         cfg.cs2, cfg.cs22, cfg.two_cs4 = float(cs2), float(cs22), float(two_cs4)
         cfg.stream = ct.c_void_p(stream) if stream else None
@@ -125,15 +132,23 @@ class Lattice:
 
     def upload_moments(self, rho=None, u=None, v=None):
         arrs = []
-        for a in (rho, u, v):
+        for k, a in enumerate((rho, u, v)):
             if a is None:
                 arrs.append(None)
                 continue
-            b = np.ascontiguousarray(a, dtype=self.dtype)
+            b = np.ascontiguousarray(a, dtype=self.dtype if k == 0 else self.uv_dtype)
             if b.shape != (self.ny, self.nx):
                 raise ValueError("moment fields must have shape (ny, nx)")
             arrs.append(b)
         self._call("lb_upload_moments", *[(_ptr(a) if a is not None else None) for a in arrs])
+
+    @property
+    def uv_dtype(self):
+        """dtype of the u / v fields: float64 for the cython schemes (as in the reference)."""
+        return self.dtype if self.scheme == "opencl" else np.dtype(np.float64)
+
+    def field_dtype(self, field):
+        return self.uv_dtype if field in ("u", "v") else self.dtype
 
     # -- the hot path -----------------------------------------------------------------
     def run(self, n, sync=True):
@@ -149,10 +164,11 @@ class Lattice:
     def download(self, field, out=None):
         """Device layout array of `field` in {'f','feq','rho','u','v'}."""
         shape = (9, self.ny, self.nx) if field in ("f", "feq") else (self.ny, self.nx)
+        dt = self.field_dtype(field)
         if out is None:
-            out = np.empty(shape, dtype=self.dtype)
+            out = np.empty(shape, dtype=dt)
         else:
-            if out.shape != shape or out.dtype != self.dtype or not out.flags.c_contiguous:
+            if out.shape != shape or out.dtype != dt or not out.flags.c_contiguous:
                 raise ValueError("out must be a C-contiguous array of the field's shape and dtype")
         self._call("lb_download", _FIELD[field], _ptr(out))
         return out

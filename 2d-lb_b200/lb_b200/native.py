@@ -18,7 +18,8 @@ WEST, EAST = 0, 1
 EDGE_BOUNDARY, EDGE_WRAP, EDGE_HALO = 0, 1, 2
 SYNTH_PIPE_RAMP, SYNTH_SHEAR_LAYERS = 0, 1
 IPC_HANDLE_BYTES = 64
-ABI_VERSION = 1
+ABI_VERSION = 2
+SCHEME_OPENCL, SCHEME_CYTHON, SCHEME_CYTHON_OLD = 0, 1, 2
 
 # every symbol include/lb_d2q9.h declares (tests/test_abi.py checks the library exports them all)
 SYMBOLS = [
@@ -48,6 +49,7 @@ class LBConfig(ct.Structure):
         ("zero_obstacle_velocity", ct.c_int32),
         ("global_nx", ct.c_int32), ("x_offset", ct.c_int32),
         ("west_edge", ct.c_int32), ("east_edge", ct.c_int32),
+        ("scheme", ct.c_int32), ("reserved0", ct.c_int32),
         ("omega", ct.c_double), ("inlet_rho", ct.c_double), ("outlet_rho", ct.c_double),
         ("cs2", ct.c_double), ("cs22", ct.c_double), ("two_cs4", ct.c_double),
         ("stream", ct.c_void_p),

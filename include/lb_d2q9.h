@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define LB_ABI_VERSION 1
+#define LB_ABI_VERSION 2
 
 typedef struct lb_sim lb_sim; /* opaque */
 
@@ -56,6 +56,18 @@ enum lb_bc { LB_BC_PIPE = 0, LB_BC_PERIODIC = 1 };
  *   LB_MATH_FAST    same formulas with reciprocal constants and FMA; agrees
  *                   with STRICT to rounding (tolerances in tests/). */
 enum lb_math { LB_MATH_STRICT = 0, LB_MATH_FAST = 1 };
+
+/* Which of the reference's two step algorithms the handle runs.
+ *   LB_SCHEME_OPENCL      stream -> BCs -> moments -> feq -> collide, D2Q9.cl driven by
+ *                         dimensionless/opencl_dim.py:372-387 (the path being replaced; default).
+ *   LB_SCHEME_CYTHON      BCs (from the previous step's u) -> stream -> moments (+boundary
+ *                         overrides) -> feq -> collide, dimensionless/cython_dim.pyx:346-359, with
+ *                         NumPy's mixed float32/float64 arithmetic.  Bit-identical to the compiled
+ *                         reference.  dtype must be LB_F32, bc LB_BC_PIPE, single slab; the u and v
+ *                         fields are float64 (as in the reference), rho/f/feq float32.
+ *   LB_SCHEME_CYTHON_OLD  the same for LB_D2Q9/OLD/cython.pyx (no wall zeroing of u,v; omega and
+ *                         inlet_rho are Python floats there, so those expressions are float32). */
+enum lb_scheme { LB_SCHEME_OPENCL = 0, LB_SCHEME_CYTHON = 1, LB_SCHEME_CYTHON_OLD = 2 };
 
 enum lb_field {
     LB_FIELD_F = 0,    /* [9][ny][nx] post-collision populations (opencl_dim.py:394-395) */
@@ -89,6 +101,8 @@ typedef struct lb_config {
     int32_t x_offset;      /* global x of local column 0 */
     int32_t west_edge;     /* lb_edge */
     int32_t east_edge;     /* lb_edge */
+    int32_t scheme;        /* lb_scheme */
+    int32_t reserved0;     /* must be 0 */
     /* physics: opencl_dim.py:118 (omega), :273-274 (inlet/outlet rho), :26-30 (lattice constants,
        passed in so that they are the very doubles the host computed) */
     double omega, inlet_rho, outlet_rho;

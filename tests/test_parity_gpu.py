@@ -315,3 +315,88 @@ def test_real_multi_gpu_slabs_bit_identical(gpu):
     print(res.stdout[-3000:])
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert "PASS" in res.stdout
+
+
+# ------------------------------------------------------------------------------------------------
+# scheme 'cython' (SURVEY.md 8f-1): the CUDA path against vectors made by the UNMODIFIED reference
+# ------------------------------------------------------------------------------------------------
+def _yx(a):
+    return np.ascontiguousarray(a.transpose(0, 2, 1) if a.ndim == 3 else a.T)
+
+
+@pytest.mark.parametrize("name,scheme", [("cython_pipe_65x33.npz", "cython"),
+                                         ("cython_cylinder_121x41.npz", "cython"),
+                                         ("old_obstacles_49x25.npz", "cython_old")])
+def test_cython_scheme_matches_reference_golden_bitexact(gpu, name, scheme):
+    """Populations, density and velocity after 1, 10 and 100 steps are BIT-IDENTICAL to what the
+    compiled reference (cython_dim.pyx / OLD/cython.pyx) produced from the same initial state."""
+    import os
+    from lb_b200 import Lattice
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name))
+    nx, ny = int(g["nx"]), int(g["ny"])
+    mask = _yx(g["mask"]) if "mask" in g.files else None
+    with Lattice(nx, ny, float(g["omega"]), float(g["inlet_rho"]), float(g["outlet_rho"]), mask=mask,
+                 dtype=np.float32, scheme=scheme) as sim:
+        sim.upload_moments(_yx(g["rho_0"]), _yx(g["u_0"]), _yx(g["v_0"]))
+        sim.upload_f(_yx(g["f_0"]))
+        done = 0
+        for s in g["steps"]:
+            sim.run(int(s) - done)          # several run() calls: exercises the pre-stream prologue too
+            done = int(s)
+            assert np.array_equal(sim.download("f"), _yx(g[f"f_{s}"])), f"f after {s} steps"
+            assert np.array_equal(sim.download("rho"), _yx(g[f"rho_{s}"])), f"rho after {s} steps"
+            u = sim.download("u")
+            assert u.dtype == np.float64
+            assert np.array_equal(u, _yx(g[f"u_{s}"])), f"u after {s} steps"
+            assert np.array_equal(sim.download("v"), _yx(g[f"v_{s}"])), f"v after {s} steps"
+
+
+def test_cython_classes_match_live_reference(gpu, orc):
+    """Same seed, same constructor arguments: lb_b200.cython_api on the GPU vs the compiled reference
+    classes on the CPU (oracle/_ref), 300 steps, bit for bit; falls back to the pinned C restatement
+    when oracle/_ref is not present."""
+    from lb_b200 import cython_api
+    from oracle import refload
+    kw = dict(diameter=1., rho=1., viscosity=0.05, pressure_grad=-1., pipe_length=1.5, N=24, time_prefactor=4.)
+    np.random.seed(7)
+    mine = cython_api.Pipe_Flow(verbose=False, **kw)
+    f0, u0, v0 = mine.f, mine.u, mine.v
+    if refload.available():
+        np.random.seed(7)
+        with refload.quiet():
+            ref = refload.cython_dim().Pipe_Flow(**kw)
+        assert (ref.nx, ref.ny) == (mine.nx, mine.ny)
+        assert ref.omega == mine.omega and ref.inlet_rho == mine.inlet_rho
+        assert np.array_equal(np.asarray(ref.f), f0), "initial populations differ"
+        ref.run(300)
+        want_f, want_u, want_rho = np.asarray(ref.f), np.asarray(ref.u), np.asarray(ref.rho)
+    else:
+        o = orc.CythonSchemeOracle(_yx(f0), _yx(u0), _yx(v0), mine.omega, mine.inlet_rho, mine.outlet_rho)
+        o.run(300)
+        want_f, want_u, want_rho = _yx(o.f), _yx(o.u), _yx(o.rho)
+    mine.run(300)
+    assert np.array_equal(mine.f, want_f)
+    assert np.array_equal(mine.u, want_u)
+    assert np.array_equal(mine.rho, want_rho)
+
+    ckw = dict(cylinder_center=[0.75, 0.5], cylinder_radius=0.1, diameter=1., rho=1., viscosity=1., pressure_grad=-10.,
+               pipe_length=3., N=6)
+    np.random.seed(8)
+    cyl = cython_api.Pipe_Flow_Cylinder(verbose=False, **ckw)
+    f0, u0, v0 = cyl.f, cyl.u, cyl.v
+    if refload.available():
+        np.random.seed(8)
+        with refload.quiet():
+            ref = refload.cython_dim().Pipe_Flow_Cylinder(**ckw)
+        assert np.array_equal(np.asarray(ref.obstacle_mask), cyl.obstacle_mask)
+        assert np.array_equal(np.asarray(ref.f), f0)
+        ref.run(150)
+        want_f, want_u = np.asarray(ref.f), np.asarray(ref.u)
+    else:
+        o = orc.CythonSchemeOracle(_yx(f0), _yx(u0), _yx(v0), cyl.omega, cyl.inlet_rho, cyl.outlet_rho,
+                                   mask=_yx(cyl.obstacle_mask))
+        o.run(150)
+        want_f, want_u = _yx(o.f), _yx(o.u)
+    cyl.run(150)
+    assert np.array_equal(cyl.f, want_f)
+    assert np.array_equal(cyl.u, want_u)
