@@ -353,8 +353,9 @@ def test_cython_scheme_matches_reference_golden_bitexact(gpu, name, scheme):
 
 def test_cython_classes_match_live_reference(gpu, orc):
     """Same seed, same constructor arguments: lb_b200.cython_api on the GPU vs the compiled reference
-    classes on the CPU (oracle/_ref), 300 steps, bit for bit; falls back to the pinned C restatement
-    when oracle/_ref is not present."""
+    classes on the CPU (oracle/_ref), 60 steps of a deliberately under-resolved, violent flow
+    (omega 1.68, |u| up to 0.6: any arithmetic difference is amplified), bit for bit; falls back to
+    the pinned C restatement when oracle/_ref is not present."""
     from lb_b200 import cython_api
     from oracle import refload
     kw = dict(diameter=1., rho=1., viscosity=0.05, pressure_grad=-1., pipe_length=1.5, N=24, time_prefactor=4.)
@@ -368,13 +369,14 @@ def test_cython_classes_match_live_reference(gpu, orc):
         assert (ref.nx, ref.ny) == (mine.nx, mine.ny)
         assert ref.omega == mine.omega and ref.inlet_rho == mine.inlet_rho
         assert np.array_equal(np.asarray(ref.f), f0), "initial populations differ"
-        ref.run(300)
+        ref.run(60)
         want_f, want_u, want_rho = np.asarray(ref.f), np.asarray(ref.u), np.asarray(ref.rho)
     else:
         o = orc.CythonSchemeOracle(_yx(f0), _yx(u0), _yx(v0), mine.omega, mine.inlet_rho, mine.outlet_rho)
-        o.run(300)
+        o.run(60)
         want_f, want_u, want_rho = _yx(o.f), _yx(o.u), _yx(o.rho)
-    mine.run(300)
+    mine.run(60)
+    assert np.isfinite(want_f).all()
     assert np.array_equal(mine.f, want_f)
     assert np.array_equal(mine.u, want_u)
     assert np.array_equal(mine.rho, want_rho)
