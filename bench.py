@@ -42,7 +42,7 @@ WORKLOADS = {
     "c4": dict(desc="cylinder wake 32768x32768 fp32, x-slab strong scaling", nx=32768, ny=32768, dtype="f32",
                bc="pipe", scaling="strong", omega=1.7, inlet_rho=1.003, init="pipe_ramp", mask="disk"),
     "c2": dict(desc="Pipe_Flow_Obstacles 4096x1024 fp32 with obstacle mask", nx=4096, ny=1024, dtype="f32",
-               bc="pipe", scaling="strong", omega=1.0, inlet_rho=1.01, init="pipe_ramp", mask="disk", zero_vel=True),
+               bc="pipe", scaling="strong", omega=1.0, inlet_rho=1.01, init="pipe_ramp", mask="cs205", zero_vel=True),
     "c3": dict(desc="periodic vortex-sheet (Kelvin-Helmholtz) 16384x16384 fp32", nx=16384, ny=16384, dtype="f32",
                bc="periodic", scaling="strong", omega=1.7, inlet_rho=1.0, init="shear_layers", mask=None),
     "c5": dict(desc="weak-scaling channel flow 16384x16384 per GPU, fp64", nx=16384, ny=16384, dtype="f64",
@@ -285,6 +285,12 @@ def main():
         lat.set_variant(args.variant)
     if wl["mask"] == "disk":
         lat.set_mask_disk(gnx / 4.0, gny / 2.0, gny / 10.0)
+    elif wl["mask"] == "cs205":
+        # docs/cs205_binary.tif of the reference (bit-packed fixture), nearest-neighbour resampled
+        # to the lattice: mask[x, y] = src[x*800//nx, y*400//ny]   
+        from lb_b200 import masks
+        src = masks.unpack(np.load(os.path.join(ROOT, "tests", "golden", "cs205_binary_mask.npz")))
+        slab.set_mask(np.ascontiguousarray(masks.resample(src, gnx, gny).T))
     lat.init_synthetic(wl["init"], u0=0.05, amplitude=1e-3, seed=2015)
     slab.prime()
     cells_global = gnx * gny

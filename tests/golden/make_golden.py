@@ -80,6 +80,14 @@ def main():
     d = record(sim, [1, 10, 100], dict(ctor_kwargs=repr(kw), seed=2, mask=mask.astype(np.uint8)))
     np.savez_compressed(os.path.join(OUT, "old_obstacles_49x25.npz"), **d)
 
+    # 4. docs/cs205_binary.tif (800x400 px, {0,255}): the obstacle of BASELINE config 2, as a bit-packed
+    #    (x, y) boolean mask.  No code in the reference loads this file; white = solid.
+    sys.path.insert(0, os.path.join(ROOT, "2d-lb_b200"))
+    from lb_b200 import masks
+    m = masks.from_image("/root/reference/docs/cs205_binary.tif")
+    assert m.shape == (800, 400) and 0.05 < m.mean() < 0.15
+    np.savez_compressed(os.path.join(OUT, "cs205_binary_mask.npz"), source="docs/cs205_binary.tif", **masks.pack(m))
+
     for n in sorted(os.listdir(OUT)):
         if n.endswith(".npz"):
             print(n, os.path.getsize(os.path.join(OUT, n)) // 1024, "KiB")

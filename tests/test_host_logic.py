@@ -127,3 +127,24 @@ def test_slab_rendezvous_gloo_world2(bc):
     else:
         assert r0[5] == {"west": (b"H019", 1), "east": (b"H019", 1)}
         assert r1[5] == {"west": (b"H000", 0), "east": (b"H000", 0)}
+
+
+def test_mask_ingestion(tmp_path):
+    """lb_b200.masks: image -> (nx, ny) bool, nearest-neighbour resampling, bit packing."""
+    from PIL import Image
+    from lb_b200 import masks
+    img = np.zeros((40, 80), np.uint8)            # (H, W), like a TIFF read by PIL
+    img[10:20, 30:50] = 255
+    path = tmp_path / "m.png"
+    Image.fromarray(img).save(path)
+    m = masks.from_image(str(path))
+    assert m.shape == (80, 40) and m.dtype == bool
+    assert m[30:50, 10:20].all() and m.sum() == 200
+    r = masks.resample(m, 160, 80)
+    assert r.shape == (160, 80) and r.sum() == 800 and r[60:100, 20:40].all()
+    assert np.array_equal(masks.resample(m, 80, 40), m)
+    assert np.array_equal(masks.unpack(masks.pack(m)), m)
+    g = np.load(os.path.join(ROOT, "tests", "golden", "cs205_binary_mask.npz"))
+    src = masks.unpack(g)
+    assert src.shape == (800, 400) and abs(src.mean() - 0.087) < 0.001      # SURVEY.md F7: 8.7 % solid
+    assert not (src[0].any() or src[-1].any() or src[:, 0].any() or src[:, -1].any())

@@ -284,15 +284,21 @@ def test_dimensionless_classes_match_oracle(gpu, orc):
 
 
 def test_c2_obstacles_4096x1024(gpu, orc):
-    """BASELINE config 2 shape (4096x1024 fp32 with an obstacle mask): 3 steps bit-exact in STRICT,
-    FAST within tolerance."""
-    from lb_b200 import Lattice
-    f0, m = pipe_case(orc, 4096, 1024, np.float32, mask="random", seed=11)
+    """BASELINE config 2: Pipe_Flow_Obstacles with the docs/cs205_binary.tif mask on 4096x1024, fp32
+    (mask fixture tests/golden/cs205_binary_mask.npz, resampled as SURVEY.md 8d says).  3 steps
+    bit-exact in STRICT, FAST within tolerance."""
+    import os
+    from lb_b200 import Lattice, masks
+    src = masks.unpack(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cs205_binary_mask.npz")))
+    m = np.ascontiguousarray(masks.resample(src, 4096, 1024).T).astype(np.uint8)
+    assert 0.08 < m.mean() < 0.095
+    f0, _ = pipe_case(orc, 4096, 1024, np.float32, seed=11)
     ref = orc.OpenCLSchemeOracle(f0, 1.0, 1.01, 1.0, mask=m, zero_obstacle_velocity=True)
     ref.run(3)
     with Lattice(4096, 1024, 1.0, 1.01, 1.0, mask=m, f0=f0, math="strict", zero_obstacle_velocity=True) as sim:
         sim.run(3)
         assert np.array_equal(sim.download("f"), ref.f)
+        assert np.array_equal(sim.download("u"), ref.u)
     with Lattice(4096, 1024, 1.0, 1.01, 1.0, mask=m, f0=f0, math="fast", zero_obstacle_velocity=True) as sim:
         sim.run(3)
         assert np.abs(sim.download("f") - ref.f).max() <= 1e-6
