@@ -90,12 +90,12 @@ static int fail(lb_sim *s, int code, const std::string &msg)
 // =====================================================================================
 struct Variant {
     const char *name;
-    int dtype, math, V, WX, WY, R;
+    int dtype, math, model, V, WX, WY, R;
     void (*launch)(const StepParams &, cudaStream_t);
     bool is_default;
 };
 
-template <typename T, int V, int MATH, int WX, int WY, int R, int MINB, int LDP, int STP>
+template <typename T, int V, int MATH, int WX, int WY, int R, int MINB, int LDP, int STP, int MODEL = MODEL_D2Q9>
 static void launch_variant(const StepParams &p_in, cudaStream_t st)
 {
     StepParams p = p_in;
@@ -114,12 +114,16 @@ static void launch_variant(const StepParams &p_in, cudaStream_t st)
         const unsigned gy = p.tiles_y < 65535 ? p.tiles_y : 65535;
         grid = dim3((unsigned)p.tiles_x, gy, ((unsigned)p.tiles_y + gy - 1) / gy);
     }
-    fused_step_kernel<T, V, MATH, WX, WY, R, MINB, LDP, STP><<<grid, 32 * WX * WY, 0, st>>>(p);
+    fused_step_kernel<T, V, MATH, WX, WY, R, MINB, LDP, STP, MODEL><<<grid, 32 * WX * WY, 0, st>>>(p);
 }
 
 #define VAR(T, TN, DT, V, M, MN, WX, WY, R, MINB, LDP, STP, DEF)                                    \
-    {TN "." MN ".v" #V ".wx" #WX ".wy" #WY ".r" #R ".b" #MINB ".ld" #LDP ".st" #STP, DT, M, V, WX,  \
-     WY, R, &launch_variant<T, V, M, WX, WY, R, MINB, LDP, STP>, DEF}
+    {TN "." MN ".v" #V ".wx" #WX ".wy" #WY ".r" #R ".b" #MINB ".ld" #LDP ".st" #STP, DT, M, MODEL_D2Q9, V, \
+     WX, WY, R, &launch_variant<T, V, M, WX, WY, R, MINB, LDP, STP>, DEF}
+// incompressible model (D2Q9i.cl): the default tile configuration only
+#define VARI(T, TN, DT, V, M, MN)                                                                   \
+    {TN "." MN ".d2q9i.v" #V ".wx2.wy2.r1.b6.ld1.st0", DT, M, MODEL_D2Q9I, V, 2, 2, 1,               \
+     &launch_variant<T, V, M, 2, 2, 1, 6, 1, 0, MODEL_D2Q9I>, true}
 
 #define VARS_FOR(T, TN, DT, VMAX, VHALF)                                                            \
     VAR(T, TN, DT, VMAX, MATH_FAST, "fast", 2, 2, 1, 6, 1, 0, true),                                \
@@ -149,13 +153,16 @@ static void launch_variant(const StepParams &p_in, cudaStream_t st)
 static const Variant g_variants[] = {
     VARS_FOR(float, "f32", LB_F32, 4, 2),
     VARS_FOR(double, "f64", LB_F64, 2, 1),
+    VARI(float, "f32", LB_F32, 4, MATH_STRICT, "strict"), VARI(float, "f32", LB_F32, 4, MATH_FAST, "fast"),
+    VARI(double, "f64", LB_F64, 2, MATH_STRICT, "strict"), VARI(double, "f64", LB_F64, 2, MATH_FAST, "fast"),
 };
 static const int g_nvariants = (int)(sizeof(g_variants) / sizeof(g_variants[0]));
 
-static int default_variant(int dtype, int math)
+static int default_variant(int dtype, int math, int model)
 {
     for (int i = 0; i < g_nvariants; ++i)
-        if (g_variants[i].dtype == dtype && g_variants[i].math == math && g_variants[i].is_default) return i;
+        if (g_variants[i].dtype == dtype && g_variants[i].math == math && g_variants[i].model == model &&
+            g_variants[i].is_default) return i;
     return -1;
 }
 
@@ -164,13 +171,14 @@ static int default_variant(int dtype, int math)
 // =====================================================================================
 template <typename T>
 __global__ void k_feq_from_moments(int nx, int ny, int pitch, long long plane, const T *rho, const T *u,
-                                   const T *v, T *feq, Consts<T> c)
+                                   const T *v, T *feq, Consts<T> c, int model)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= nx || y >= ny) return;
     const long long i = (long long)y * pitch + x;
     T e[9];
-    feq_strict<T>(c, rho[i], u[i], v[i], e);
+    if (model == MODEL_D2Q9I) feq_strict_i<T>(c, rho[i], u[i], v[i], e);
+    else feq_strict<T>(c, rho[i], u[i], v[i], e);
 #pragma unroll
     for (int j = 0; j < 9; ++j) feq[j * plane + i] = e[j];
 }
@@ -198,7 +206,7 @@ __global__ void k_stage_move(int nx, int ny, int pitch, long long plane, int per
 
 template <typename T>
 __global__ void k_stage_bcs(int nx, int ny, int pitch, long long plane, int gnx, int x_off, int do_pipe,
-                            const uint8_t *mask, int mask_pitch, T *f, Consts<T> c)
+                            const uint8_t *mask, int mask_pitch, T *f, Consts<T> c, int model)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= nx || y >= ny) return;
@@ -210,14 +218,17 @@ __global__ void k_stage_bcs(int nx, int ny, int pitch, long long plane, int gnx,
     T g[9];
 #pragma unroll
     for (int j = 0; j < 9; ++j) g[j] = f[j * plane + i];
-    if (bnd) pipe_bc<T>(c, gx, y, gnx, ny, g);
+    if (bnd) {
+        if (model == MODEL_D2Q9I) pipe_bc<T, MODEL_D2Q9I>(c, gx, y, gnx, ny, g);
+        else pipe_bc<T, MODEL_D2Q9>(c, gx, y, gnx, ny, g);
+    }
     if (solid) bounce_back<T>(g);
 #pragma unroll
     for (int j = 0; j < 9; ++j) f[j * plane + i] = g[j];
 }
 
 template <typename T>
-__global__ void k_stage_hydro(int nx, int ny, int pitch, long long plane, const T *f, T *rho, T *u, T *v)
+__global__ void k_stage_hydro(int nx, int ny, int pitch, long long plane, const T *f, T *rho, T *u, T *v, int model)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= nx || y >= ny) return;
@@ -226,7 +237,8 @@ __global__ void k_stage_hydro(int nx, int ny, int pitch, long long plane, const 
 #pragma unroll
     for (int j = 0; j < 9; ++j) g[j] = f[j * plane + i];
     T r, a, b;
-    moments<T, MATH_STRICT>(g, r, a, b);
+    if (model == MODEL_D2Q9I) moments<T, MATH_STRICT, MODEL_D2Q9I>(g, r, a, b);
+    else moments<T, MATH_STRICT, MODEL_D2Q9>(g, r, a, b);
     rho[i] = r; u[i] = a; v[i] = b;
 }
 
@@ -249,6 +261,14 @@ __global__ void k_zero_velocity(int nx, int ny, int pitch, const uint8_t *mask, 
         u[(long long)y * pitch + x] = (T)0;
         v[(long long)y * pitch + x] = (T)0;
     }
+}
+
+template <typename T>
+__global__ void k_subsample(int nx, int ny, int pitch, int sx, int sy, int ox, const T *src, T *dst)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+    if (i >= ox) return;
+    dst[(long long)j * ox + i] = src[(long long)(j * sy) * pitch + (long long)i * sx];
 }
 
 // one flag byte per 32 cells of a row: does the group contain a solid node
@@ -291,7 +311,7 @@ __device__ __forceinline__ double normal01(unsigned long long seed, unsigned lon
 template <typename T>
 __global__ void k_init_synth(int nx, int ny, int pitch, long long plane, int gnx, int x_off, int kind, double u0,
                              double amplitude, unsigned long long seed, double inlet_rho, double outlet_rho,
-                             const uint8_t *mask, int mask_pitch, T *f0, T *f1, T *rho, T *u, T *v, Consts<T> c)
+                             const uint8_t *mask, int mask_pitch, T *f0, T *f1, T *rho, T *u, T *v, Consts<T> c, int model)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= nx || y >= ny) return;
@@ -310,7 +330,8 @@ __global__ void k_init_synth(int nx, int ny, int pitch, long long plane, int gnx
     if (mask && mask[(long long)y * mask_pitch + x] == 1) { a = (T)0; b = (T)0; }
     rho[i] = r; u[i] = a; v[i] = b;
     T e[9];
-    feq_strict<T>(c, r, a, b, e);
+    if (model == MODEL_D2Q9I) feq_strict_i<T>(c, r, a, b, e);
+    else feq_strict<T>(c, r, a, b, e);
     const unsigned long long cell = (unsigned long long)y * (unsigned long long)gnx + (unsigned long long)gx;
 #pragma unroll
     for (int j = 0; j < 9; ++j) {
@@ -481,8 +502,11 @@ int lb_create(const lb_config *cfg, lb_sim **out)
     if (cfg->global_nx < cfg->nx || cfg->x_offset < 0 || cfg->x_offset + cfg->nx > cfg->global_nx)
         return fail(nullptr, LB_ERR_INVALID, "lb_create: slab does not fit the global lattice");
     if (!(cfg->omega > 0.0 && cfg->omega < 2.0)) return fail(nullptr, LB_ERR_INVALID, "lb_create: omega must be in (0,2)");
-    if (cfg->scheme < LB_SCHEME_OPENCL || cfg->scheme > LB_SCHEME_CYTHON_OLD || cfg->reserved0 != 0)
+    if (cfg->scheme < LB_SCHEME_OPENCL || cfg->scheme > LB_SCHEME_CYTHON_OLD)
         return fail(nullptr, LB_ERR_INVALID, "lb_create: bad scheme");
+    if (cfg->model != LB_MODEL_D2Q9 && cfg->model != LB_MODEL_D2Q9I) return fail(nullptr, LB_ERR_INVALID, "lb_create: bad model");
+    if (cfg->model == LB_MODEL_D2Q9I && (cfg->scheme != LB_SCHEME_OPENCL || cfg->bc != LB_BC_PIPE))
+        return fail(nullptr, LB_ERR_INVALID, "lb_create: the D2Q9i model exists for LB_SCHEME_OPENCL pipe flow only");
     if (cfg->scheme != LB_SCHEME_OPENCL &&
         (cfg->dtype != LB_F32 || cfg->bc != LB_BC_PIPE || cfg->west_edge != LB_EDGE_BOUNDARY ||
          cfg->east_edge != LB_EDGE_BOUNDARY || cfg->global_nx != cfg->nx))
@@ -501,7 +525,7 @@ int lb_create(const lb_config *cfg, lb_sim **out)
     const int per512 = 512 / sim->elem;
     sim->pitch = (cfg->nx + per512 - 1) / per512 * per512;
     sim->plane = (long long)sim->pitch * cfg->ny;
-    sim->variant = default_variant(cfg->dtype, cfg->math);
+    sim->variant = default_variant(cfg->dtype, cfg->math, cfg->model);
     auto bail = [&](int code, const std::string &m) { g_create_error = m; lb_destroy(sim); return code; };
 #define CUC(call)                                                                                  \
     do {                                                                                           \
@@ -555,9 +579,10 @@ int lb_destroy(lb_sim *sim)
 int lb_set_variant(lb_sim *sim, int variant)
 {
     if (!sim) return LB_ERR_INVALID;
-    if (variant < 0) variant = default_variant(sim->cfg.dtype, sim->cfg.math);
-    if (variant >= g_nvariants || g_variants[variant].dtype != sim->cfg.dtype || g_variants[variant].math != sim->cfg.math)
-        return fail(sim, LB_ERR_INVALID, "lb_set_variant: variant does not match the handle's dtype/math");
+    if (variant < 0) variant = default_variant(sim->cfg.dtype, sim->cfg.math, sim->cfg.model);
+    if (variant >= g_nvariants || g_variants[variant].dtype != sim->cfg.dtype || g_variants[variant].math != sim->cfg.math ||
+        g_variants[variant].model != sim->cfg.model)
+        return fail(sim, LB_ERR_INVALID, "lb_set_variant: variant does not match the handle's dtype/math/model");
     sim->variant = variant;
     return LB_OK;
 }
@@ -668,10 +693,10 @@ static int compute_feq(lb_sim *sim)
             (const double *)sim->u, (const double *)sim->v, (float *)sim->feq, cy_consts_of(sim));
     else if (sim->cfg.dtype == LB_F32)
         k_feq_from_moments<float><<<grid2d(sim), 128, 0, sim->stream>>>(nx, ny, sim->pitch, sim->plane, (const float *)sim->rho,
-            (const float *)sim->u, (const float *)sim->v, (float *)sim->feq, consts_of<float>(sim));
+            (const float *)sim->u, (const float *)sim->v, (float *)sim->feq, consts_of<float>(sim), sim->cfg.model);
     else
         k_feq_from_moments<double><<<grid2d(sim), 128, 0, sim->stream>>>(nx, ny, sim->pitch, sim->plane, (const double *)sim->rho,
-            (const double *)sim->u, (const double *)sim->v, (double *)sim->feq, consts_of<double>(sim));
+            (const double *)sim->u, (const double *)sim->v, (double *)sim->feq, consts_of<double>(sim), sim->cfg.model);
     CU(cudaGetLastError());
     return LB_OK;
 }
@@ -803,6 +828,26 @@ int lb_download(lb_sim *sim, int field, void *host_out)
     return lb_sync(sim);
 }
 
+int lb_download_strided(lb_sim *sim, int field, int stride_x, int stride_y, void *host_out)
+{
+    if (!sim || !host_out) return fail(sim, LB_ERR_INVALID, "lb_download_strided: null argument");
+    if (stride_x < 1 || stride_y < 1) return fail(sim, LB_ERR_INVALID, "lb_download_strided: strides must be >= 1");
+    const void *src = field == LB_FIELD_RHO ? sim->rho : field == LB_FIELD_U ? sim->u : field == LB_FIELD_V ? sim->v : nullptr;
+    if (!src) return fail(sim, LB_ERR_INVALID, "lb_download_strided: field must be rho, u or v");
+    CU(cudaSetDevice(sim->cfg.device));
+    const int eb = field == LB_FIELD_RHO ? sim->elem : sim->uv_elem;
+    const int ox = (sim->cfg.nx + stride_x - 1) / stride_x, oy = (sim->cfg.ny + stride_y - 1) / stride_y;
+    void *tmp = nullptr;
+    CU(cudaMallocAsync(&tmp, (size_t)ox * oy * eb, sim->stream));
+    const dim3 grid((ox + 127) / 128, oy);
+    if (eb == 4) k_subsample<float><<<grid, 128, 0, sim->stream>>>(sim->cfg.nx, sim->cfg.ny, sim->pitch, stride_x, stride_y, ox, (const float *)src, (float *)tmp);
+    else k_subsample<double><<<grid, 128, 0, sim->stream>>>(sim->cfg.nx, sim->cfg.ny, sim->pitch, stride_x, stride_y, ox, (const double *)src, (double *)tmp);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(host_out, tmp, (size_t)ox * oy * eb, cudaMemcpyDeviceToHost, sim->stream));
+    CU(cudaFreeAsync(tmp, sim->stream));
+    return lb_sync(sim);
+}
+
 void *lb_stream(lb_sim *sim) { return sim ? (void *)sim->stream : nullptr; }
 
 int lb_device_ptr(lb_sim *sim, int field, void **ptr, int64_t *pitch_elems)
@@ -846,7 +891,7 @@ int lb_stage_move_bcs(lb_sim *sim)
     if (sim->cfg.scheme != LB_SCHEME_OPENCL) return fail(sim, LB_ERR_STATE, "lb_stage_move_bcs: single stages exist for LB_SCHEME_OPENCL only");
     CU(cudaSetDevice(sim->cfg.device));
     DISPATCH(k_stage_bcs, grid2d(sim), sim->cfg.nx, sim->cfg.ny, sim->pitch, sim->plane, sim->cfg.global_nx, sim->cfg.x_offset,
-             sim->cfg.bc == LB_BC_PIPE, sim->mask, sim->mask_pitch, (T *)sim->buf[sim->cur], consts_of<T>(sim));
+             sim->cfg.bc == LB_BC_PIPE, sim->mask, sim->mask_pitch, (T *)sim->buf[sim->cur], consts_of<T>(sim), sim->cfg.model);
     return LB_OK;
 }
 
@@ -856,7 +901,7 @@ int lb_stage_update_hydro(lb_sim *sim)
     if (sim->cfg.scheme != LB_SCHEME_OPENCL) return fail(sim, LB_ERR_STATE, "lb_stage_update_hydro: single stages exist for LB_SCHEME_OPENCL only");
     CU(cudaSetDevice(sim->cfg.device));
     DISPATCH(k_stage_hydro, grid2d(sim), sim->cfg.nx, sim->cfg.ny, sim->pitch, sim->plane, (const T *)sim->buf[sim->cur],
-             (T *)sim->rho, (T *)sim->u, (T *)sim->v);
+             (T *)sim->rho, (T *)sim->u, (T *)sim->v, sim->cfg.model);
     if (sim->cfg.zero_obstacle_velocity && sim->mask) return lb_stage_zero_velocity(sim);
     return LB_OK;
 }
@@ -903,7 +948,7 @@ int lb_init_synthetic(lb_sim *sim, int kind, double u0, double amplitude, uint64
     CU(cudaSetDevice(sim->cfg.device));
     DISPATCH(k_init_synth, grid2d(sim), sim->cfg.nx, sim->cfg.ny, sim->pitch, sim->plane, sim->cfg.global_nx, sim->cfg.x_offset, kind,
              u0, amplitude, (unsigned long long)seed, sim->cfg.inlet_rho, sim->cfg.outlet_rho, sim->mask, sim->mask_pitch,
-             (T *)sim->buf[sim->cur], (T *)sim->buf[sim->cur ^ 1], (T *)sim->rho, (T *)sim->u, (T *)sim->v, consts_of<T>(sim));
+             (T *)sim->buf[sim->cur], (T *)sim->buf[sim->cur ^ 1], (T *)sim->rho, (T *)sim->u, (T *)sim->v, consts_of<T>(sim), sim->cfg.model);
     return LB_OK;
 }
 

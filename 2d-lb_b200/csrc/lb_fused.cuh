@@ -143,7 +143,7 @@ __device__ __forceinline__ void wait_flag(const unsigned int *flag, unsigned int
 }
 
 // ---- the fused kernel -----------------------------------------------------------------
-template <typename T, int V, int MATH, int WX, int WY, int R, int MINB, int LDP, int STP>
+template <typename T, int V, int MATH, int WX, int WY, int R, int MINB, int LDP, int STP, int MODEL = MODEL_D2Q9>
 __global__ void __launch_bounds__(32 * WX * WY, MINB) fused_step_kernel(const StepParams p)
 {
     constexpr int SPAN = 32 * V;
@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(32 * WX * WY, MINB) fused_step_kernel(const St
                     T g[9];
 #pragma unroll
                     for (int j = 0; j < 9; ++j) g[j] = q[j].v[e];
-                    pipe_bc<T>(c, p.x_off + x0 + e, y, p.gnx, ny, g);
+                    pipe_bc<T, MODEL>(c, p.x_off + x0 + e, y, p.gnx, ny, g);
 #pragma unroll
                     for (int j = 0; j < 9; ++j) q[j].v[e] = g[j];
                 }
@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(32 * WX * WY, MINB) fused_step_kernel(const St
                 T g[9];
 #pragma unroll
                 for (int j = 0; j < 9; ++j) g[j] = q[j].v[e];
-                collide_node<T, MATH>(c, g, mrho.v[e], mu.v[e], mv.v[e], (zero_bits >> e) & 1u);
+                collide_node<T, MATH, MODEL>(c, g, mrho.v[e], mu.v[e], mv.v[e], (zero_bits >> e) & 1u);
 #pragma unroll
                 for (int j = 0; j < 9; ++j) q[j].v[e] = g[j];
             }

@@ -41,6 +41,7 @@ class Lattice:
            oracle, and HBM-bound like 'fast') or 'fast' (FMA + reciprocal constants, ~30% fewer
            instructions, agrees to rounding)
     dtype  np.float32 (the reference's precision) or np.float64
+    model  'd2q9' (D2Q9.cl) or 'd2q9i' (the incompressible variant D2Q9i.cl; scheme 'opencl', pipe flow)
     scheme 'opencl' (default: the step order of opencl_dim.py), 'cython' or
            'cython_old' (the reference's CPU classes, cython_dim.pyx / OLD/cython.pyx, including
            their mixed-precision arithmetic; float32 populations, float64 u and v)
@@ -48,7 +49,8 @@ class Lattice:
 
     def __init__(self, nx, ny, omega, inlet_rho=1.0, outlet_rho=1.0, mask=None, f0=None, bc="pipe",
                  dtype=np.float32, math="strict", device=0, zero_obstacle_velocity=False,
-                 global_nx=None, x_offset=0, west_edge=None, east_edge=None, stream=None, scheme="opencl"):
+                 global_nx=None, x_offset=0, west_edge=None, east_edge=None, stream=None, scheme="opencl",
+                 model="d2q9"):
         self._h = None
         self.scheme = scheme
         self.nx, self.ny = int(nx), int(ny)
@@ -70,7 +72,8 @@ class Lattice:
         cfg.west_edge = _EDGE[west_edge or default_edge]
         cfg.east_edge = _EDGE[east_edge or default_edge]
         cfg.scheme = _SCHEME[scheme]
-        cfg.reserved0 = 0
+        cfg.model = {"d2q9": N.MODEL_D2Q9, "d2q9i": N.MODEL_D2Q9I}[model]
+        self.model = model
         cfg.omega, cfg.inlet_rho, cfg.outlet_rho = float(omega), float(inlet_rho), float(outlet_rho)
         cfg.cs2, cfg.cs22, cfg.two_cs4 = float(cs2), float(cs22), float(two_cs4)
         cfg.stream = ct.c_void_p(stream) if stream else None
@@ -171,6 +174,17 @@ class Lattice:
             if out.shape != shape or out.dtype != dt or not out.flags.c_contiguous:
                 raise ValueError("out must be a C-contiguous array of the field's shape and dtype")
         self._call("lb_download", _FIELD[field], _ptr(out))
+        return out
+
+    def download_strided(self, field, stride_x, stride_y=None):
+        """Every stride_x-th column / stride_y-th row of rho, u or v (gathered on the device): frames for
+        long visual runs without a full-field copy per frame."""
+        stride_y = stride_x if stride_y is None else stride_y
+        if field not in ("rho", "u", "v"):
+            raise ValueError("download_strided serves rho, u and v")
+        out = np.empty(((self.ny + stride_y - 1) // stride_y, (self.nx + stride_x - 1) // stride_x),
+                       dtype=self.field_dtype(field))
+        self._call("lb_download_strided", _FIELD[field], int(stride_x), int(stride_y), _ptr(out))
         return out
 
     def fields(self):

@@ -20,11 +20,12 @@ SYNTH_PIPE_RAMP, SYNTH_SHEAR_LAYERS = 0, 1
 IPC_HANDLE_BYTES = 64
 ABI_VERSION = 2
 SCHEME_OPENCL, SCHEME_CYTHON, SCHEME_CYTHON_OLD = 0, 1, 2
+MODEL_D2Q9, MODEL_D2Q9I = 0, 1
 
 # every symbol include/lb_d2q9.h declares (tests/test_abi.py checks the library exports them all)
 SYMBOLS = [
     "lb_abi_version", "lb_device_count", "lb_create", "lb_destroy", "lb_last_error",
-    "lb_set_mask", "lb_upload_f", "lb_upload_moments", "lb_step", "lb_sync", "lb_download",
+    "lb_set_mask", "lb_upload_f", "lb_upload_moments", "lb_step", "lb_sync", "lb_download", "lb_download_strided",
     "lb_stage_move", "lb_stage_move_bcs", "lb_stage_update_hydro", "lb_stage_update_feq",
     "lb_stage_collide", "lb_stage_zero_velocity", "lb_init_synthetic", "lb_set_mask_disk",
     "lb_total_mass", "lb_launch_count", "lb_set_variant", "lb_variant_count", "lb_variant_name",
@@ -49,7 +50,7 @@ class LBConfig(ct.Structure):
         ("zero_obstacle_velocity", ct.c_int32),
         ("global_nx", ct.c_int32), ("x_offset", ct.c_int32),
         ("west_edge", ct.c_int32), ("east_edge", ct.c_int32),
-        ("scheme", ct.c_int32), ("reserved0", ct.c_int32),
+        ("scheme", ct.c_int32), ("model", ct.c_int32),
         ("omega", ct.c_double), ("inlet_rho", ct.c_double), ("outlet_rho", ct.c_double),
         ("cs2", ct.c_double), ("cs22", ct.c_double), ("two_cs4", ct.c_double),
         ("stream", ct.c_void_p),
@@ -73,6 +74,7 @@ def _declare(lib):
         "lb_step": (i, [vp, i]),
         "lb_sync": (i, [vp]),
         "lb_download": (i, [vp, i, vp]),
+        "lb_download_strided": (i, [vp, i, i, i, vp]),
         "lb_stage_move": (i, [vp]),
         "lb_stage_move_bcs": (i, [vp]),
         "lb_stage_update_hydro": (i, [vp]),

