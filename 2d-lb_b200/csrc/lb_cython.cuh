@@ -31,9 +31,15 @@ struct CyConsts {
     float rin_f, rout_f;           // cdef float inlet_rho / outlet_rho      (:227-228)
     float keep_f, om_f;            // OLD flavour: omega is a Python float -> float32 relaxation
     float w0, w1, w2;
+    // velocity-inlet / y-periodic family (OLD/cython.pyx:268-360)
+    double u_w, u_e;               // Python floats self.u_w, self.u_e
+    float u_w_f, u_e_f;            // `cdef float u_w, u_e` in move_bcs (:283-284)
+    double kw_d, ke_d;             // 1./(1.-u_w), 1./(1.+u_e) with the float u_w / u_e (C code, :295, :302)
+    float kw_f, ke_f;              // the same factors as NumPy's float32 scalars in update_hydro (:355, :358)
 };
 
-inline CyConsts make_cy_consts(double omega, double rin, double rout, double cs2, double cs22)
+inline CyConsts make_cy_consts(double omega, double rin, double rout, double cs2, double cs22,
+                               double u_w = 0.0, double u_e = 0.0)
 {
     CyConsts c;
     c.omega = omega; c.keep = 1. - omega;
@@ -45,6 +51,10 @@ inline CyConsts make_cy_consts(double omega, double rin, double rout, double cs2
     c.rin_f = (float)rin; c.rout_f = (float)rout;
     c.keep_f = (float)c.keep; c.om_f = (float)omega;
     c.w0 = (float)(4. / 9.); c.w1 = (float)(1. / 9.); c.w2 = (float)(1. / 36.);
+    c.u_w = u_w; c.u_e = u_e;
+    c.u_w_f = (float)u_w; c.u_e_f = (float)u_e;
+    c.kw_d = 1. / (1. - (double)c.u_w_f); c.ke_d = 1. / (1. + (double)c.u_e_f);
+    c.kw_f = (float)(1. / (1. - u_w)); c.ke_f = (float)(1. / (1. + u_e));
     return c;
 }
 
@@ -98,6 +108,49 @@ __device__ __forceinline__ void cy_prestream_bc(const CyConsts &c, int x, int y,
         g[3] = f1; g[4] = f2; g[7] = f5;
         g[6] = (float)(.5 * t); g[8] = g[6];
     }
+}
+
+// ---- velocity-inlet closure of one node (OLD/cython.pyx:291-303): inlet / outlet nodes with
+//      1 <= y < ly only; the row exchange of :305-316 is folded into the pull (see the kernel).
+__device__ __forceinline__ void cyv_prestream_bc(const CyConsts &c, int x, int y, int lx, int ly, float (&g)[9])
+{
+    if (y < 1 || y >= ly) return;
+    const float f0 = g[0], f1 = g[1], f2 = g[2], f3 = g[3], f4 = g[4], f5 = g[5], f6 = g[6], f7 = g[7], f8 = g[8];
+    if (x == 0) {
+        const float rho_w = (float)(c.kw_d * ((double)((f0 + f2) + f4) + 2. * (double)((f3 + f6) + f7)));
+        g[1] = (float)((double)f3 + ((2. / 3.) * (double)rho_w) * (double)c.u_w_f);
+        g[5] = (float)(((double)f7 - (1. / 2.) * (double)(f2 - f4)) + ((1. / 6.) * (double)rho_w) * (double)c.u_w_f);
+        g[8] = (float)(((double)f6 + (1. / 2.) * (double)(f2 - f4)) + ((1. / 6.) * (double)rho_w) * (double)c.u_w_f);
+    } else if (x == lx) {
+        const float rho_e = (float)(c.ke_d * ((double)((f0 + f2) + f4) + 2. * (double)((f1 + f5) + f8)));
+        g[3] = (float)((double)f1 - ((2. / 3.) * (double)rho_e) * (double)c.u_e_f);
+        g[7] = (float)(((double)f5 + (1. / 2.) * (double)(f2 - f4)) - ((1. / 6.) * (double)rho_e) * (double)c.u_e_f);
+        g[6] = (float)(((double)f8 - (1. / 2.) * (double)(f2 - f4)) - ((1. / 6.) * (double)rho_e) * (double)c.u_e_f);
+    }
+}
+
+// ---- moments of the velocity-inlet class (OLD/cython.pyx:331-360, :375-378) ---------------------
+__device__ __forceinline__ void cyv_moments(const CyConsts &c, const float (&g)[9], int x, int y, int lx, int ly,
+                                            bool solid, float &rho, double &u, double &v)
+{
+    float r = g[0];
+#pragma unroll
+    for (int j = 1; j < 9; ++j) r = r + g[j];
+    const float inv = 1.0f / r;
+    u = (double)((((((g[1] - g[3]) + g[5]) - g[6]) - g[7]) + g[8]) * inv);
+    v = (double)((((((g[5] + g[2]) + g[6]) - g[7]) - g[4]) - g[8]) * inv);
+    rho = r;
+    if (y >= 1 && y < ly) {
+        if (x == 0) {
+            u = c.u_w;
+            rho = c.kw_f * (((g[0] + g[2]) + g[4]) + 2.0f * ((g[3] + g[6]) + g[7]));
+        }
+        if (x == lx) {
+            u = c.u_e;
+            rho = c.ke_f * (((g[0] + g[2]) + g[4]) + 2.0f * ((g[1] + g[5]) + g[8]));
+        }
+    }
+    if (solid) { u = 0.0; v = 0.0; }
 }
 
 // ---- moments with the boundary overrides (cython_dim.pyx:302-333, :459-466) -------------------
@@ -178,7 +231,7 @@ __global__ void cy_feq_kernel(int nx, int ny, int pitch, long long plane, const 
 
 // BC + obstacle swap in place, from the stored u (start of a run; cython_dim.pyx:204-269, :486-513)
 __global__ void cy_prestream_kernel(int nx, int ny, int pitch, long long plane, float *f, const double *u,
-                                    const uint8_t *mask, int mask_pitch, CyConsts c)
+                                    const uint8_t *mask, int mask_pitch, CyConsts c, int velocity_inlet)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= nx || y >= ny) return;
@@ -189,14 +242,21 @@ __global__ void cy_prestream_kernel(int nx, int ny, int pitch, long long plane, 
     float g[9];
 #pragma unroll
     for (int j = 0; j < 9; ++j) g[j] = f[j * plane + i];
-    if (bnd) cy_prestream_bc(c, x, y, nx - 1, ny - 1, u[i], g);
+    if (bnd) {
+        if (velocity_inlet) cyv_prestream_bc(c, x, y, nx - 1, ny - 1, g);
+        else cy_prestream_bc(c, x, y, nx - 1, ny - 1, u[i], g);
+    }
     if (solid) bounce_back<float>(g);
 #pragma unroll
     for (int j = 0; j < 9; ++j) f[j * plane + i] = g[j];
 }
 
 // ---- the fused step -------------------------------------------------------------------------
-template <bool OLD, int WX, int WY, int MINB>
+// VIN = true: OLD/cython.pyx's velocity-inlet / y-periodic family.  Its row exchange
+// (f4,f8,f7 of row ly <- row 0 ; f2,f6,f5 of row 0 <- row ly, before streaming) is folded into the
+// pull: a population that would be read from row ly (0) after the exchange is read from row 0 (ly)
+// of the stored field instead -- a warp-uniform change of the source row.
+template <bool OLD, bool VIN, int WX, int WY, int MINB>
 __global__ void __launch_bounds__(32 * WX * WY, MINB) fused_step_cython_kernel(const CyParams p)
 {
     constexpr int V = 4, SPAN = 32 * V;
@@ -213,9 +273,11 @@ __global__ void __launch_bounds__(32 * WX * WY, MINB) fused_step_cython_kernel(c
     const int nx = p.nx, ny = p.ny, pitch = p.pitch, lx = nx - 1, ly = ny - 1;
     const CyConsts &c = p.c;
     const long long rc = (long long)y * pitch + x0;
+    const int ym = (VIN && y == 1) ? ly : y - 1;          // row read by populations 2,5,6
+    const int yp = (VIN && y == ly - 1) ? 0 : y + 1;      // row read by populations 4,7,8
     const float *pc = src + rc;
-    const float *pm = src + (rc - pitch) + 2 * plane;
-    const float *pp = src + (rc + pitch) + 4 * plane;
+    const float *pm = src + ((long long)ym * pitch + x0) + 2 * plane;
+    const float *pp = src + ((long long)yp * pitch + x0) + 4 * plane;
 
     Pack<float, V> q[9];
     q[0] = load_pack<float, V, 1>(pc);
@@ -255,7 +317,14 @@ __global__ void __launch_bounds__(32 * WX * WY, MINB) fused_step_cython_kernel(c
     if (on_boundary) {
         Pack<float, V> own[9];
 #pragma unroll
-        for (int j = 1; j < 9; ++j) own[j] = load_pack<float, V, 1>(src + j * plane + rc);
+        for (int j = 1; j < 9; ++j) {
+            long long ro = rc;
+            if (VIN) {                                     // the node's own value AFTER the row exchange
+                if (y == 0 && (j == 2 || j == 6 || j == 5)) ro = (long long)ly * pitch + x0;
+                if (y == ly && (j == 4 || j == 8 || j == 7)) ro = x0;
+            }
+            own[j] = load_pack<float, V, 1>(src + j * plane + ro);
+        }
 #pragma unroll
         for (int e = 0; e < V; ++e) {
             const int x = x0 + e;
@@ -290,10 +359,14 @@ __global__ void __launch_bounds__(32 * WX * WY, MINB) fused_step_cython_kernel(c
 #pragma unroll
         for (int j = 0; j < 9; ++j) g[j] = q[j].v[e];
         const bool solid = (solid_bits >> e) & 1u;
-        cy_moments<OLD>(c, g, x, y, lx, ly, solid, mrho[e], mu[e], mv[e]);
+        if (VIN) cyv_moments(c, g, x, y, lx, ly, solid, mrho[e], mu[e], mv[e]);
+        else cy_moments<OLD>(c, g, x, y, lx, ly, solid, mrho[e], mu[e], mv[e]);
         cy_collide<OLD>(c, g, mrho[e], mu[e], mv[e]);
         if (p.apply_next_bc) {
-            if (on_boundary && x <= lx) cy_prestream_bc(c, x, y, lx, ly, mu[e], g);
+            if (on_boundary && x <= lx) {
+                if (VIN) cyv_prestream_bc(c, x, y, lx, ly, g);
+                else cy_prestream_bc(c, x, y, lx, ly, mu[e], g);
+            }
             if (solid) bounce_back<float>(g);
         }
 #pragma unroll

@@ -401,7 +401,8 @@ static Consts<T> consts_of(const lb_sim *s)
 
 static CyConsts cy_consts_of(const lb_sim *s)
 {
-    return make_cy_consts(s->cfg.omega, s->cfg.inlet_rho, s->cfg.outlet_rho, s->cfg.cs2, s->cfg.cs22);
+    return make_cy_consts(s->cfg.omega, s->cfg.inlet_rho, s->cfg.outlet_rho, s->cfg.cs2, s->cfg.cs22,
+                          s->cfg.u_west, s->cfg.u_east);
 }
 
 static void drop_graphs(lb_sim *s)
@@ -490,13 +491,16 @@ int lb_create(const lb_config *cfg, lb_sim **out)
         return fail(nullptr, LB_ERR_INVALID, "lb_create: lb_config size mismatch (ABI)");
     if (cfg->nx < 2 || cfg->ny < 2) return fail(nullptr, LB_ERR_INVALID, "lb_create: nx, ny must be >= 2");
     if (cfg->dtype != LB_F32 && cfg->dtype != LB_F64) return fail(nullptr, LB_ERR_INVALID, "lb_create: bad dtype");
-    if (cfg->bc != LB_BC_PIPE && cfg->bc != LB_BC_PERIODIC) return fail(nullptr, LB_ERR_INVALID, "lb_create: bad bc");
+    if (cfg->bc != LB_BC_PIPE && cfg->bc != LB_BC_PERIODIC && cfg->bc != LB_BC_VELOCITY_YPERIODIC)
+        return fail(nullptr, LB_ERR_INVALID, "lb_create: bad bc");
+    if (cfg->bc == LB_BC_VELOCITY_YPERIODIC && (cfg->scheme != LB_SCHEME_CYTHON_OLD || cfg->ny < 4))
+        return fail(nullptr, LB_ERR_INVALID, "lb_create: LB_BC_VELOCITY_YPERIODIC needs LB_SCHEME_CYTHON_OLD and ny >= 4");
     if (cfg->math != LB_MATH_STRICT && cfg->math != LB_MATH_FAST) return fail(nullptr, LB_ERR_INVALID, "lb_create: bad math");
     for (int e : {cfg->west_edge, cfg->east_edge}) {
         if (e < LB_EDGE_BOUNDARY || e > LB_EDGE_HALO) return fail(nullptr, LB_ERR_INVALID, "lb_create: bad edge kind");
         if (cfg->bc == LB_BC_PERIODIC && e == LB_EDGE_BOUNDARY)
             return fail(nullptr, LB_ERR_INVALID, "lb_create: a periodic box needs WRAP or HALO edges");
-        if (cfg->bc == LB_BC_PIPE && e == LB_EDGE_WRAP)
+        if (cfg->bc != LB_BC_PERIODIC && e == LB_EDGE_WRAP)
             return fail(nullptr, LB_ERR_INVALID, "lb_create: pipe flow cannot wrap in x");
     }
     if (cfg->global_nx < cfg->nx || cfg->x_offset < 0 || cfg->x_offset + cfg->nx > cfg->global_nx)
@@ -508,7 +512,7 @@ int lb_create(const lb_config *cfg, lb_sim **out)
     if (cfg->model == LB_MODEL_D2Q9I && (cfg->scheme != LB_SCHEME_OPENCL || cfg->bc != LB_BC_PIPE))
         return fail(nullptr, LB_ERR_INVALID, "lb_create: the D2Q9i model exists for LB_SCHEME_OPENCL pipe flow only");
     if (cfg->scheme != LB_SCHEME_OPENCL &&
-        (cfg->dtype != LB_F32 || cfg->bc != LB_BC_PIPE || cfg->west_edge != LB_EDGE_BOUNDARY ||
+        (cfg->dtype != LB_F32 || cfg->bc == LB_BC_PERIODIC || cfg->west_edge != LB_EDGE_BOUNDARY ||
          cfg->east_edge != LB_EDGE_BOUNDARY || cfg->global_nx != cfg->nx))
         return fail(nullptr, LB_ERR_INVALID, "lb_create: the cython schemes need dtype F32, bc PIPE and a single slab");
     int ndev = 0;
@@ -610,6 +614,10 @@ int lb_set_mask(lb_sim *sim, const void *host_mask, int elem_bytes)
         const int32_t *m = (const int32_t *)host_mask;
         for (size_t i = 0; i < packed.size(); ++i) packed[i] = (m[i] == 1) ? 1 : 0;
     }
+    if (sim->cfg.bc == LB_BC_VELOCITY_YPERIODIC)
+        for (int x = 0; x < nx; ++x)
+            if (packed[x] || packed[(size_t)(ny - 1) * nx + x])
+                return fail(sim, LB_ERR_INVALID, "lb_set_mask: with LB_BC_VELOCITY_YPERIODIC the exchanged rows y=0 and y=ny-1 must be free of solid nodes");
     if (!sim->mask) {
         sim->mask_pitch = sim->pitch;
         sim->nspans = sim->pitch / 32;
@@ -709,7 +717,8 @@ static int cython_steps(lb_sim *sim, int n_steps)
     const CyConsts c = cy_consts_of(sim);
     if (!sim->prestream_done) {
         cy_prestream_kernel<<<grid2d(sim), 128, 0, sim->stream>>>(nx, ny, sim->pitch, sim->plane, (float *)sim->buf[sim->cur],
-                                                                   (const double *)sim->u, sim->mask, sim->mask_pitch, c);
+                                                                   (const double *)sim->u, sim->mask, sim->mask_pitch, c,
+                                                                   sim->cfg.bc == LB_BC_VELOCITY_YPERIODIC);
         CU(cudaGetLastError());
     }
     constexpr int WX = 2, WY = 2;
@@ -726,8 +735,9 @@ static int cython_steps(lb_sim *sim, int n_steps)
         p.mask = sim->mask; p.mask_pitch = sim->mask_pitch;
         p.rho = (float *)sim->rho; p.u = (double *)sim->u; p.v = (double *)sim->v;
         p.c = c;
-        if (sim->cfg.scheme == LB_SCHEME_CYTHON_OLD) fused_step_cython_kernel<true, WX, WY, 4><<<grid, 32 * WX * WY, 0, sim->stream>>>(p);
-        else fused_step_cython_kernel<false, WX, WY, 4><<<grid, 32 * WX * WY, 0, sim->stream>>>(p);
+        if (sim->cfg.bc == LB_BC_VELOCITY_YPERIODIC) fused_step_cython_kernel<true, true, WX, WY, 4><<<grid, 32 * WX * WY, 0, sim->stream>>>(p);
+        else if (sim->cfg.scheme == LB_SCHEME_CYTHON_OLD) fused_step_cython_kernel<true, false, WX, WY, 4><<<grid, 32 * WX * WY, 0, sim->stream>>>(p);
+        else fused_step_cython_kernel<false, false, WX, WY, 4><<<grid, 32 * WX * WY, 0, sim->stream>>>(p);
         CU(cudaGetLastError());
         sim->launches++;
         sim->cur ^= 1; sim->state_index++;

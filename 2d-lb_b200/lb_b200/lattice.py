@@ -18,7 +18,7 @@ cs2 = cs ** 2
 cs22 = 2 * cs2
 two_cs4 = 2 * cs ** 4
 
-_BC = {"pipe": N.BC_PIPE, "periodic": N.BC_PERIODIC}
+_BC = {"pipe": N.BC_PIPE, "periodic": N.BC_PERIODIC, "velocity_yperiodic": N.BC_VELOCITY_YPERIODIC}
 _MATH = {"strict": N.MATH_STRICT, "fast": N.MATH_FAST}
 _EDGE = {"boundary": N.EDGE_BOUNDARY, "wrap": N.EDGE_WRAP, "halo": N.EDGE_HALO}
 _SCHEME = {"opencl": N.SCHEME_OPENCL, "cython": N.SCHEME_CYTHON, "cython_old": N.SCHEME_CYTHON_OLD}
@@ -36,7 +36,8 @@ class Lattice:
     obstacle mask, populations) rather than the physical parameters of the simulation
     classes; `lb_b200.dimensionless` builds on this.
 
-    bc     'pipe' (pressure inlet/outlet + walls, D2Q9.cl:173-261) or 'periodic'
+    bc     'pipe' (pressure inlet/outlet + walls, D2Q9.cl:173-261), 'periodic', or 'velocity_yperiodic'
+           (imposed inlet/outlet velocity u_west/u_east, rows 0 and ny-1 exchanged; scheme 'cython_old')
     math   'strict' (default: D2Q9.cl's arithmetic operation for operation, bit-identical to the CPU
            oracle, and HBM-bound like 'fast') or 'fast' (FMA + reciprocal constants, ~30% fewer
            instructions, agrees to rounding)
@@ -50,7 +51,7 @@ class Lattice:
     def __init__(self, nx, ny, omega, inlet_rho=1.0, outlet_rho=1.0, mask=None, f0=None, bc="pipe",
                  dtype=np.float32, math="strict", device=0, zero_obstacle_velocity=False,
                  global_nx=None, x_offset=0, west_edge=None, east_edge=None, stream=None, scheme="opencl",
-                 model="d2q9"):
+                 model="d2q9", u_west=0.0, u_east=0.0):
         self._h = None
         self.scheme = scheme
         self.nx, self.ny = int(nx), int(ny)
@@ -76,6 +77,7 @@ class Lattice:
         self.model = model
         cfg.omega, cfg.inlet_rho, cfg.outlet_rho = float(omega), float(inlet_rho), float(outlet_rho)
         cfg.cs2, cfg.cs22, cfg.two_cs4 = float(cs2), float(cs22), float(two_cs4)
+        cfg.u_west, cfg.u_east = float(u_west), float(u_east)
         cfg.stream = ct.c_void_p(stream) if stream else None
         self.cfg = cfg
         self.omega, self.inlet_rho, self.outlet_rho = cfg.omega, cfg.inlet_rho, cfg.outlet_rho

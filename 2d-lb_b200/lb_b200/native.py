@@ -11,14 +11,14 @@ LIB_PATH = os.path.join(os.path.dirname(_PKG), "csrc", "liblb_d2q9.so")
 
 # enums of lb_d2q9.h
 F32, F64 = 0, 1
-BC_PIPE, BC_PERIODIC = 0, 1
+BC_PIPE, BC_PERIODIC, BC_VELOCITY_YPERIODIC = 0, 1, 2
 MATH_STRICT, MATH_FAST = 0, 1
 FIELD_F, FIELD_FEQ, FIELD_RHO, FIELD_U, FIELD_V = 0, 1, 2, 3, 4
 WEST, EAST = 0, 1
 EDGE_BOUNDARY, EDGE_WRAP, EDGE_HALO = 0, 1, 2
 SYNTH_PIPE_RAMP, SYNTH_SHEAR_LAYERS = 0, 1
 IPC_HANDLE_BYTES = 64
-ABI_VERSION = 2
+ABI_VERSION = 3
 SCHEME_OPENCL, SCHEME_CYTHON, SCHEME_CYTHON_OLD = 0, 1, 2
 MODEL_D2Q9, MODEL_D2Q9I = 0, 1
 
@@ -53,6 +53,7 @@ class LBConfig(ct.Structure):
         ("scheme", ct.c_int32), ("model", ct.c_int32),
         ("omega", ct.c_double), ("inlet_rho", ct.c_double), ("outlet_rho", ct.c_double),
         ("cs2", ct.c_double), ("cs22", ct.c_double), ("two_cs4", ct.c_double),
+        ("u_west", ct.c_double), ("u_east", ct.c_double),
         ("stream", ct.c_void_p),
     ]
 

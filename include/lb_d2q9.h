@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define LB_ABI_VERSION 2
+#define LB_ABI_VERSION 3
 
 typedef struct lb_sim lb_sim; /* opaque */
 
@@ -46,8 +46,16 @@ enum lb_dtype { LB_F32 = 0, LB_F64 = 1 };
  *   LB_BC_PIPE      pressure (Zou-He) inlet x=0 / outlet x=nx-1, walls y=0 / y=ny-1,
  *                   four corner closures -- D2Q9.cl:173-261 (`move_bcs`).
  *   LB_BC_PERIODIC  doubly periodic box -- rocket_yeast.cl:152-191 /
- *                   multi.cl:330-369 (`move_periodic`). */
-enum lb_bc { LB_BC_PIPE = 0, LB_BC_PERIODIC = 1 };
+ *                   multi.cl:330-369 (`move_periodic`).
+ *   LB_BC_VELOCITY_YPERIODIC  see below. */
+enum lb_bc {
+    LB_BC_PIPE = 0,
+    LB_BC_PERIODIC = 1,
+    /* imposed x-velocity u_west / u_east at inlet / outlet (Zou-He), rows y=0 and y=ny-1 exchange
+     * their incoming populations -- LB_D2Q9/OLD/cython.pyx:268-360 (Pipe_Flow_PeriodicBC_VelocityInlet,
+     * the CPU twin of D2Q9.cl:263-374).  Available with LB_SCHEME_CYTHON_OLD. */
+    LB_BC_VELOCITY_YPERIODIC = 2
+};
 
 /* Arithmetic contract of the fused kernel.
  *   LB_MATH_STRICT  mirrors D2Q9.cl operation by operation (association order,
@@ -113,6 +121,7 @@ typedef struct lb_config {
        passed in so that they are the very doubles the host computed) */
     double omega, inlet_rho, outlet_rho;
     double cs2, cs22, two_cs4;
+    double u_west, u_east; /* LB_BC_VELOCITY_YPERIODIC: imposed inlet / outlet x-velocity */
     void *stream;          /* cudaStream_t to enqueue on; NULL = the handle creates its own */
 } lb_config;
 

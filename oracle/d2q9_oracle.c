@@ -63,6 +63,10 @@ typedef struct {
     int nx, ny;
     double omega, inlet_rho, outlet_rho;
     double cs2, cs22, cssq;      /* cs**2, 2*cs2, 2.0/9.0  (cython_dim.pyx:20-23) */
+    int velocity_inlet;          /* 1: OLD/cython.pyx Pipe_Flow_PeriodicBC_VelocityInlet (:268-360): imposed
+                                    x-velocity u_w / u_e at inlet / outlet, rows y=0 and y=ly exchange their
+                                    incoming populations ("periodic"), no wall or corner closure */
+    double u_w, u_e;             /* Python floats in the reference */
     int old_api;                 /* 1: LB_D2Q9/OLD/cython.pyx flavour -- no wall zeroing in update_hydro
                                     (OLD/cython.pyx:126-149), and omega / inlet_rho are plain Python floats
                                     there ("weak" under NEP 50), so the inlet velocity and the relaxation
@@ -285,15 +289,83 @@ void oracle_cy_collide(const cy_params *p, float *f, const float *feq)
     for (size_t i = 0; i < n; ++i) f[i] = (float)((double)f[i] * keep + om * (double)feq[i]);
 }
 
+/* OLD/cython.pyx:278-316 -- Pipe_Flow_PeriodicBC_VelocityInlet.move_bcs.  Typed-memoryview code:
+ * C arithmetic, double literals, `cdef float u_w, u_e`, rho_w / rho_e stored as float. */
+void oracle_cyv_move_bcs(const cy_params *p, float *f)
+{
+    const int nx = p->nx, ny = p->ny, lx = nx - 1, ly = ny - 1;
+    const size_t plane = (size_t)nx * ny;
+    const float u_w = (float)p->u_w, u_e = (float)p->u_e;
+    for (int y = 1; y < ly; ++y) {
+        {
+            const float f0 = f[IDX(0, 0, y)], f2 = f[IDX(2, 0, y)], f3 = f[IDX(3, 0, y)], f4 = f[IDX(4, 0, y)];
+            const float f6 = f[IDX(6, 0, y)], f7 = f[IDX(7, 0, y)];
+            const float rho_w = (float)((1. / (1. - (double)u_w)) * ((double)((f0 + f2) + f4) + 2. * (double)((f3 + f6) + f7)));
+            f[IDX(1, 0, y)] = (float)((double)f3 + ((2. / 3.) * (double)rho_w) * (double)u_w);
+            f[IDX(5, 0, y)] = (float)(((double)f7 - (1. / 2.) * (double)(f2 - f4)) + ((1. / 6.) * (double)rho_w) * (double)u_w);
+            f[IDX(8, 0, y)] = (float)(((double)f6 + (1. / 2.) * (double)(f2 - f4)) + ((1. / 6.) * (double)rho_w) * (double)u_w);
+        }
+        {
+            const float f0 = f[IDX(0, lx, y)], f1 = f[IDX(1, lx, y)], f2 = f[IDX(2, lx, y)], f4 = f[IDX(4, lx, y)];
+            const float f5 = f[IDX(5, lx, y)], f8 = f[IDX(8, lx, y)];
+            const float rho_e = (float)((1. / (1. + (double)u_e)) * ((double)((f0 + f2) + f4) + 2. * (double)((f1 + f5) + f8)));
+            f[IDX(3, lx, y)] = (float)((double)f1 - ((2. / 3.) * (double)rho_e) * (double)u_e);
+            f[IDX(7, lx, y)] = (float)(((double)f5 + (1. / 2.) * (double)(f2 - f4)) - ((1. / 6.) * (double)rho_e) * (double)u_e);
+            f[IDX(6, lx, y)] = (float)(((double)f8 - (1. / 2.) * (double)(f2 - f4)) - ((1. / 6.) * (double)rho_e) * (double)u_e);
+        }
+    }
+    for (int x = 0; x <= lx; ++x) {            /* :305-316, north then south, in this order per column */
+        f[IDX(4, x, ly)] = f[IDX(4, x, 0)];
+        f[IDX(8, x, ly)] = f[IDX(8, x, 0)];
+        f[IDX(7, x, ly)] = f[IDX(7, x, 0)];
+        f[IDX(2, x, 0)] = f[IDX(2, x, ly)];
+        f[IDX(6, x, 0)] = f[IDX(6, x, ly)];
+        f[IDX(5, x, 0)] = f[IDX(5, x, ly)];
+    }
+}
+
+/* OLD/cython.pyx:331-360 -- update_hydro of the velocity-inlet class (NumPy: u_w is a Python float,
+ * so the rho expressions are float32) (+ :375-378 mask zeroing in the Obstacles variant) */
+void oracle_cyv_update_hydro(const cy_params *p, const float *f, float *rho, double *u, double *v,
+                             const uint8_t *mask)
+{
+    const int nx = p->nx, ny = p->ny, lx = nx - 1, ly = ny - 1;
+    const size_t plane = (size_t)nx * ny;
+    for (size_t c = 0; c < plane; ++c) {
+        float g[9];
+        for (int j = 0; j < 9; ++j) g[j] = f[(size_t)j * plane + c];
+        float r = g[0];
+        for (int j = 1; j < 9; ++j) r = r + g[j];
+        rho[c] = r;
+        const float inv = 1.0f / r;
+        u[c] = (double)((((((g[1] - g[3]) + g[5]) - g[6]) - g[7]) + g[8]) * inv);
+        v[c] = (double)((((((g[5] + g[2]) + g[6]) - g[7]) - g[4]) - g[8]) * inv);
+    }
+    const float kw = (float)(1. / (1. - p->u_w)), ke = (float)(1. / (1. + p->u_e));
+    for (int y = 1; y < ly; ++y) {
+        u[(size_t)y * nx + 0] = p->u_w;
+        rho[(size_t)y * nx + 0] = kw * (((f[IDX(0, 0, y)] + f[IDX(2, 0, y)]) + f[IDX(4, 0, y)]) +
+                                        2.0f * ((f[IDX(3, 0, y)] + f[IDX(6, 0, y)]) + f[IDX(7, 0, y)]));
+        u[(size_t)y * nx + lx] = p->u_e;
+        rho[(size_t)y * nx + lx] = ke * (((f[IDX(0, lx, y)] + f[IDX(2, lx, y)]) + f[IDX(4, lx, y)]) +
+                                         2.0f * ((f[IDX(1, lx, y)] + f[IDX(5, lx, y)]) + f[IDX(8, lx, y)]));
+    }
+    if (mask)
+        for (size_t c = 0; c < plane; ++c)
+            if (mask[c]) { u[c] = 0; v[c] = 0; }
+}
+
 /* cython_dim.pyx:346-359 (+ :468-513).  scratch: 9*nx*ny floats. */
 void oracle_cy_run(const cy_params *p, int n_steps, float *f, float *feq, float *rho,
                    double *u, double *v, const uint8_t *mask, float *scratch)
 {
     for (int it = 0; it < n_steps; ++it) {
-        oracle_cy_move_bcs(p, f, u);
+        if (p->velocity_inlet) oracle_cyv_move_bcs(p, f);
+        else oracle_cy_move_bcs(p, f, u);
         if (mask) oracle_cy_bounceback(p, mask, f);
         oracle_cy_move(p, f, scratch);
-        oracle_cy_update_hydro(p, f, rho, u, v, mask);
+        if (p->velocity_inlet) oracle_cyv_update_hydro(p, f, rho, u, v, mask);
+        else oracle_cy_update_hydro(p, f, rho, u, v, mask);
         oracle_cy_update_feq(p, rho, u, v, feq);
         oracle_cy_collide(p, f, feq);
     }

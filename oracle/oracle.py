@@ -56,7 +56,8 @@ def _p(a):
 class CyParams(ct.Structure):
     _fields_ = [("nx", ct.c_int), ("ny", ct.c_int), ("omega", ct.c_double),
                 ("inlet_rho", ct.c_double), ("outlet_rho", ct.c_double),
-                ("cs2", ct.c_double), ("cs22", ct.c_double), ("cssq", ct.c_double), ("old_api", ct.c_int)]
+                ("cs2", ct.c_double), ("cs22", ct.c_double), ("cssq", ct.c_double),
+                ("velocity_inlet", ct.c_int), ("u_w", ct.c_double), ("u_e", ct.c_double), ("old_api", ct.c_int)]
 
 
 def feq_of(rho, u, v, dtype, incompressible=False):
@@ -147,10 +148,11 @@ class CythonSchemeOracle:
 
     f: (9, ny, nx) float32; u, v: (ny, nx) float64 (the lagged velocity the
     first move_bcs reads); mask: (ny, nx) bool or None.  old_api=True selects the
-    LB_D2Q9/OLD/cython.pyx flavour (see cy_params.old_api in d2q9_oracle.c).
+    LB_D2Q9/OLD/cython.pyx flavour (see cy_params.old_api in d2q9_oracle.c); velocity_inlet=(u_w, u_e)
+    additionally selects OLD's Pipe_Flow_PeriodicBC_VelocityInlet boundary family.
     """
 
-    def __init__(self, f0, u0, v0, omega, inlet_rho, outlet_rho, mask=None, old_api=False):
+    def __init__(self, f0, u0, v0, omega, inlet_rho, outlet_rho, mask=None, old_api=False, velocity_inlet=None):
         self.f = np.array(f0, dtype=np.float32, order="C", copy=True)
         _, self.ny, self.nx = self.f.shape
         self.u = np.array(u0, dtype=np.float64, order="C", copy=True)
@@ -160,7 +162,9 @@ class CythonSchemeOracle:
         self.scratch = np.zeros_like(self.f)
         self.mask = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
         self.p = CyParams(self.nx, self.ny, float(omega), float(inlet_rho), float(outlet_rho),
-                          float(cs2), float(cs22), float(cssq), int(bool(old_api)))
+                          float(cs2), float(cs22), float(cssq),
+                          int(velocity_inlet is not None), float((velocity_inlet or (0, 0))[0]),
+                          float((velocity_inlet or (0, 0))[1]), int(bool(old_api)))
 
     def run(self, n):
         lib().oracle_cy_run(ct.byref(self.p), ct.c_int(int(n)), _p(self.f), _p(self.feq), _p(self.rho),

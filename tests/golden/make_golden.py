@@ -80,6 +80,22 @@ def main():
     d = record(sim, [1, 10, 100], dict(ctor_kwargs=repr(kw), seed=2, mask=mask.astype(np.uint8)))
     np.savez_compressed(os.path.join(OUT, "old_obstacles_49x25.npz"), **d)
 
+    # 3b. OLD/cython velocity-inlet / y-periodic family, with and without obstacles
+    lx, ly = 60, 30
+    kw = dict(lx=lx, ly=ly, omega=1.3, deltaP=-0.0, u_w=0.05)
+    np.random.seed(3)
+    sim = old.Pipe_Flow_PeriodicBC_VelocityInlet(**kw)
+    d = record(sim, [1, 10, 100], dict(ctor_kwargs=repr(kw), seed=3, u_w=float(sim.u_w), u_e=float(sim.u_e)))
+    np.savez_compressed(os.path.join(OUT, "old_velocity_inlet_61x31.npz"), **d)
+    mask = np.zeros((lx + 1, ly + 1), dtype=bool)
+    mask[15:20, 10:18] = True
+    mask[40:44, 2:6] = True
+    np.random.seed(4)
+    sim = old.Pipe_Flow_Obstacles_PeriodicBC_VelocityInlet(obstacle_mask=mask, **kw)
+    d = record(sim, [1, 10, 100], dict(ctor_kwargs=repr(kw), seed=4, u_w=float(sim.u_w), u_e=float(sim.u_e),
+                                       mask=mask.astype(np.uint8)))
+    np.savez_compressed(os.path.join(OUT, "old_velocity_inlet_obstacles_61x31.npz"), **d)
+
     # 4. docs/cs205_binary.tif (800x400 px, {0,255}): the obstacle of BASELINE config 2, as a bit-packed
     #    (x, y) boolean mask.  No code in the reference loads this file; white = solid.
     sys.path.insert(0, os.path.join(ROOT, "2d-lb_b200"))

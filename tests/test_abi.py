@@ -28,7 +28,7 @@ def test_library_loads_and_reports_variants():
     assert L.lb_abi_version() == native.ABI_VERSION
     v = native.variants()
     assert any(n.startswith("f32.fast.") for n in v) and any(n.startswith("f64.strict.") for n in v)
-    assert ct.sizeof(native.LBConfig) == 112      # 14 x int32 + 6 x double + pointer
+    assert ct.sizeof(native.LBConfig) == 128      # 14 x int32 + 8 x double + pointer
 
 
 def test_no_device_means_loud_failure_not_fallback():

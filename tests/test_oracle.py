@@ -27,13 +27,15 @@ def _yx(a):
     return np.ascontiguousarray(a.transpose(0, 2, 1) if a.ndim == 3 else a.T)
 
 
-@pytest.mark.parametrize("name", ["cython_pipe_65x33.npz", "cython_cylinder_121x41.npz", "old_obstacles_49x25.npz"])
+@pytest.mark.parametrize("name", ["cython_pipe_65x33.npz", "cython_cylinder_121x41.npz", "old_obstacles_49x25.npz",
+                                  "old_velocity_inlet_61x31.npz", "old_velocity_inlet_obstacles_61x31.npz"])
 def test_cython_scheme_matches_reference_golden_bitexact(orc, name):
     g = _load(name)
     mask = _yx(g["mask"]) if "mask" in g.files else None
+    vin = (float(g["u_w"]), float(g["u_e"])) if "u_w" in g.files else None
     o = orc.CythonSchemeOracle(_yx(g["f_0"]), _yx(g["u_0"]), _yx(g["v_0"]), float(g["omega"]),
                                float(g["inlet_rho"]), float(g["outlet_rho"]), mask=mask,
-                               old_api=name.startswith("old_"))
+                               old_api=name.startswith("old_"), velocity_inlet=vin)
     done = 0
     for s in g["steps"]:
         o.run(int(s) - done)

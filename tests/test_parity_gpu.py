@@ -332,7 +332,9 @@ def _yx(a):
 
 @pytest.mark.parametrize("name,scheme", [("cython_pipe_65x33.npz", "cython"),
                                          ("cython_cylinder_121x41.npz", "cython"),
-                                         ("old_obstacles_49x25.npz", "cython_old")])
+                                         ("old_obstacles_49x25.npz", "cython_old"),
+                                         ("old_velocity_inlet_61x31.npz", "cython_old"),
+                                         ("old_velocity_inlet_obstacles_61x31.npz", "cython_old")])
 def test_cython_scheme_matches_reference_golden_bitexact(gpu, name, scheme):
     """Populations, density and velocity after 1, 10 and 100 steps are BIT-IDENTICAL to what the
     compiled reference (cython_dim.pyx / OLD/cython.pyx) produced from the same initial state."""
@@ -341,8 +343,9 @@ def test_cython_scheme_matches_reference_golden_bitexact(gpu, name, scheme):
     g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name))
     nx, ny = int(g["nx"]), int(g["ny"])
     mask = _yx(g["mask"]) if "mask" in g.files else None
+    extra = dict(bc="velocity_yperiodic", u_west=float(g["u_w"]), u_east=float(g["u_e"])) if "u_w" in g.files else {}
     with Lattice(nx, ny, float(g["omega"]), float(g["inlet_rho"]), float(g["outlet_rho"]), mask=mask,
-                 dtype=np.float32, scheme=scheme) as sim:
+                 dtype=np.float32, scheme=scheme, **extra) as sim:
         sim.upload_moments(_yx(g["rho_0"]), _yx(g["u_0"]), _yx(g["v_0"]))
         sim.upload_f(_yx(g["f_0"]))
         done = 0
@@ -476,3 +479,49 @@ def test_strided_download(gpu, orc):
             full = sim.download(field)
             assert np.array_equal(sim.download_strided(field, 4, 3), full[::3, ::4])
             assert np.array_equal(sim.download_strided(field, 1), full)
+
+
+def test_old_cython_classes_match_live_reference(gpu, orc):
+    """lb_b200.old_cython_api vs the compiled LB_D2Q9/OLD/cython.pyx classes (oracle/_ref), same
+    constructor arguments, bit for bit -- including the velocity-inlet / y-periodic family
+    (SURVEY.md 8f-2).  Falls back to the pinned C restatement without oracle/_ref."""
+    from lb_b200 import old_cython_api as mine_mod
+    from oracle import refload
+    lx, ly = 70, 36
+    mask = np.zeros((lx + 1, ly + 1), dtype=bool)
+    mask[20:27, 12:20] = True
+    cases = [("Pipe_Flow", dict(omega=1.1, lx=lx, ly=ly, deltaP=-0.02), None),
+             ("Pipe_Flow_Obstacles", dict(omega=1.1, lx=lx, ly=ly, deltaP=-0.02, obstacle_mask=mask), mask),
+             ("Pipe_Flow_PeriodicBC_VelocityInlet", dict(u_w=0.04, omega=1.2, lx=lx, ly=ly, deltaP=-0.0), None),
+             ("Pipe_Flow_Obstacles_PeriodicBC_VelocityInlet", dict(u_w=0.04, omega=1.2, lx=lx, ly=ly, deltaP=-0.0,
+                                                                  obstacle_mask=mask), mask)]
+    for name, kw, m in cases:
+        np.random.seed(21)
+        mine = getattr(mine_mod, name)(**kw)
+        f0, u0, v0 = mine.f, mine.u, mine.v
+        if refload.available():
+            np.random.seed(21)
+            ref = getattr(refload.old_cython(), name)(**kw)
+            assert np.array_equal(np.asarray(ref.f), f0), name
+            ref.run(120)
+            want_f, want_u, want_rho = np.asarray(ref.f), np.asarray(ref.u), np.asarray(ref.rho)
+        else:
+            vin = (kw["u_w"], kw["u_w"]) if "u_w" in kw else None
+            o = orc.CythonSchemeOracle(_yx(f0), _yx(u0), _yx(v0), mine.omega, mine.inlet_rho, mine.outlet_rho,
+                                       mask=None if m is None else _yx(m), old_api=True, velocity_inlet=vin)
+            o.run(120)
+            want_f, want_u, want_rho = _yx(o.f), _yx(o.u), _yx(o.rho)
+        mine.run(120)
+        assert np.isfinite(want_f).all(), name
+        assert np.array_equal(mine.f, want_f), name
+        assert np.array_equal(mine.u, want_u), name
+        assert np.array_equal(mine.rho, want_rho), name
+
+
+def test_velocity_inlet_rejects_solids_on_exchanged_rows(gpu):
+    from lb_b200 import Lattice, native
+    m = np.zeros((20, 30), np.uint8)
+    m[0, 5] = 1
+    with Lattice(30, 20, 1.0, bc="velocity_yperiodic", scheme="cython_old", u_west=0.05, u_east=0.05) as sim:
+        with pytest.raises(native.LBError, match="exchanged rows"):
+            sim.set_mask(m)
