@@ -5,6 +5,7 @@
 #include "../../include/lb_d2q9.h"
 #include "lb_fused.cuh"
 #include "lb_cython.cuh"
+#include "lb_tma.cuh"
 
 #include <cstdio>
 #include <cstring>
@@ -68,6 +69,8 @@ struct lb_sim {
     char *peer[2] = {nullptr, nullptr};   // neighbour arenas (mapped)
     bool peer_ipc[2] = {false, false};
     double *mass_scratch = nullptr;
+    CUtensorMap tmap[2][3];       // [buffer][box height 2,4,8]: TMA descriptors of the two ping-pong buffers
+    bool tmap_ok = false;
     std::string err;
 };
 
@@ -93,7 +96,23 @@ struct Variant {
     int dtype, math, model, V, WX, WY, R;
     void (*launch)(const StepParams &, cudaStream_t);
     bool is_default;
+    void (*launch_tma)(const CUtensorMap &, const StepParams &, cudaStream_t);   // non-null: TMA-staged kernel
+    int tma_ty;                                                                   // its box height
 };
+
+template <typename T, int V, int MATH, int TY, int MINB, int STP, int MODEL>
+static void launch_tma_variant(const CUtensorMap &map, const StepParams &p_in, cudaStream_t st)
+{
+    StepParams p = p_in;
+    p.tiles_x = (p.pitch + 32 * V - 1) / (32 * V);
+    p.tiles_y = (p.ny + TY - 1) / TY;
+    const unsigned gy = p.tiles_y < 65535 ? p.tiles_y : 65535;
+    const dim3 grid((unsigned)p.tiles_x, gy, ((unsigned)p.tiles_y + gy - 1) / gy);
+    fused_step_tma_kernel<T, V, MATH, TY, MINB, STP, MODEL><<<grid, 32 * TY, 0, st>>>(map, p);
+}
+#define VART(T, TN, DT, V, M, MN, TY, MINB)                                                         \
+    {TN "." MN ".tma.v" #V ".ty" #TY ".b" #MINB, DT, M, MODEL_D2Q9, V, 1, TY, 1, nullptr, false,       \
+     &launch_tma_variant<T, V, M, TY, MINB, 0, MODEL_D2Q9>, TY}
 
 template <typename T, int V, int MATH, int WX, int WY, int R, int MINB, int LDP, int STP, int MODEL = MODEL_D2Q9>
 static void launch_variant(const StepParams &p_in, cudaStream_t st)
@@ -119,11 +138,11 @@ static void launch_variant(const StepParams &p_in, cudaStream_t st)
 
 #define VAR(T, TN, DT, V, M, MN, WX, WY, R, MINB, LDP, STP, DEF)                                    \
     {TN "." MN ".v" #V ".wx" #WX ".wy" #WY ".r" #R ".b" #MINB ".ld" #LDP ".st" #STP, DT, M, MODEL_D2Q9, V, \
-     WX, WY, R, &launch_variant<T, V, M, WX, WY, R, MINB, LDP, STP>, DEF}
+     WX, WY, R, &launch_variant<T, V, M, WX, WY, R, MINB, LDP, STP>, DEF, nullptr, 0}
 // incompressible model (D2Q9i.cl): the default tile configuration only
 #define VARI(T, TN, DT, V, M, MN)                                                                   \
     {TN "." MN ".d2q9i.v" #V ".wx2.wy2.r1.b6.ld1.st0", DT, M, MODEL_D2Q9I, V, 2, 2, 1,               \
-     &launch_variant<T, V, M, 2, 2, 1, 6, 1, 0, MODEL_D2Q9I>, true}
+     &launch_variant<T, V, M, 2, 2, 1, 6, 1, 0, MODEL_D2Q9I>, true, nullptr, 0}
 
 #define VARS_FOR(T, TN, DT, VMAX, VHALF)                                                            \
     VAR(T, TN, DT, VMAX, MATH_FAST, "fast", 2, 2, 1, 6, 1, 0, true),                                \
@@ -155,6 +174,12 @@ static const Variant g_variants[] = {
     VARS_FOR(double, "f64", LB_F64, 2, 1),
     VARI(float, "f32", LB_F32, 4, MATH_STRICT, "strict"), VARI(float, "f32", LB_F32, 4, MATH_FAST, "fast"),
     VARI(double, "f64", LB_F64, 2, MATH_STRICT, "strict"), VARI(double, "f64", LB_F64, 2, MATH_FAST, "fast"),
+    VART(float, "f32", LB_F32, 4, MATH_STRICT, "strict", 4, 6), VART(float, "f32", LB_F32, 4, MATH_STRICT, "strict", 4, 4),
+    VART(float, "f32", LB_F32, 4, MATH_STRICT, "strict", 8, 3), VART(float, "f32", LB_F32, 4, MATH_STRICT, "strict", 8, 2),
+    VART(float, "f32", LB_F32, 4, MATH_STRICT, "strict", 2, 8), VART(float, "f32", LB_F32, 4, MATH_FAST, "fast", 4, 6),
+    VART(float, "f32", LB_F32, 4, MATH_FAST, "fast", 8, 3),
+    VART(double, "f64", LB_F64, 2, MATH_STRICT, "strict", 4, 6), VART(double, "f64", LB_F64, 2, MATH_STRICT, "strict", 8, 3),
+    VART(double, "f64", LB_F64, 2, MATH_FAST, "fast", 4, 6),
 };
 static const int g_nvariants = (int)(sizeof(g_variants) / sizeof(g_variants[0]));
 
@@ -453,11 +478,48 @@ static void fill_params(lb_sim *s, StepParams &p, int src_idx, int write_moments
     }
 }
 
+// TMA descriptors: the guarded 9-plane buffer as one [4 + 9*ny][pitch] tensor, box = (32*V) x TY
+typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int ensure_tmaps(lb_sim *sim)
+{
+    if (sim->tmap_ok) return LB_OK;
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CU(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) return fail(sim, LB_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+    const encode_tiled_fn encode = (encode_tiled_fn)fn;
+    const int V = sim->cfg.dtype == LB_F32 ? 4 : 2;
+    const int heights[3] = {2, 4, 8};
+    for (int b = 0; b < 2; ++b)
+        for (int h = 0; h < 3; ++h) {
+            const cuuint64_t dims[2] = {(cuuint64_t)sim->pitch, (cuuint64_t)9 * sim->cfg.ny + 4};
+            const cuuint64_t strides[1] = {(cuuint64_t)sim->pitch * sim->elem};
+            const cuuint32_t box[2] = {(cuuint32_t)(32 * V), (cuuint32_t)heights[h]};
+            const cuuint32_t estr[2] = {1, 1};
+            const CUresult r = encode(&sim->tmap[b][h], sim->cfg.dtype == LB_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64,
+                                      2, sim->buf_base[b], dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return fail(sim, LB_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+        }
+    sim->tmap_ok = true;
+    return LB_OK;
+}
+
 static int launch_step(lb_sim *sim, int src_idx, int write_moments, uint32_t state_index)
 {
     StepParams p;
     fill_params(sim, p, src_idx, write_moments, state_index);
-    g_variants[sim->variant].launch(p, sim->stream);
+    const Variant &var = g_variants[sim->variant];
+    if (var.launch_tma) {
+        int rc = ensure_tmaps(sim);
+        if (rc) return rc;
+        const int hi = var.tma_ty == 2 ? 0 : var.tma_ty == 4 ? 1 : 2;
+        var.launch_tma(sim->tmap[src_idx][hi], p, sim->stream);
+    } else var.launch(p, sim->stream);
     CU(cudaGetLastError());
     sim->launches++;
     return LB_OK;
@@ -587,7 +649,10 @@ int lb_set_variant(lb_sim *sim, int variant)
     if (variant >= g_nvariants || g_variants[variant].dtype != sim->cfg.dtype || g_variants[variant].math != sim->cfg.math ||
         g_variants[variant].model != sim->cfg.model)
         return fail(sim, LB_ERR_INVALID, "lb_set_variant: variant does not match the handle's dtype/math/model");
+    if (g_variants[variant].launch_tma && (uses_halo(sim) || sim->cfg.bc == LB_BC_PERIODIC || sim->cfg.scheme != LB_SCHEME_OPENCL))
+        return fail(sim, LB_ERR_INVALID, "lb_set_variant: the TMA-staged kernel serves single-slab, non-periodic lattices");
     sim->variant = variant;
+    drop_graphs(sim);
     return LB_OK;
 }
 

@@ -142,6 +142,154 @@ __device__ __forceinline__ void wait_flag(const unsigned int *flag, unsigned int
     __syncthreads();
 }
 
+// ---- everything after the nine shifted populations of a thread's V nodes are in registers:
+//      slab-edge fix-ups, boundary closure, obstacles, collision, stores, halo publication.
+//      Shared by the register-shuffle kernel below and the TMA kernel (lb_tma.cuh).
+template <typename T, int V, int MATH, int STP, int MODEL>
+__device__ __forceinline__ void finish_row(const StepParams &p, const Consts<T> &c, Pack<T, V> (&q)[9],
+                                           const T *__restrict__ src, T *__restrict__ dst,
+                                           int x0, int span0, int y, int ym, int yp)
+{
+    constexpr int SPAN = 32 * V;
+    const long long plane = p.plane;
+    const int nx = p.nx, ny = p.ny, pitch = p.pitch;
+    const bool periodic = (p.bc == BC_PERIODIC);
+    const int el_east = (nx - 1) - x0;                // element index of column nx-1 in this thread, if in [0,V)
+    const bool has_west = (x0 == 0);
+    const bool has_east = (el_east >= 0 && el_east < V);
+    const long long rc = (long long)y * pitch + x0;
+
+    // --- first / last column of the slab: wrap, ghost column, or domain boundary ---
+    if (has_west && p.west != EDGE_BOUNDARY) {
+        T a1, a5, a8;
+        if (p.west == EDGE_WRAP) {
+            a1 = src[1 * plane + (long long)y * pitch + (nx - 1)];
+            a5 = src[5 * plane + (long long)ym * pitch + (nx - 1)];
+            a8 = src[8 * plane + (long long)yp * pitch + (nx - 1)];
+        } else {
+            const T *gw = static_cast<const T *>(p.ghost_w);
+            a1 = __ldcv(gw + 0 * (ny + 2) + (y + 1));
+            a5 = __ldcv(gw + 1 * (ny + 2) + (ym + 1));
+            a8 = __ldcv(gw + 2 * (ny + 2) + (yp + 1));
+        }
+        q[1].v[0] = a1; q[5].v[0] = a5; q[8].v[0] = a8;
+    }
+    if (has_east && p.east != EDGE_BOUNDARY) {
+        T a3, a6, a7;
+        if (p.east == EDGE_WRAP) {
+            a3 = src[3 * plane + (long long)y * pitch];
+            a6 = src[6 * plane + (long long)ym * pitch];
+            a7 = src[7 * plane + (long long)yp * pitch];
+        } else {
+            const T *ge = static_cast<const T *>(p.ghost_e);
+            a3 = __ldcv(ge + 0 * (ny + 2) + (y + 1));
+            a6 = __ldcv(ge + 1 * (ny + 2) + (ym + 1));
+            a7 = __ldcv(ge + 2 * (ny + 2) + (yp + 1));
+        }
+#pragma unroll
+        for (int e = 0; e < V; ++e)
+            if (e == el_east) { q[3].v[e] = a3; q[6].v[e] = a6; q[7].v[e] = a7; }
+    }
+
+    // --- boundary closure: only threads that own a wall / inlet / outlet node ---
+    const bool row_is_wall = (!periodic) && (y == 0 || y == ny - 1);
+    if ((!periodic) && (row_is_wall || (has_west && p.west == EDGE_BOUNDARY) ||
+                        (has_east && p.east == EDGE_BOUNDARY))) {
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+            T g[9];
+#pragma unroll
+            for (int j = 0; j < 9; ++j) g[j] = q[j].v[e];
+            pipe_bc<T, MODEL>(c, p.x_off + x0 + e, y, p.gnx, ny, g);
+#pragma unroll
+            for (int j = 0; j < 9; ++j) q[j].v[e] = g[j];
+        }
+    }
+
+    // --- obstacles: one flag byte per (row, 32 cells) says whether to look at the mask at all.
+    //     The vote makes the branch warp-uniform, so warps without solids issue nothing here.
+    uint32_t solid_bits = 0;
+    if (p.mask != nullptr) {
+        const uint8_t *sf = p.span_solid + (long long)y * p.nspans + (span0 >> 5);
+        unsigned int any = 0;
+#pragma unroll
+        for (int k = 0; k < SPAN / 32; ++k) any |= sf[k];
+        if (__any_sync(0xffffffffu, any != 0)) {
+#pragma unroll
+            for (int e = 0; e < V; ++e)
+                if (x0 + e < nx && p.mask[(long long)y * p.mask_pitch + x0 + e] == 1) solid_bits |= (1u << e);
+            if (__any_sync(0xffffffffu, solid_bits != 0)) {
+#pragma unroll
+                for (int e = 0; e < V; ++e) {
+                    if ((solid_bits >> e) & 1u) {         // D2Q9.cl:410-431
+                        T t;
+                        t = q[1].v[e]; q[1].v[e] = q[3].v[e]; q[3].v[e] = t;
+                        t = q[2].v[e]; q[2].v[e] = q[4].v[e]; q[4].v[e] = t;
+                        t = q[5].v[e]; q[5].v[e] = q[7].v[e]; q[7].v[e] = t;
+                        t = q[6].v[e]; q[6].v[e] = q[8].v[e]; q[8].v[e] = t;
+                    }
+                }
+            }
+        }
+    }
+    const uint32_t zero_bits = p.zero_obstacle_velocity ? solid_bits : 0u;
+
+    // --- per node: moments + equilibrium + BGK relaxation, in registers ---
+    Pack<T, V> mrho, mu, mv;
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+        T g[9];
+#pragma unroll
+        for (int j = 0; j < 9; ++j) g[j] = q[j].v[e];
+        collide_node<T, MATH, MODEL>(c, g, mrho.v[e], mu.v[e], mv.v[e], (zero_bits >> e) & 1u);
+#pragma unroll
+        for (int j = 0; j < 9; ++j) q[j].v[e] = g[j];
+    }
+
+    // --- stores: aligned vectors; the one thread straddling column nx-1 goes scalar ---
+    if (x0 + V <= nx) {
+        T *pd = dst + rc;
+#pragma unroll
+        for (int j = 0; j < 9; ++j) store_pack<T, V, STP>(pd + j * plane, q[j]);
+        if (p.write_moments) {
+            store_pack<T, V, 0>(static_cast<T *>(p.rho) + rc, mrho);
+            store_pack<T, V, 0>(static_cast<T *>(p.u) + rc, mu);
+            store_pack<T, V, 0>(static_cast<T *>(p.v) + rc, mv);
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+            if (x0 + e < nx) {
+#pragma unroll
+                for (int j = 0; j < 9; ++j) dst[j * plane + rc + e] = q[j].v[e];
+                if (p.write_moments) {
+                    static_cast<T *>(p.rho)[rc + e] = mrho.v[e];
+                    static_cast<T *>(p.u)[rc + e] = mu.v[e];
+                    static_cast<T *>(p.v)[rc + e] = mv.v[e];
+                }
+            }
+        }
+    }
+
+    // --- publish my boundary columns into the neighbours' ghost columns ---
+    if (has_west && p.west == EDGE_HALO) {
+        T *ow = static_cast<T *>(p.out_w);
+        ow[0 * (ny + 2) + (y + 1)] = q[3].v[0];
+        ow[1 * (ny + 2) + (y + 1)] = q[6].v[0];
+        ow[2 * (ny + 2) + (y + 1)] = q[7].v[0];
+    }
+    if (has_east && p.east == EDGE_HALO) {
+        T *oe = static_cast<T *>(p.out_e);
+#pragma unroll
+        for (int e = 0; e < V; ++e)
+            if (e == el_east) {
+                oe[0 * (ny + 2) + (y + 1)] = q[1].v[e];
+                oe[1 * (ny + 2) + (y + 1)] = q[5].v[e];
+                oe[2 * (ny + 2) + (y + 1)] = q[8].v[e];
+            }
+    }
+}
+
 // ---- the fused kernel -----------------------------------------------------------------
 template <typename T, int V, int MATH, int WX, int WY, int R, int MINB, int LDP, int STP, int MODEL = MODEL_D2Q9>
 __global__ void __launch_bounds__(32 * WX * WY, MINB) fused_step_kernel(const StepParams p)
@@ -189,9 +337,6 @@ __global__ void __launch_bounds__(32 * WX * WY, MINB) fused_step_kernel(const St
     const int nx = p.nx, ny = p.ny, pitch = p.pitch;
     const Consts<T> &c = consts_in<T>(p);
     const bool periodic = (p.bc == BC_PERIODIC);
-    const int el_east = (nx - 1) - x0;                // element index of column nx-1 in this thread, if in [0,V)
-    const bool has_west = (x0 == 0);
-    const bool has_east = (el_east >= 0 && el_east < V);
 
     if (warp_active) {
         for (int r = 0; r < rows; ++r) {
@@ -253,135 +398,7 @@ __global__ void __launch_bounds__(32 * WX * WY, MINB) fused_step_kernel(const St
             }
             q[3].v[V - 1] = r3; q[6].v[V - 1] = r6; q[7].v[V - 1] = r7;
 
-            // --- first / last column of the slab: wrap, ghost column, or domain boundary ---
-            if (has_west && p.west != EDGE_BOUNDARY) {
-                T a1, a5, a8;
-                if (p.west == EDGE_WRAP) {
-                    a1 = src[1 * plane + (long long)y * pitch + (nx - 1)];
-                    a5 = src[5 * plane + (long long)ym * pitch + (nx - 1)];
-                    a8 = src[8 * plane + (long long)yp * pitch + (nx - 1)];
-                } else {
-                    const T *gw = static_cast<const T *>(p.ghost_w);
-                    a1 = __ldcv(gw + 0 * (ny + 2) + (y + 1));
-                    a5 = __ldcv(gw + 1 * (ny + 2) + (ym + 1));
-                    a8 = __ldcv(gw + 2 * (ny + 2) + (yp + 1));
-                }
-                q[1].v[0] = a1; q[5].v[0] = a5; q[8].v[0] = a8;
-            }
-            if (has_east && p.east != EDGE_BOUNDARY) {
-                T a3, a6, a7;
-                if (p.east == EDGE_WRAP) {
-                    a3 = src[3 * plane + (long long)y * pitch];
-                    a6 = src[6 * plane + (long long)ym * pitch];
-                    a7 = src[7 * plane + (long long)yp * pitch];
-                } else {
-                    const T *ge = static_cast<const T *>(p.ghost_e);
-                    a3 = __ldcv(ge + 0 * (ny + 2) + (y + 1));
-                    a6 = __ldcv(ge + 1 * (ny + 2) + (ym + 1));
-                    a7 = __ldcv(ge + 2 * (ny + 2) + (yp + 1));
-                }
-#pragma unroll
-                for (int e = 0; e < V; ++e)
-                    if (e == el_east) { q[3].v[e] = a3; q[6].v[e] = a6; q[7].v[e] = a7; }
-            }
-
-            // --- boundary closure: only threads that own a wall / inlet / outlet node ---
-            const bool row_is_wall = (!periodic) && (y == 0 || y == ny - 1);
-            if ((!periodic) && (row_is_wall || (has_west && p.west == EDGE_BOUNDARY) ||
-                                (has_east && p.east == EDGE_BOUNDARY))) {
-#pragma unroll
-                for (int e = 0; e < V; ++e) {
-                    T g[9];
-#pragma unroll
-                    for (int j = 0; j < 9; ++j) g[j] = q[j].v[e];
-                    pipe_bc<T, MODEL>(c, p.x_off + x0 + e, y, p.gnx, ny, g);
-#pragma unroll
-                    for (int j = 0; j < 9; ++j) q[j].v[e] = g[j];
-                }
-            }
-
-            // --- obstacles: one flag byte per (row, 32 cells) says whether to look at the mask at all.
-            //     The vote makes the branch warp-uniform, so warps without solids issue nothing here.
-            uint32_t solid_bits = 0;
-            if (p.mask != nullptr) {
-                const uint8_t *sf = p.span_solid + (long long)y * p.nspans + (span0 >> 5);
-                unsigned int any = 0;
-#pragma unroll
-                for (int k = 0; k < SPAN / 32; ++k) any |= sf[k];
-                if (__any_sync(0xffffffffu, any != 0)) {
-#pragma unroll
-                    for (int e = 0; e < V; ++e)
-                        if (x0 + e < nx && p.mask[(long long)y * p.mask_pitch + x0 + e] == 1) solid_bits |= (1u << e);
-                    if (__any_sync(0xffffffffu, solid_bits != 0)) {
-#pragma unroll
-                        for (int e = 0; e < V; ++e) {
-                            if ((solid_bits >> e) & 1u) {         // D2Q9.cl:410-431
-                                T t;
-                                t = q[1].v[e]; q[1].v[e] = q[3].v[e]; q[3].v[e] = t;
-                                t = q[2].v[e]; q[2].v[e] = q[4].v[e]; q[4].v[e] = t;
-                                t = q[5].v[e]; q[5].v[e] = q[7].v[e]; q[7].v[e] = t;
-                                t = q[6].v[e]; q[6].v[e] = q[8].v[e]; q[8].v[e] = t;
-                            }
-                        }
-                    }
-                }
-            }
-            const uint32_t zero_bits = p.zero_obstacle_velocity ? solid_bits : 0u;
-
-            // --- per node: moments + equilibrium + BGK relaxation, in registers ---
-            Pack<T, V> mrho, mu, mv;
-#pragma unroll
-            for (int e = 0; e < V; ++e) {
-                T g[9];
-#pragma unroll
-                for (int j = 0; j < 9; ++j) g[j] = q[j].v[e];
-                collide_node<T, MATH, MODEL>(c, g, mrho.v[e], mu.v[e], mv.v[e], (zero_bits >> e) & 1u);
-#pragma unroll
-                for (int j = 0; j < 9; ++j) q[j].v[e] = g[j];
-            }
-
-            // --- stores: aligned vectors; the one thread straddling column nx-1 goes scalar ---
-            if (x0 + V <= nx) {
-                T *pd = dst + rc;
-#pragma unroll
-                for (int j = 0; j < 9; ++j) store_pack<T, V, STP>(pd + j * plane, q[j]);
-                if (p.write_moments) {
-                    store_pack<T, V, 0>(static_cast<T *>(p.rho) + rc, mrho);
-                    store_pack<T, V, 0>(static_cast<T *>(p.u) + rc, mu);
-                    store_pack<T, V, 0>(static_cast<T *>(p.v) + rc, mv);
-                }
-            } else {
-#pragma unroll
-                for (int e = 0; e < V; ++e) {
-                    if (x0 + e < nx) {
-#pragma unroll
-                        for (int j = 0; j < 9; ++j) dst[j * plane + rc + e] = q[j].v[e];
-                        if (p.write_moments) {
-                            static_cast<T *>(p.rho)[rc + e] = mrho.v[e];
-                            static_cast<T *>(p.u)[rc + e] = mu.v[e];
-                            static_cast<T *>(p.v)[rc + e] = mv.v[e];
-                        }
-                    }
-                }
-            }
-
-            // --- publish my boundary columns into the neighbours' ghost columns ---
-            if (has_west && p.west == EDGE_HALO) {
-                T *ow = static_cast<T *>(p.out_w);
-                ow[0 * (ny + 2) + (y + 1)] = q[3].v[0];
-                ow[1 * (ny + 2) + (y + 1)] = q[6].v[0];
-                ow[2 * (ny + 2) + (y + 1)] = q[7].v[0];
-            }
-            if (has_east && p.east == EDGE_HALO) {
-                T *oe = static_cast<T *>(p.out_e);
-#pragma unroll
-                for (int e = 0; e < V; ++e)
-                    if (e == el_east) {
-                        oe[0 * (ny + 2) + (y + 1)] = q[1].v[e];
-                        oe[1 * (ny + 2) + (y + 1)] = q[5].v[e];
-                        oe[2 * (ny + 2) + (y + 1)] = q[8].v[e];
-                    }
-            }
+            finish_row<T, V, MATH, STP, MODEL>(p, c, q, src, dst, x0, span0, y, ym, yp);
         }
     }
 
