@@ -69,7 +69,7 @@ struct lb_sim {
     char *peer[2] = {nullptr, nullptr};   // neighbour arenas (mapped)
     bool peer_ipc[2] = {false, false};
     double *mass_scratch = nullptr;
-    CUtensorMap tmap[2][3];       // [buffer][box height 2,4,8]: TMA descriptors of the two ping-pong buffers
+    CUtensorMap tmap[2][3][2];    // [buffer][box height 2,4,8][plain | haloed box]: TMA descriptors of the ping-pong buffers
     bool tmap_ok = false;
     std::string err;
 };
@@ -96,19 +96,19 @@ struct Variant {
     int dtype, math, model, V, WX, WY, R;
     void (*launch)(const StepParams &, cudaStream_t);
     bool is_default;
-    void (*launch_tma)(const CUtensorMap &, const StepParams &, cudaStream_t);   // non-null: TMA-staged kernel
+    void (*launch_tma)(const CUtensorMap &, const CUtensorMap &, const StepParams &, cudaStream_t);   // non-null: TMA-staged kernel
     int tma_ty;                                                                   // its box height
 };
 
 template <typename T, int V, int MATH, int TY, int MINB, int STP, int MODEL>
-static void launch_tma_variant(const CUtensorMap &map, const StepParams &p_in, cudaStream_t st)
+static void launch_tma_variant(const CUtensorMap &map_n, const CUtensorMap &map_w, const StepParams &p_in, cudaStream_t st)
 {
     StepParams p = p_in;
     p.tiles_x = (p.pitch + 32 * V - 1) / (32 * V);
     p.tiles_y = (p.ny + TY - 1) / TY;
     const unsigned gy = p.tiles_y < 65535 ? p.tiles_y : 65535;
     const dim3 grid((unsigned)p.tiles_x, gy, ((unsigned)p.tiles_y + gy - 1) / gy);
-    fused_step_tma_kernel<T, V, MATH, TY, MINB, STP, MODEL><<<grid, 32 * TY, 0, st>>>(map, p);
+    fused_step_tma_kernel<T, V, MATH, TY, MINB, STP, MODEL><<<grid, 32 * TY, 0, st>>>(map_n, map_w, p);
 }
 #define VART(T, TN, DT, V, M, MN, TY, MINB)                                                         \
     {TN "." MN ".tma.v" #V ".ty" #TY ".b" #MINB, DT, M, MODEL_D2Q9, V, 1, TY, 1, nullptr, false,       \
@@ -493,13 +493,15 @@ static int ensure_tmaps(lb_sim *sim)
     const encode_tiled_fn encode = (encode_tiled_fn)fn;
     const int V = sim->cfg.dtype == LB_F32 ? 4 : 2;
     const int heights[3] = {2, 4, 8};
+    const int halo = 16 / sim->elem;
     for (int b = 0; b < 2; ++b)
-        for (int h = 0; h < 3; ++h) {
+        for (int h = 0; h < 3; ++h)
+            for (int wide = 0; wide < 2; ++wide) {
             const cuuint64_t dims[2] = {(cuuint64_t)sim->pitch, (cuuint64_t)9 * sim->cfg.ny + 4};
             const cuuint64_t strides[1] = {(cuuint64_t)sim->pitch * sim->elem};
-            const cuuint32_t box[2] = {(cuuint32_t)(32 * V), (cuuint32_t)heights[h]};
+            const cuuint32_t box[2] = {(cuuint32_t)(32 * V + (wide ? 2 * halo : 0)), (cuuint32_t)heights[h]};
             const cuuint32_t estr[2] = {1, 1};
-            const CUresult r = encode(&sim->tmap[b][h], sim->cfg.dtype == LB_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64,
+            const CUresult r = encode(&sim->tmap[b][h][wide], sim->cfg.dtype == LB_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64,
                                       2, sim->buf_base[b], dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                       CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -518,7 +520,7 @@ static int launch_step(lb_sim *sim, int src_idx, int write_moments, uint32_t sta
         int rc = ensure_tmaps(sim);
         if (rc) return rc;
         const int hi = var.tma_ty == 2 ? 0 : var.tma_ty == 4 ? 1 : 2;
-        var.launch_tma(sim->tmap[src_idx][hi], p, sim->stream);
+        var.launch_tma(sim->tmap[src_idx][hi][0], sim->tmap[src_idx][hi][1], p, sim->stream);
     } else var.launch(p, sim->stream);
     CU(cudaGetLastError());
     sim->launches++;

@@ -1,16 +1,19 @@
 // TMA-staged variant of the fused step (sm_100a: cp.async.bulk.tensor + mbarrier).
 //
-// The register-shuffle kernel (lb_fused.cuh) resolves the +-1 x-shift of the moving populations
-// with shuffles, two predicated scalar loads per shifted population and ~60 instructions of 64-bit
-// address arithmetic per thread-row.  Here the shift is absorbed by the TMA unit instead: one
-// elected thread issues nine 2-D box loads whose start coordinates are already displaced by
-// (-cx_j, -cy_j), the hardware zero-fills what lies left / right of the row, and every thread then
-// reads its nine vectors from shared memory at ONE common offset (LDS.128, conflict-free).
+// One elected thread issues nine 2-D box loads into shared memory; the -cy_j row displacement of
+// each population is absorbed by the box's row coordinate.  The -cx_j displacement can NOT be
+// absorbed the same way: UTMALDG requires the box start to be 16-byte aligned in the innermost
+// dimension -- a box at x0-1 raises "illegal instruction" (compute-sanitizer, round 1) -- so the six
+// x-moving populations are staged with an aligned halo of 16 B on each side (box start x0-H, width
+// 32*V + 2H, H = 16/sizeof(T)) and every thread takes its own aligned vector with LDS.128 plus ONE
+// neighbouring element with LDS.32/64.  Compared with the register-shuffle kernel this removes the
+// shuffles, the predicated lane-0/31 global loads and most of the 64-bit address arithmetic.
 // Everything after the loads is the same code as the other kernel (finish_row).
 //
 // The whole ping-pong buffer -- guard rows and all nine planes, which are contiguous in y -- is one
 // 2-D tensor [2 + 9*ny + 2][pitch]; plane j / row y is tensor row 2 + j*ny + y.  Rows "above" y=0 or
-// "below" y=ny-1 of a plane are a neighbouring plane's rows: garbage that the boundary closure
+// "below" y=ny-1 of a plane are a neighbouring plane's rows, and columns left of x=0 / right of the
+// pitch are zero-filled by the TMA unit: garbage that the boundary closure or the slab-edge fix-up
 // overwrites, exactly as in the register kernel.  Used for single-slab, non-periodic lattices; other
 // configurations take the register-shuffle kernel.
 #pragma once
@@ -51,12 +54,17 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
 }
 
 // CTA = TY warps; tile = TY rows x (32*V) cells; one thread = V cells of one row.
+// tmap_n: box (32*V) x TY for the populations with cx = 0; tmap_w: box (32*V + 2H) x TY for the others.
 template <typename T, int V, int MATH, int TY, int MINB, int STP, int MODEL>
 __global__ void __launch_bounds__(32 * TY, MINB)
-fused_step_tma_kernel(const __grid_constant__ CUtensorMap tmap, const StepParams p)
+fused_step_tma_kernel(const __grid_constant__ CUtensorMap tmap_n, const __grid_constant__ CUtensorMap tmap_w,
+                      const StepParams p)
 {
     constexpr int TX = 32 * V;
-    __shared__ alignas(128) T tile[9][TY][TX];
+    constexpr int H = 16 / (int)sizeof(T);                     // halo elements = 16 bytes
+    constexpr int TW = TX + 2 * H;
+    __shared__ alignas(128) T tile_n[3][TY][TX];               // populations 0, 2, 4
+    __shared__ alignas(128) T tile_w[6][TY][TW];               // populations 1, 5, 8 (from x-1) and 3, 6, 7 (from x+1)
     __shared__ alignas(8) unsigned long long bar_storage;
 
     const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
@@ -67,26 +75,45 @@ fused_step_tma_kernel(const __grid_constant__ CUtensorMap tmap, const StepParams
     if (threadIdx.x == 0) mbar_init(bar, 1);
     __syncthreads();
     if (threadIdx.x == 0) {
-        mbar_expect_tx(bar, 9u * TY * TX * (uint32_t)sizeof(T));
+        mbar_expect_tx(bar, (uint32_t)(sizeof(tile_n) + sizeof(tile_w)));
         const int r0 = 2 + ty0, ny = p.ny;                     // 2 guard rows precede plane 0
-        tma_load_2d(smem_u32(&tile[0][0][0]), &tmap, tx0,     r0 + 0 * ny,     bar);
-        tma_load_2d(smem_u32(&tile[1][0][0]), &tmap, tx0 - 1, r0 + 1 * ny,     bar);
-        tma_load_2d(smem_u32(&tile[2][0][0]), &tmap, tx0,     r0 + 2 * ny - 1, bar);
-        tma_load_2d(smem_u32(&tile[3][0][0]), &tmap, tx0 + 1, r0 + 3 * ny,     bar);
-        tma_load_2d(smem_u32(&tile[4][0][0]), &tmap, tx0,     r0 + 4 * ny + 1, bar);
-        tma_load_2d(smem_u32(&tile[5][0][0]), &tmap, tx0 - 1, r0 + 5 * ny - 1, bar);
-        tma_load_2d(smem_u32(&tile[6][0][0]), &tmap, tx0 + 1, r0 + 6 * ny - 1, bar);
-        tma_load_2d(smem_u32(&tile[7][0][0]), &tmap, tx0 + 1, r0 + 7 * ny + 1, bar);
-        tma_load_2d(smem_u32(&tile[8][0][0]), &tmap, tx0 - 1, r0 + 8 * ny + 1, bar);
+        const int xw = tx0 - H;                                // aligned start of the haloed boxes
+        tma_load_2d(smem_u32(&tile_n[0][0][0]), &tmap_n, tx0, r0 + 0 * ny,     bar);   // f0: row y
+        tma_load_2d(smem_u32(&tile_n[1][0][0]), &tmap_n, tx0, r0 + 2 * ny - 1, bar);   // f2: row y-1
+        tma_load_2d(smem_u32(&tile_n[2][0][0]), &tmap_n, tx0, r0 + 4 * ny + 1, bar);   // f4: row y+1
+        tma_load_2d(smem_u32(&tile_w[0][0][0]), &tmap_w, xw,  r0 + 1 * ny,     bar);   // f1: row y
+        tma_load_2d(smem_u32(&tile_w[1][0][0]), &tmap_w, xw,  r0 + 5 * ny - 1, bar);   // f5: row y-1
+        tma_load_2d(smem_u32(&tile_w[2][0][0]), &tmap_w, xw,  r0 + 8 * ny + 1, bar);   // f8: row y+1
+        tma_load_2d(smem_u32(&tile_w[3][0][0]), &tmap_w, xw,  r0 + 3 * ny,     bar);   // f3: row y
+        tma_load_2d(smem_u32(&tile_w[4][0][0]), &tmap_w, xw,  r0 + 6 * ny - 1, bar);   // f6: row y-1
+        tma_load_2d(smem_u32(&tile_w[5][0][0]), &tmap_w, xw,  r0 + 7 * ny + 1, bar);   // f7: row y+1
     }
     mbar_wait(bar, 0);
 
     const int y = ty0 + wy;
     if (y >= p.ny) return;                                     // warp-uniform; nothing follows the barrier
     using VT = typename VecOf<T, V>::type;
-    Pack<T, V> q[9];
+    Pack<T, V> q[9], own;
+    unpack(*reinterpret_cast<const VT *>(&tile_n[0][wy][lane * V]), q[0]);
+    unpack(*reinterpret_cast<const VT *>(&tile_n[1][wy][lane * V]), q[2]);
+    unpack(*reinterpret_cast<const VT *>(&tile_n[2][wy][lane * V]), q[4]);
+    constexpr int plus_x[3] = {1, 5, 8}, minus_x[3] = {3, 6, 7};
 #pragma unroll
-    for (int j = 0; j < 9; ++j) unpack(*reinterpret_cast<const VT *>(&tile[j][wy][lane * V]), q[j]);
+    for (int k = 0; k < 3; ++k) {                              // movers in +x take the cell to their left
+        const T *base = &tile_w[k][wy][H + lane * V];
+        unpack(*reinterpret_cast<const VT *>(base), own);
+        q[plus_x[k]].v[0] = base[-1];
+#pragma unroll
+        for (int e = 1; e < V; ++e) q[plus_x[k]].v[e] = own.v[e - 1];
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {                              // movers in -x take the cell to their right
+        const T *base = &tile_w[3 + k][wy][H + lane * V];
+        unpack(*reinterpret_cast<const VT *>(base), own);
+#pragma unroll
+        for (int e = 0; e < V - 1; ++e) q[minus_x[k]].v[e] = own.v[e + 1];
+        q[minus_x[k]].v[V - 1] = base[V];
+    }
     finish_row<T, V, MATH, STP, MODEL>(p, consts_in<T>(p), q, static_cast<const T *>(p.src), static_cast<T *>(p.dst),
                                        tx0 + lane * V, tx0, y, y - 1, y + 1);
 }
