@@ -63,8 +63,10 @@ fused_step_tma_kernel(const __grid_constant__ CUtensorMap tmap_n, const __grid_c
     constexpr int TX = 32 * V;
     constexpr int H = 16 / (int)sizeof(T);                     // halo elements = 16 bytes
     constexpr int TW = TX + 2 * H;
-    __shared__ alignas(128) T tile_n[3][TY][TX];               // populations 0, 2, 4
-    __shared__ alignas(128) T tile_w[6][TY][TW];               // populations 1, 5, 8 (from x-1) and 3, 6, 7 (from x+1)
+    struct alignas(128) NTile { T v[TY][TX]; };                // every TMA destination must be 128-byte aligned
+    struct alignas(128) WTile { T v[TY][TW]; };
+    __shared__ NTile tile_n[3];                                // populations 0, 2, 4
+    __shared__ WTile tile_w[6];                                // populations 1, 5, 8 (from x-1) and 3, 6, 7 (from x+1)
     __shared__ alignas(8) unsigned long long bar_storage;
 
     const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
@@ -75,18 +77,18 @@ fused_step_tma_kernel(const __grid_constant__ CUtensorMap tmap_n, const __grid_c
     if (threadIdx.x == 0) mbar_init(bar, 1);
     __syncthreads();
     if (threadIdx.x == 0) {
-        mbar_expect_tx(bar, (uint32_t)(sizeof(tile_n) + sizeof(tile_w)));
+        mbar_expect_tx(bar, (uint32_t)((3 * TY * TX + 6 * TY * TW) * sizeof(T)));
         const int r0 = 2 + ty0, ny = p.ny;                     // 2 guard rows precede plane 0
         const int xw = tx0 - H;                                // aligned start of the haloed boxes
-        tma_load_2d(smem_u32(&tile_n[0][0][0]), &tmap_n, tx0, r0 + 0 * ny,     bar);   // f0: row y
-        tma_load_2d(smem_u32(&tile_n[1][0][0]), &tmap_n, tx0, r0 + 2 * ny - 1, bar);   // f2: row y-1
-        tma_load_2d(smem_u32(&tile_n[2][0][0]), &tmap_n, tx0, r0 + 4 * ny + 1, bar);   // f4: row y+1
-        tma_load_2d(smem_u32(&tile_w[0][0][0]), &tmap_w, xw,  r0 + 1 * ny,     bar);   // f1: row y
-        tma_load_2d(smem_u32(&tile_w[1][0][0]), &tmap_w, xw,  r0 + 5 * ny - 1, bar);   // f5: row y-1
-        tma_load_2d(smem_u32(&tile_w[2][0][0]), &tmap_w, xw,  r0 + 8 * ny + 1, bar);   // f8: row y+1
-        tma_load_2d(smem_u32(&tile_w[3][0][0]), &tmap_w, xw,  r0 + 3 * ny,     bar);   // f3: row y
-        tma_load_2d(smem_u32(&tile_w[4][0][0]), &tmap_w, xw,  r0 + 6 * ny - 1, bar);   // f6: row y-1
-        tma_load_2d(smem_u32(&tile_w[5][0][0]), &tmap_w, xw,  r0 + 7 * ny + 1, bar);   // f7: row y+1
+        tma_load_2d(smem_u32(&tile_n[0].v[0][0]), &tmap_n, tx0, r0 + 0 * ny,     bar);   // f0: row y
+        tma_load_2d(smem_u32(&tile_n[1].v[0][0]), &tmap_n, tx0, r0 + 2 * ny - 1, bar);   // f2: row y-1
+        tma_load_2d(smem_u32(&tile_n[2].v[0][0]), &tmap_n, tx0, r0 + 4 * ny + 1, bar);   // f4: row y+1
+        tma_load_2d(smem_u32(&tile_w[0].v[0][0]), &tmap_w, xw,  r0 + 1 * ny,     bar);   // f1: row y
+        tma_load_2d(smem_u32(&tile_w[1].v[0][0]), &tmap_w, xw,  r0 + 5 * ny - 1, bar);   // f5: row y-1
+        tma_load_2d(smem_u32(&tile_w[2].v[0][0]), &tmap_w, xw,  r0 + 8 * ny + 1, bar);   // f8: row y+1
+        tma_load_2d(smem_u32(&tile_w[3].v[0][0]), &tmap_w, xw,  r0 + 3 * ny,     bar);   // f3: row y
+        tma_load_2d(smem_u32(&tile_w[4].v[0][0]), &tmap_w, xw,  r0 + 6 * ny - 1, bar);   // f6: row y-1
+        tma_load_2d(smem_u32(&tile_w[5].v[0][0]), &tmap_w, xw,  r0 + 7 * ny + 1, bar);   // f7: row y+1
     }
     mbar_wait(bar, 0);
 
@@ -94,13 +96,13 @@ fused_step_tma_kernel(const __grid_constant__ CUtensorMap tmap_n, const __grid_c
     if (y >= p.ny) return;                                     // warp-uniform; nothing follows the barrier
     using VT = typename VecOf<T, V>::type;
     Pack<T, V> q[9], own;
-    unpack(*reinterpret_cast<const VT *>(&tile_n[0][wy][lane * V]), q[0]);
-    unpack(*reinterpret_cast<const VT *>(&tile_n[1][wy][lane * V]), q[2]);
-    unpack(*reinterpret_cast<const VT *>(&tile_n[2][wy][lane * V]), q[4]);
+    unpack(*reinterpret_cast<const VT *>(&tile_n[0].v[wy][lane * V]), q[0]);
+    unpack(*reinterpret_cast<const VT *>(&tile_n[1].v[wy][lane * V]), q[2]);
+    unpack(*reinterpret_cast<const VT *>(&tile_n[2].v[wy][lane * V]), q[4]);
     constexpr int plus_x[3] = {1, 5, 8}, minus_x[3] = {3, 6, 7};
 #pragma unroll
     for (int k = 0; k < 3; ++k) {                              // movers in +x take the cell to their left
-        const T *base = &tile_w[k][wy][H + lane * V];
+        const T *base = &tile_w[k].v[wy][H + lane * V];
         unpack(*reinterpret_cast<const VT *>(base), own);
         q[plus_x[k]].v[0] = base[-1];
 #pragma unroll
@@ -108,7 +110,7 @@ fused_step_tma_kernel(const __grid_constant__ CUtensorMap tmap_n, const __grid_c
     }
 #pragma unroll
     for (int k = 0; k < 3; ++k) {                              // movers in -x take the cell to their right
-        const T *base = &tile_w[3 + k][wy][H + lane * V];
+        const T *base = &tile_w[3 + k].v[wy][H + lane * V];
         unpack(*reinterpret_cast<const VT *>(base), own);
 #pragma unroll
         for (int e = 0; e < V - 1; ++e) q[minus_x[k]].v[e] = own.v[e + 1];

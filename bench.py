@@ -11,6 +11,7 @@ Prints ONE JSON line (rank 0).  Metric: MLUPS = lattice updates / second / 1e6, 
 definition (docs/python_cython_opencl_comparison.ipynb cell 16).  A "step" is one lattice update of
 the whole grid.  Workloads are BASELINE.json's configs:
   c4 (default) cylinder wake 32768x32768 fp32, x-slab STRONG scaling over the N GPUs
+  c1           Poiseuille 256x128 fp64 (the reference's CPU-runnable case; launch-bound on a GPU)
   c2           Pipe_Flow_Obstacles-style 4096x1024 fp32 with an obstacle mask (1 GPU)
   c3           periodic shear layers (Kelvin-Helmholtz) 16384x16384 fp32 (1 GPU)
   c5           channel flow 16384x16384 fp64 PER GPU, weak scaling
@@ -41,6 +42,8 @@ WORKLOADS = {
     # name: (description, global nx per GPU count fn, ny, dtype, bc, scaling, omega, inlet_rho, init, mask)
     "c4": dict(desc="cylinder wake 32768x32768 fp32, x-slab strong scaling", nx=32768, ny=32768, dtype="f32",
                bc="pipe", scaling="strong", omega=1.7, inlet_rho=1.003, init="pipe_ramp", mask="disk"),
+    "c1": dict(desc="Poiseuille pipe flow 256x128 fp64 (launch-bound: 32-step CUDA graphs)", nx=256, ny=128, dtype="f64",
+               bc="pipe", scaling="strong", omega=1.000265, inlet_rho=1.00495022, init="pipe_ramp", mask=None),
     "c2": dict(desc="Pipe_Flow_Obstacles 4096x1024 fp32 with obstacle mask", nx=4096, ny=1024, dtype="f32",
                bc="pipe", scaling="strong", omega=1.0, inlet_rho=1.01, init="pipe_ramp", mask="cs205", zero_vel=True),
     "c3": dict(desc="periodic vortex-sheet (Kelvin-Helmholtz) 16384x16384 fp32", nx=16384, ny=16384, dtype="f32",
