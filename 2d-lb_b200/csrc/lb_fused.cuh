@@ -97,6 +97,21 @@ __device__ __forceinline__ void st_vec(VT *p, const VT &v)
     else *p = v;
 }
 
+// predicated scalar load through the read-only path: `@p ld.global.nc` -- no branch
+template <typename T> __device__ __forceinline__ T ld_if(const T *p, bool pred);
+template <> __device__ __forceinline__ float ld_if<float>(const float *p, bool pred)
+{
+    float v = 0.0f;
+    asm volatile("{\n.reg .pred P;\nsetp.ne.b32 P, %2, 0;\n@P ld.global.nc.f32 %0, [%1];\n}" : "+f"(v) : "l"(p), "r"((int)pred));
+    return v;
+}
+template <> __device__ __forceinline__ double ld_if<double>(const double *p, bool pred)
+{
+    double v = 0.0;
+    asm volatile("{\n.reg .pred P;\nsetp.ne.b32 P, %2, 0;\n@P ld.global.nc.f64 %0, [%1];\n}" : "+d"(v) : "l"(p), "r"((int)pred));
+    return v;
+}
+
 template <typename T, int V, int LDP>
 __device__ __forceinline__ Pack<T, V> load_pack(const T *p)
 {
@@ -364,39 +379,31 @@ __global__ void __launch_bounds__(32 * WX * WY, MINB) fused_step_kernel(const St
             q[7] = load_pack<T, V, LDP>(pp + 3 * plane);
             q[8] = load_pack<T, V, LDP>(pp + 4 * plane);
             // --- elements that cross the warp boundary (same 32-B sector the neighbour warp loads) ---
-            T l1 = (T)0, l5 = (T)0, l8 = (T)0, r3 = (T)0, r6 = (T)0, r7 = (T)0;
-            if (lane == 0) {
-                l1 = pc[plane - 1];
-                l5 = pm[3 * plane - 1];
-                l8 = pp[4 * plane - 1];
-            }
-            if (lane == 31) {
-                r3 = pc[3 * plane + V];
-                r6 = pm[4 * plane + V];
-                r7 = pp[3 * plane + V];
-            }
+            //     written as predicated loads off the vector loads' own addresses: no branch, no new address math
+            const T l1 = ld_if<T>(pc + plane - 1, lane == 0);
+            const T l5 = ld_if<T>(pm + 3 * plane - 1, lane == 0);
+            const T l8 = ld_if<T>(pp + 4 * plane - 1, lane == 0);
+            const T r3 = ld_if<T>(pc + 3 * plane + V, lane == 31);
+            const T r6 = ld_if<T>(pm + 4 * plane + V, lane == 31);
+            const T r7 = ld_if<T>(pp + 3 * plane + V, lane == 31);
             // --- elements that cross the thread boundary ---
-            {
-                const T s1 = __shfl_up_sync(0xffffffffu, q[1].v[V - 1], 1);
-                const T s5 = __shfl_up_sync(0xffffffffu, q[5].v[V - 1], 1);
-                const T s8 = __shfl_up_sync(0xffffffffu, q[8].v[V - 1], 1);
-                const T s3 = __shfl_down_sync(0xffffffffu, q[3].v[0], 1);
-                const T s6 = __shfl_down_sync(0xffffffffu, q[6].v[0], 1);
-                const T s7 = __shfl_down_sync(0xffffffffu, q[7].v[0], 1);
-                if (lane != 0) { l1 = s1; l5 = s5; l8 = s8; }
-                if (lane != 31) { r3 = s3; r6 = s6; r7 = s7; }
-            }
+            const T s1 = __shfl_up_sync(0xffffffffu, q[1].v[V - 1], 1);
+            const T s5 = __shfl_up_sync(0xffffffffu, q[5].v[V - 1], 1);
+            const T s8 = __shfl_up_sync(0xffffffffu, q[8].v[V - 1], 1);
+            const T s3 = __shfl_down_sync(0xffffffffu, q[3].v[0], 1);
+            const T s6 = __shfl_down_sync(0xffffffffu, q[6].v[0], 1);
+            const T s7 = __shfl_down_sync(0xffffffffu, q[7].v[0], 1);
             // shift: populations moving +x take the value of the cell to their left, and vice versa
 #pragma unroll
             for (int e = V - 1; e > 0; --e) {
                 q[1].v[e] = q[1].v[e - 1]; q[5].v[e] = q[5].v[e - 1]; q[8].v[e] = q[8].v[e - 1];
             }
-            q[1].v[0] = l1; q[5].v[0] = l5; q[8].v[0] = l8;
+            q[1].v[0] = lane == 0 ? l1 : s1; q[5].v[0] = lane == 0 ? l5 : s5; q[8].v[0] = lane == 0 ? l8 : s8;
 #pragma unroll
             for (int e = 0; e < V - 1; ++e) {
                 q[3].v[e] = q[3].v[e + 1]; q[6].v[e] = q[6].v[e + 1]; q[7].v[e] = q[7].v[e + 1];
             }
-            q[3].v[V - 1] = r3; q[6].v[V - 1] = r6; q[7].v[V - 1] = r7;
+            q[3].v[V - 1] = lane == 31 ? r3 : s3; q[6].v[V - 1] = lane == 31 ? r6 : s6; q[7].v[V - 1] = lane == 31 ? r7 : s7;
 
             finish_row<T, V, MATH, STP, MODEL>(p, c, q, src, dst, x0, span0, y, ym, yp);
         }
