@@ -296,6 +296,19 @@ __global__ void k_subsample(int nx, int ny, int pitch, int sx, int sy, int ox, c
     dst[(long long)j * ox + i] = src[(long long)(j * sy) * pitch + (long long)i * sx];
 }
 
+__global__ void k_selftest_rcp(uint32_t first, uint32_t last, unsigned long long *bad)
+{
+    unsigned long long local = 0;
+    const unsigned long long n = (unsigned long long)last - first + 1ull;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const float x = __uint_as_float(first + (uint32_t)i);
+        if (__float_as_uint(rcp_rn_nobranch(x)) != __float_as_uint(1.0f / x)) ++local;
+        if (__float_as_uint(rcp_rn_nobranch(-x)) != __float_as_uint(1.0f / -x)) ++local;
+    }
+    if (local) atomicAdd(bad, local);
+}
+
 // one flag byte per 32 cells of a row: does the group contain a solid node
 __global__ void k_span_solid(int nx, int ny, const uint8_t *mask, int mask_pitch, uint8_t *span_solid, int nspans)
 {
@@ -542,6 +555,21 @@ int lb_device_count(void)
 }
 
 const char *lb_last_error(const lb_sim *sim) { return sim ? sim->err.c_str() : g_create_error.c_str(); }
+
+int lb_selftest_rcp(int device, uint32_t first_bits, uint32_t last_bits, uint64_t *mismatches)
+{
+    if (!mismatches || last_bits < first_bits) return LB_ERR_INVALID;
+    if (cudaSetDevice(device) != cudaSuccess) return LB_ERR_CUDA;
+    unsigned long long *d = nullptr, h = 0;
+    if (cudaMalloc((void **)&d, sizeof(h)) != cudaSuccess) return LB_ERR_CUDA;
+    cudaMemset(d, 0, sizeof(h));
+    k_selftest_rcp<<<148 * 16, 256>>>(first_bits, last_bits, d);
+    const cudaError_t e = cudaMemcpy(&h, d, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return LB_ERR_CUDA;
+    *mismatches = h;
+    return LB_OK;
+}
 
 int lb_variant_count(void) { return g_nvariants; }
 const char *lb_variant_name(int v) { return (v >= 0 && v < g_nvariants) ? g_variants[v].name : nullptr; }

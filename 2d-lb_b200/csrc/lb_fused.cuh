@@ -174,50 +174,52 @@ __device__ __forceinline__ void finish_row(const StepParams &p, const Consts<T> 
     const bool has_east = (el_east >= 0 && el_east < V);
     const long long rc = (long long)y * pitch + x0;
 
-    // --- first / last column of the slab: wrap, ghost column, or domain boundary ---
-    if (has_west && p.west != EDGE_BOUNDARY) {
-        T a1, a5, a8;
-        if (p.west == EDGE_WRAP) {
-            a1 = src[1 * plane + (long long)y * pitch + (nx - 1)];
-            a5 = src[5 * plane + (long long)ym * pitch + (nx - 1)];
-            a8 = src[8 * plane + (long long)yp * pitch + (nx - 1)];
-        } else {
-            const T *gw = static_cast<const T *>(p.ghost_w);
-            a1 = __ldcv(gw + 0 * (ny + 2) + (y + 1));
-            a5 = __ldcv(gw + 1 * (ny + 2) + (ym + 1));
-            a8 = __ldcv(gw + 2 * (ny + 2) + (yp + 1));
-        }
-        q[1].v[0] = a1; q[5].v[0] = a5; q[8].v[0] = a8;
-    }
-    if (has_east && p.east != EDGE_BOUNDARY) {
-        T a3, a6, a7;
-        if (p.east == EDGE_WRAP) {
-            a3 = src[3 * plane + (long long)y * pitch];
-            a6 = src[6 * plane + (long long)ym * pitch];
-            a7 = src[7 * plane + (long long)yp * pitch];
-        } else {
-            const T *ge = static_cast<const T *>(p.ghost_e);
-            a3 = __ldcv(ge + 0 * (ny + 2) + (y + 1));
-            a6 = __ldcv(ge + 1 * (ny + 2) + (ym + 1));
-            a7 = __ldcv(ge + 2 * (ny + 2) + (yp + 1));
-        }
-#pragma unroll
-        for (int e = 0; e < V; ++e)
-            if (e == el_east) { q[3].v[e] = a3; q[6].v[e] = a6; q[7].v[e] = a7; }
-    }
-
-    // --- boundary closure: only threads that own a wall / inlet / outlet node ---
+    // --- threads that own the first / last column of the slab or a wall row (rare): slab-edge
+    //     fix-up (wrap, ghost column) and the boundary closure, behind ONE branch
     const bool row_is_wall = (!periodic) && (y == 0 || y == ny - 1);
-    if ((!periodic) && (row_is_wall || (has_west && p.west == EDGE_BOUNDARY) ||
-                        (has_east && p.east == EDGE_BOUNDARY))) {
+    if (has_west || has_east || row_is_wall) {
+        if (has_west && p.west != EDGE_BOUNDARY) {
+            T a1, a5, a8;
+            if (p.west == EDGE_WRAP) {
+                a1 = src[1 * plane + (long long)y * pitch + (nx - 1)];
+                a5 = src[5 * plane + (long long)ym * pitch + (nx - 1)];
+                a8 = src[8 * plane + (long long)yp * pitch + (nx - 1)];
+            } else {
+                const T *gw = static_cast<const T *>(p.ghost_w);
+                a1 = __ldcv(gw + 0 * (ny + 2) + (y + 1));
+                a5 = __ldcv(gw + 1 * (ny + 2) + (ym + 1));
+                a8 = __ldcv(gw + 2 * (ny + 2) + (yp + 1));
+            }
+            q[1].v[0] = a1; q[5].v[0] = a5; q[8].v[0] = a8;
+        }
+        if (has_east && p.east != EDGE_BOUNDARY) {
+            T a3, a6, a7;
+            if (p.east == EDGE_WRAP) {
+                a3 = src[3 * plane + (long long)y * pitch];
+                a6 = src[6 * plane + (long long)ym * pitch];
+                a7 = src[7 * plane + (long long)yp * pitch];
+            } else {
+                const T *ge = static_cast<const T *>(p.ghost_e);
+                a3 = __ldcv(ge + 0 * (ny + 2) + (y + 1));
+                a6 = __ldcv(ge + 1 * (ny + 2) + (ym + 1));
+                a7 = __ldcv(ge + 2 * (ny + 2) + (yp + 1));
+            }
 #pragma unroll
-        for (int e = 0; e < V; ++e) {
-            T g[9];
+            for (int e = 0; e < V; ++e)
+                if (e == el_east) { q[3].v[e] = a3; q[6].v[e] = a6; q[7].v[e] = a7; }
+        }
+        // boundary closure: only threads that own a wall / inlet / outlet node
+        if ((!periodic) && (row_is_wall || (has_west && p.west == EDGE_BOUNDARY) ||
+                            (has_east && p.east == EDGE_BOUNDARY))) {
 #pragma unroll
-            for (int j = 0; j < 9; ++j) g[j] = q[j].v[e];
-            pipe_bc<T, MODEL>(c, p.x_off + x0 + e, y, p.gnx, ny, g);
+            for (int e = 0; e < V; ++e) {
+                T g[9];
 #pragma unroll
-            for (int j = 0; j < 9; ++j) q[j].v[e] = g[j];
+                for (int j = 0; j < 9; ++j) g[j] = q[j].v[e];
+                pipe_bc<T, MODEL>(c, p.x_off + x0 + e, y, p.gnx, ny, g);
+#pragma unroll
+                for (int j = 0; j < 9; ++j) q[j].v[e] = g[j];
+            }
         }
     }
 
@@ -247,18 +249,30 @@ __device__ __forceinline__ void finish_row(const StepParams &p, const Consts<T> 
             }
         }
     }
-    const uint32_t zero_bits = p.zero_obstacle_velocity ? solid_bits : 0u;
-
-    // --- per node: moments + equilibrium + BGK relaxation, in registers ---
+    // --- per node: moments + equilibrium + BGK relaxation, in registers.  Warps that hold a solid node
+    //     whose velocity must be zeroed take a copy of the loop with the per-node flag; all others run
+    //     the flag-free copy (warp-uniform choice).
     Pack<T, V> mrho, mu, mv;
+    if (p.zero_obstacle_velocity && __any_sync(0xffffffffu, solid_bits != 0)) {
 #pragma unroll
-    for (int e = 0; e < V; ++e) {
-        T g[9];
+        for (int e = 0; e < V; ++e) {
+            T g[9];
 #pragma unroll
-        for (int j = 0; j < 9; ++j) g[j] = q[j].v[e];
-        collide_node<T, MATH, MODEL>(c, g, mrho.v[e], mu.v[e], mv.v[e], (zero_bits >> e) & 1u);
+            for (int j = 0; j < 9; ++j) g[j] = q[j].v[e];
+            collide_node<T, MATH, MODEL>(c, g, mrho.v[e], mu.v[e], mv.v[e], (solid_bits >> e) & 1u);
 #pragma unroll
-        for (int j = 0; j < 9; ++j) q[j].v[e] = g[j];
+            for (int j = 0; j < 9; ++j) q[j].v[e] = g[j];
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+            T g[9];
+#pragma unroll
+            for (int j = 0; j < 9; ++j) g[j] = q[j].v[e];
+            collide_node<T, MATH, MODEL>(c, g, mrho.v[e], mu.v[e], mv.v[e], false);
+#pragma unroll
+            for (int j = 0; j < 9; ++j) q[j].v[e] = g[j];
+        }
     }
 
     // --- stores: aligned vectors; the one thread straddling column nx-1 goes scalar ---
@@ -287,6 +301,7 @@ __device__ __forceinline__ void finish_row(const StepParams &p, const Consts<T> 
     }
 
     // --- publish my boundary columns into the neighbours' ghost columns ---
+    if (!(has_west || has_east)) return;
     if (has_west && p.west == EDGE_HALO) {
         T *ow = static_cast<T *>(p.out_w);
         ow[0 * (ny + 2) + (y + 1)] = q[3].v[0];

@@ -187,6 +187,10 @@ int lb_init_synthetic(lb_sim *sim, int kind, double u0, double amplitude, uint64
 int lb_set_mask_disk(lb_sim *sim, double cx, double cy, double r);
 
 /* -- diagnostics */
+/* Device self-test of the branch-free reciprocal used by STRICT fp32 math: compares it with IEEE
+ * division for every float whose bit pattern lies in [first_bits, last_bits]; returns the count of
+ * mismatches in *mismatches. */
+int lb_selftest_rcp(int device, uint32_t first_bits, uint32_t last_bits, uint64_t *mismatches);
 /* sum over all populations and cells of this slab, accumulated in double (mass check) */
 int lb_total_mass(lb_sim *sim, double *out);
 /* number of fused-kernel launches issued by this handle since creation */

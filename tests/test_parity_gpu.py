@@ -548,3 +548,17 @@ def test_tma_variants_bitexact(gpu, orc):
     with Lattice(64, 32, 1.0, bc="periodic") as sim:
         with pytest.raises(native.LBError, match="TMA"):
             sim.set_variant("f32.strict.tma.v4.ty4.b6")
+
+
+def test_rcp_fast_path_is_ieee(gpu):
+    """STRICT fp32 math takes 1/rho with MUFU.RCP + one FMA Newton step and no special-case branch.
+    Exhaustive device check: for EVERY float x with 2^-100 <= |x| <= 2^100 the result equals the IEEE
+    quotient 1.0f/x bit for bit."""
+    import ctypes as ct
+    import struct
+    from lb_b200 import native
+    lo = struct.unpack("<I", struct.pack("<f", 2.0 ** -100))[0]
+    hi = struct.unpack("<I", struct.pack("<f", 2.0 ** 100))[0]
+    bad = ct.c_uint64(12345)
+    native.check(native.lib().lb_selftest_rcp(0, lo, hi, ct.byref(bad)))
+    assert bad.value == 0, f"{bad.value} mismatches among {2 * (hi - lo + 1)} inputs"
