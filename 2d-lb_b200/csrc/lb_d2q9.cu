@@ -400,6 +400,24 @@ __global__ void k_mass(int nx, int ny, int pitch, long long plane, const T *f, d
     if (threadIdx.x == 0) out[y] = sh[0];
 }
 
+template <typename T>
+__global__ void k_checksum(int nx, int ny, int pitch, long long plane, const T *f, unsigned long long *out)
+{
+    unsigned long long acc = 0;
+    const int y = blockIdx.x;
+    for (int x = threadIdx.x; x < nx; x += blockDim.x) {
+        const long long i = (long long)y * pitch + x;
+#pragma unroll
+        for (int j = 0; j < 9; ++j) {
+            const T val = f[j * plane + i];
+            if (sizeof(T) == 4) acc += (unsigned long long)__float_as_uint((float)val);
+            else acc += (unsigned long long)__double_as_longlong((double)val);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
+}
+
 // copies the current boundary columns into the neighbours' ghost columns and publishes the flag
 template <typename T>
 __global__ void k_halo_prime(int nx, int ny, int pitch, long long plane, const T *f, T *out_w, T *out_e,
@@ -1073,6 +1091,24 @@ int lb_total_mass(lb_sim *sim, double *out)
     long double acc = 0;
     for (double r : rows) acc += r;
     *out = (double)acc;
+    return LB_OK;
+}
+
+int lb_checksum(lb_sim *sim, uint64_t *out)
+{
+    if (!sim || !out) return LB_ERR_INVALID;
+    CU(cudaSetDevice(sim->cfg.device));
+    unsigned long long *d = (unsigned long long *)sim->mass_scratch;      // ny doubles: room for one u64
+    CU(cudaMemsetAsync(d, 0, sizeof(unsigned long long), sim->stream));
+    if (sim->cfg.dtype == LB_F32)
+        k_checksum<float><<<sim->cfg.ny, 256, 0, sim->stream>>>(sim->cfg.nx, sim->cfg.ny, sim->pitch, sim->plane, (const float *)sim->buf[sim->cur], d);
+    else
+        k_checksum<double><<<sim->cfg.ny, 256, 0, sim->stream>>>(sim->cfg.nx, sim->cfg.ny, sim->pitch, sim->plane, (const double *)sim->buf[sim->cur], d);
+    CU(cudaGetLastError());
+    unsigned long long h = 0;
+    CU(cudaMemcpyAsync(&h, d, sizeof(h), cudaMemcpyDeviceToHost, sim->stream));
+    CU(cudaStreamSynchronize(sim->stream));
+    *out = h;
     return LB_OK;
 }
 

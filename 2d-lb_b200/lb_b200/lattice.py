@@ -224,6 +224,12 @@ class Lattice:
         self._call("lb_total_mass", ct.byref(out))
         return out.value
 
+    def checksum(self):
+        """Order-independent exact checksum of the populations (64-bit sum of their bit patterns)."""
+        out = ct.c_uint64()
+        self._call("lb_checksum", ct.byref(out))
+        return out.value
+
     @property
     def launch_count(self):
         return int(N.lib().lb_launch_count(self._h))
@@ -350,3 +356,15 @@ class LocalSlabs:
 
     def total_mass(self):
         return sum(s.total_mass() for s in self.slabs)
+
+    def checksum(self):
+        return sum(s.checksum() for s in self.slabs) & 0xFFFFFFFFFFFFFFFF
+
+    def init_synthetic(self, *a, **k):
+        for s in self.slabs:
+            s.init_synthetic(*a, **k)
+        self.prime()
+
+    def set_mask_disk(self, *a):
+        for s in self.slabs:
+            s.set_mask_disk(*a)

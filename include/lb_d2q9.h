@@ -193,6 +193,10 @@ int lb_set_mask_disk(lb_sim *sim, double cx, double cy, double r);
 int lb_selftest_rcp(int device, uint32_t first_bits, uint32_t last_bits, uint64_t *mismatches);
 /* sum over all populations and cells of this slab, accumulated in double (mass check) */
 int lb_total_mass(lb_sim *sim, double *out);
+/* order-independent exact checksum of the populations: the 64-bit wrap-around sum of the raw bit
+ * patterns of all 9*nx*ny values (fp32 patterns are zero-extended).  Equal checksums under a
+ * re-decomposition into slabs or a periodic shift of the lattice mean bit-identical multisets. */
+int lb_checksum(lb_sim *sim, uint64_t *out);
 /* number of fused-kernel launches issued by this handle since creation */
 int64_t lb_launch_count(const lb_sim *sim);
 /* choose one of the compiled tile configurations of the fused kernel (-1 = default);
