@@ -367,7 +367,7 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            v, wall, kind, cells = time_reference_cpu(300, 2, 1)
+            v, wall, kind, cells = time_reference_cpu(600, 2, 1)
             cpu = {"value": v, "unit": "MLUPS", "cores": 1, "kind": kind,
                    "sample": f"{CPU_SAMPLE}, 300 steps, 1 thread ({wall:.1f} s) of {os.cpu_count()} host cores available"}
         except Exception as exc:
