@@ -13,7 +13,8 @@ follow the reference line by line so that the same seed gives the same initial p
   Pipe_Flow_Cylinder            :441-518                 Pipe_Flow_Obstacles (template) :616-657
 
 Extensions (keyword-only, defaults reproduce the reference): dtype, math, device, verbose,
-zero_obstacle_velocity_each_step, and units='opencl' | 'cython'.  The reference's OpenCL and
+zero_obstacle_velocity_each_step, devices=[...] (x-slab decomposition over several GPUs of this
+process, peer-memory halos; the reference is single-device), and units='opencl' | 'cython'.  The reference's OpenCL and
 Cython modules map the same physical inputs to different lattice parameters:
 units='cython' selects cython_dim.pyx's algebra (T = 8 rho nu/(|grad p| L), Reynolds-number based
 omega, pressure drop scaled by the non-dimensional gradient; cython_dim.pyx:70,85-88,115-116,
@@ -22,7 +23,7 @@ omega, pressure drop scaled by the non-dimensional gradient; cython_dim.pyx:70,8
 import numpy as np
 
 from . import draw
-from .lattice import Lattice, cs2
+from .lattice import Lattice, LocalSlabs, cs2
 
 NUM_JUMPERS = 9
 
@@ -46,7 +47,8 @@ class Pipe_Flow(object):
                  N=200, time_prefactor=1.,
                  two_d_local_size=(32, 32), three_d_local_size=(32, 32, 1), use_interop=False,
                  dtype=np.float32, math="strict", device=0, verbose=True,
-                 zero_obstacle_velocity_each_step=None, units="opencl"):
+                 zero_obstacle_velocity_each_step=None, units="opencl", devices=None):
+        self._devices = list(devices) if devices else None
         if units not in ("opencl", "cython"):
             raise ValueError("units must be 'opencl' or 'cython'")
         self._units = units
@@ -156,9 +158,12 @@ class Pipe_Flow(object):
 
     def init_cuda(self):
         """Replaces init_opencl + allocate_constants (opencl_dim.py:203-255)."""
-        self.sim = Lattice(self.nx, self.ny, self.omega, self.inlet_rho, self.outlet_rho, bc="pipe",
-                           dtype=self.dtype, math=self._math, device=self._device,
-                           zero_obstacle_velocity=self._zero_vel)
+        kw = dict(omega=self.omega, inlet_rho=self.inlet_rho, outlet_rho=self.outlet_rho, bc="pipe",
+                  dtype=self.dtype, math=self._math, zero_obstacle_velocity=self._zero_vel)
+        if self._devices and len(self._devices) > 1:
+            self.sim = LocalSlabs(self.nx, self.ny, devices=self._devices, **kw)      # one x-slab per GPU
+        else:
+            self.sim = Lattice(self.nx, self.ny, device=self._devices[0] if self._devices else self._device, **kw)
 
     # -- initialisation (individually callable, SURVEY.md F2) -------------------------------
     def init_hydro(self):

@@ -294,20 +294,34 @@ def slab_edges(rank, parts, bc):
 
 
 class LocalSlabs:
-    """`parts` x-slabs of one lattice living in ONE process (virtual ranks).
+    """`parts` x-slabs of one lattice living in ONE process, with the same interface as `Lattice`
+    (device-layout global arrays in, global arrays out).
 
-    Slabs on the same device share one stream and advance in lock-step, one step at a time, so the flag
-    hand-shake of the fused kernel is always already satisfied when a kernel starts.  Used to
-    prove that the decomposition is arithmetic-neutral (bit-identical to a single slab) and as
-    the single-process multi-device path when `devices` lists several GPUs.
+    * several slabs on ONE device ("virtual ranks"): they share a stream and advance in lock-step,
+      one step at a time, so the flag hand-shake of the fused kernel is always already satisfied
+      when a kernel starts.  Used to prove that the decomposition is arithmetic-neutral.
+    * one slab per DEVICE (`devices=[0, 1, ...]`): every slab has its own stream; steps are enqueued
+      asynchronously in bounded chunks, round-robin over the slabs, and the kernels synchronise
+      among themselves through the peer-memory flags -- the single-process multi-GPU path behind
+      `Pipe_Flow(..., devices=[...])`.
     """
 
-    def __init__(self, global_nx, ny, parts, devices=None, **kw):
+    CHUNK = 32      # steps enqueued per slab before moving to the next one (bounds launch-queue depth)
+
+    def __init__(self, global_nx, ny, parts=None, devices=None, **kw):
+        if parts is None:
+            parts = len(devices)
         self.global_nx, self.ny, self.parts = int(global_nx), int(ny), int(parts)
+        self.nx = self.global_nx
         self.bc = kw.get("bc", "pipe")
+        self.scheme = kw.get("scheme", "opencl")
         self.ranges = split_slabs(global_nx, parts)
-        devices = devices or [kw.pop("device", 0)] * parts
+        devices = list(devices) if devices else [kw.pop("device", 0)] * parts
         kw.pop("device", None)
+        if len(devices) != parts:
+            raise ValueError("one device per slab")
+        self.devices = devices
+        self.concurrent = len(set(devices)) == parts and parts > 1
         self.slabs = []
         streams = {}          # one stream per device, shared by the slabs that live there
         for r, (x0, w) in enumerate(self.ranges):
@@ -318,47 +332,109 @@ class LocalSlabs:
             s._stream_owner = lender       # the lender (which owns the stream) must outlive the borrower
             streams.setdefault(devices[r], s)
             self.slabs.append(s)
+        self.dtype = self.slabs[0].dtype
         if parts > 1:
             for r, s in enumerate(self.slabs):
                 if s.cfg.west_edge == N.EDGE_HALO:
                     s.halo_connect_local("west", self.slabs[(r - 1) % parts])
                 if s.cfg.east_edge == N.EDGE_HALO:
                     s.halo_connect_local("east", self.slabs[(r + 1) % parts])
+        self._primed = False
 
     def close(self):
         for s in reversed(self.slabs):     # borrowers of a shared stream first, its owner last
             s.close()
 
-    def set_mask(self, mask):
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _each(self, a):
         for s, (x0, w) in zip(self.slabs, self.ranges):
-            s.set_mask(np.ascontiguousarray(mask[:, x0:x0 + w]))
+            yield s, (None if a is None else np.ascontiguousarray(a[..., x0:x0 + w]))
+
+    # -- uploads (global device-layout arrays) -------------------------------------------------------
+    def set_mask(self, mask):
+        for s, part in self._each(None if mask is None else np.asarray(mask)):
+            s.set_mask(part)
 
     def upload_f(self, f):
-        for s, (x0, w) in zip(self.slabs, self.ranges):
-            s.upload_f(np.ascontiguousarray(f[:, :, x0:x0 + w]))
+        for s, part in self._each(np.asarray(f)):
+            s.upload_f(part)
         self.prime()
 
+    def upload_moments(self, rho=None, u=None, v=None):
+        parts = [list(self._each(None if a is None else np.asarray(a))) for a in (rho, u, v)]
+        for k, s in enumerate(self.slabs):
+            s.upload_moments(parts[0][k][1], parts[1][k][1], parts[2][k][1])
+
     def prime(self):
+        """Publish every slab's boundary columns to its neighbours (after any change of f)."""
         for s in self.slabs:
             s.sync()
         for s in self.slabs:
             s.halo_prime()
+        self._primed = True
 
-    def run(self, n):
-        for _ in range(int(n)):
-            for s in self.slabs:
-                s.run(1, sync=False)
+    # -- hot path ---------------------------------------------------------------------------------
+    def run(self, n, sync=True):
+        n = int(n)
+        if self.parts > 1 and not self._primed:
+            self.prime()
+        if self.concurrent:
+            done = 0
+            while done < n:
+                chunk = min(self.CHUNK, n - done)
+                for s in self.slabs:
+                    s.run(chunk, sync=False)
+                done += chunk
+        else:
+            for _ in range(n):
+                for s in self.slabs:
+                    s.run(1, sync=False)
+        if sync:
+            self.sync()
+
+    def sync(self):
         for s in self.slabs:
             s.sync()
 
-    def download(self, field):
-        return np.concatenate([s.download(field) for s in self.slabs], axis=-1)
+    # -- stages that need no halo -----------------------------------------------------------------
+    def update_feq(self):
+        for s in self.slabs:
+            s.update_feq()
+
+    def zero_velocity_in_obstacle(self):
+        for s in self.slabs:
+            s.zero_velocity_in_obstacle()
+
+    def _no_single_stage(self, *_):
+        raise N.LBError(-3, "single stages are not available on a slab-decomposed lattice; use run()")
+
+    move = move_bcs = update_hydro = collide_particles = _no_single_stage
+
+    # -- readback ------------------------------------------------------------------------------------
+    def download(self, field, out=None):
+        whole = np.concatenate([s.download(field) for s in self.slabs], axis=-1)
+        if out is None:
+            return whole
+        out[...] = whole
+        return out
+
+    def fields(self):
+        return {k: self.download(k) for k in ("f", "feq", "rho", "u", "v")}
 
     def total_mass(self):
         return sum(s.total_mass() for s in self.slabs)
 
     def checksum(self):
         return sum(s.checksum() for s in self.slabs) & 0xFFFFFFFFFFFFFFFF
+
+    @property
+    def launch_count(self):
+        return sum(s.launch_count for s in self.slabs)
 
     def init_synthetic(self, *a, **k):
         for s in self.slabs:

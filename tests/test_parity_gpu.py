@@ -624,3 +624,24 @@ def test_full_size_periodic_box_c3(gpu, dtype):
             sums.append(sim.checksum())
         assert abs(m1 - m0) / m0 < (2e-6 if dtype == np.float32 else 1e-13)
     assert sums[0] == sums[1]
+
+
+def test_drop_in_class_on_virtual_slabs(gpu, orc):
+    """Pipe_Flow_Cylinder(devices=[0, 0, 0]): the drop-in class on three x-slabs (virtual ranks on one
+    GPU here; one per GPU in tools/check_multigpu.py) gives the single-lattice result bit for bit."""
+    import lb_b200.dimensionless as lb
+    kw = dict(cylinder_center=[0.75, 0.5], cylinder_radius=0.1, diameter=1., rho=1., viscosity=1., pressure_grad=-10.,
+              pipe_length=3., N=8, time_prefactor=4., verbose=False)
+    np.random.seed(3)
+    multi = lb.Pipe_Flow_Cylinder(devices=[0, 0, 0], **kw)
+    np.random.seed(3)
+    single = lb.Pipe_Flow_Cylinder(**kw)
+    assert np.array_equal(multi.get_fields()["f"], single.get_fields()["f"])
+    multi.run(60)
+    single.run(60)
+    fm, fs = multi.get_fields(), single.get_fields()
+    for k in ("f", "feq", "rho", "u", "v"):
+        assert fm[k].flags.f_contiguous and np.array_equal(fm[k], fs[k]), k
+    multi.run(5)
+    single.run(5)
+    assert np.array_equal(multi.get_fields()["f"], single.get_fields()["f"])

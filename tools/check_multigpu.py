@@ -65,6 +65,24 @@ def main():
                           f"{'bit-identical' if same else 'MISMATCH'}  mass {mass:.10e} vs {m1:.10e}", flush=True)
                     ok = ok and same
                 dist.barrier()
+    # single-process multi-device path behind the drop-in classes (rank 0 drives all visible GPUs)
+    if rank == 0 and torch.cuda.device_count() >= 2:
+        import lb_b200.dimensionless as lb
+        devs = list(range(min(torch.cuda.device_count(), 4)))
+        kw = dict(cylinder_center=[0.75, 0.5], cylinder_radius=0.1, diameter=1., rho=1., viscosity=1., pressure_grad=-10.,
+                  pipe_length=3., N=20, time_prefactor=4., verbose=False)
+        np.random.seed(3)
+        multi = lb.Pipe_Flow_Cylinder(devices=devs, **kw)
+        np.random.seed(3)
+        single = lb.Pipe_Flow_Cylinder(device=local, **kw)
+        multi.run(150)
+        single.run(150)
+        fm, fs = multi.get_fields(), single.get_fields()
+        same = all(np.array_equal(fm[k], fs[k]) for k in ("f", "feq", "rho", "u", "v"))
+        print(f"[check_multigpu] single-process Pipe_Flow_Cylinder(devices={devs}) {multi.nx}x{multi.ny}: "
+              f"{'bit-identical' if same else 'MISMATCH'}", flush=True)
+        ok = ok and same
+    dist.barrier()
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)
     dist.destroy_process_group()
