@@ -50,9 +50,13 @@ def main():
     sim.init_synthetic("pipe_ramp" if a.bc == "pipe" else "shear_layers", u0=0.05, amplitude=1e-3, seed=1)
     sim.sync()
     rows = []
-    names = [n for n in native.variants() if n.startswith(f"{a.dtype}.{a.math}.") and a.filter in n]
+    names = [n for n in native.variants() if n.startswith(f"{a.dtype}.{a.math}.") and a.filter in n and ".d2q9i." not in n]
     for name in names:
-        sim.set_variant(name)
+        try:
+            sim.set_variant(name)
+        except native.LBError as exc:          # e.g. TMA variants on a periodic box
+            print(f"{name:42s} skipped: {exc}", flush=True)
+            continue
         sim.run(3)
         best = None
         for _ in range(a.reps):
