@@ -148,3 +148,38 @@ def test_mask_ingestion(tmp_path):
     src = masks.unpack(g)
     assert src.shape == (800, 400) and abs(src.mean() - 0.087) < 0.001      # 8.7 % solid
     assert not (src[0].any() or src[-1].any() or src[:, 0].any() or src[:, -1].any())
+
+
+@pytest.mark.parametrize("name", ["opencl_pipe_65x33", "opencl_cylinder_121x41", "opencl_d2q9i_pipe_49x25",
+                                  "opencl_d2q9i_cylinder_121x41"])
+def test_class_parameter_algebra_equals_the_reference_opencl_classes(name):
+    """Grid size, omega, inlet density and cylinder mask computed by the drop-in classes (device calls
+    stubbed out) equal what the reference's opencl_dim / opencl_dim_D2Q9i classes computed for the
+    same constructor call (stored with the golden vectors), to the last bit."""
+    import ast
+    import lb_b200.dimensionless as lb
+    from lb_b200 import dimensionless_D2Q9i as lbi
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
+    kw = ast.literal_eval(str(g["ctor_kwargs"]))
+    mod = lbi if "d2q9i" in name else lb
+    base = mod.Pipe_Flow_Cylinder if "cylinder" in name else mod.Pipe_Flow
+
+    class NoDevice(base):
+        def init_cuda(self):
+            pass
+
+        def init_hydro(self):
+            self._set_boundary_densities()
+
+        def update_feq(self):
+            pass
+
+        def init_pop(self):
+            pass
+
+    s = NoDevice(verbose=False, **kw)
+    assert (s.nx, s.ny) == (int(g["nx"]), int(g["ny"]))
+    assert float(s.omega) == float(g["omega"]) and float(s.inlet_rho) == float(g["inlet_rho"])
+    assert float(s.outlet_rho) == float(g["outlet_rho"])
+    if "mask" in g.files:
+        assert np.array_equal(s.obstacle_mask_host, g["mask"])
