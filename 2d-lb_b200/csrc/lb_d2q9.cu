@@ -5,6 +5,7 @@
 #include "../../include/lb_d2q9.h"
 #include "lb_fused.cuh"
 #include "lb_cython.cuh"
+#include "lb_oldcl.cuh"
 #include "lb_tma.cuh"
 
 #include <cstdio>
@@ -44,7 +45,8 @@ struct lb_sim {
     lb_config cfg;
     int elem = 4;                 // bytes per population value
     int uv_elem = 4;              // bytes per u / v value (8 for the cython schemes: float64 like the reference)
-    bool prestream_done = false;  // cython schemes: is the next step's BC + swap already applied to `cur`
+    bool prestream_done = false;  // cython / opencl_old schemes: is the next step's BC + swap already applied to `cur`
+    float *frozen = nullptr;      // opencl_old: the populations `move` never writes (lb_oldcl.cuh)
     int pitch = 0;                // row pitch in elements (multiple of 512 B)
     long long plane = 0;          // elements per plane
     size_t buf_bytes = 0;         // bytes of one guarded 9-plane buffer
@@ -461,6 +463,22 @@ static CyConsts cy_consts_of(const lb_sim *s)
                           s->cfg.u_west, s->cfg.u_east);
 }
 
+static inline bool is_cython(const lb_sim *s) { return s->cfg.scheme == LB_SCHEME_CYTHON || s->cfg.scheme == LB_SCHEME_CYTHON_OLD; }
+static inline bool is_oldcl(const lb_sim *s) { return s->cfg.scheme == LB_SCHEME_OPENCL_OLD; }
+
+static OcParams oc_params_of(const lb_sim *s)
+{
+    OcParams p{};
+    p.plane = s->plane; p.nx = s->cfg.nx; p.ny = s->cfg.ny; p.pitch = s->pitch;
+    p.mask = s->mask; p.mask_pitch = s->mask_pitch;
+    p.rho = (float *)s->rho; p.u = (float *)s->u; p.v = (float *)s->v;
+    p.frozen = s->frozen;
+    p.c = consts_of<float>(s);
+    p.u_w = (float)s->cfg.u_west; p.u_e = (float)s->cfg.u_east;
+    p.kw = 1. / (1. - (double)p.u_w); p.ke = 1. / (1. + (double)p.u_e);
+    return p;
+}
+
 static void drop_graphs(lb_sim *s)
 {
     for (int i = 0; i < 2; ++i) {
@@ -603,8 +621,11 @@ int lb_create(const lb_config *cfg, lb_sim **out)
     if (cfg->dtype != LB_F32 && cfg->dtype != LB_F64) return fail(nullptr, LB_ERR_INVALID, "lb_create: bad dtype");
     if (cfg->bc != LB_BC_PIPE && cfg->bc != LB_BC_PERIODIC && cfg->bc != LB_BC_VELOCITY_YPERIODIC)
         return fail(nullptr, LB_ERR_INVALID, "lb_create: bad bc");
-    if (cfg->bc == LB_BC_VELOCITY_YPERIODIC && (cfg->scheme != LB_SCHEME_CYTHON_OLD || cfg->ny < 4))
-        return fail(nullptr, LB_ERR_INVALID, "lb_create: LB_BC_VELOCITY_YPERIODIC needs LB_SCHEME_CYTHON_OLD and ny >= 4");
+    if (cfg->bc == LB_BC_VELOCITY_YPERIODIC &&
+        ((cfg->scheme != LB_SCHEME_CYTHON_OLD && cfg->scheme != LB_SCHEME_OPENCL_OLD) || cfg->ny < 4))
+        return fail(nullptr, LB_ERR_INVALID, "lb_create: LB_BC_VELOCITY_YPERIODIC needs LB_SCHEME_CYTHON_OLD or LB_SCHEME_OPENCL_OLD and ny >= 4");
+    if (cfg->scheme == LB_SCHEME_OPENCL_OLD && cfg->bc != LB_BC_VELOCITY_YPERIODIC)
+        return fail(nullptr, LB_ERR_INVALID, "lb_create: LB_SCHEME_OPENCL_OLD serves LB_BC_VELOCITY_YPERIODIC only (the pressure-driven classes of OLD/opencl.py diverge as shipped)");
     if (cfg->math != LB_MATH_STRICT && cfg->math != LB_MATH_FAST) return fail(nullptr, LB_ERR_INVALID, "lb_create: bad math");
     for (int e : {cfg->west_edge, cfg->east_edge}) {
         if (e < LB_EDGE_BOUNDARY || e > LB_EDGE_HALO) return fail(nullptr, LB_ERR_INVALID, "lb_create: bad edge kind");
@@ -616,7 +637,7 @@ int lb_create(const lb_config *cfg, lb_sim **out)
     if (cfg->global_nx < cfg->nx || cfg->x_offset < 0 || cfg->x_offset + cfg->nx > cfg->global_nx)
         return fail(nullptr, LB_ERR_INVALID, "lb_create: slab does not fit the global lattice");
     if (!(cfg->omega > 0.0 && cfg->omega < 2.0)) return fail(nullptr, LB_ERR_INVALID, "lb_create: omega must be in (0,2)");
-    if (cfg->scheme < LB_SCHEME_OPENCL || cfg->scheme > LB_SCHEME_CYTHON_OLD)
+    if (cfg->scheme < LB_SCHEME_OPENCL || cfg->scheme > LB_SCHEME_OPENCL_OLD)
         return fail(nullptr, LB_ERR_INVALID, "lb_create: bad scheme");
     if (cfg->model != LB_MODEL_D2Q9 && cfg->model != LB_MODEL_D2Q9I) return fail(nullptr, LB_ERR_INVALID, "lb_create: bad model");
     if (cfg->model == LB_MODEL_D2Q9I && (cfg->scheme != LB_SCHEME_OPENCL || cfg->bc != LB_BC_PIPE))
@@ -624,7 +645,7 @@ int lb_create(const lb_config *cfg, lb_sim **out)
     if (cfg->scheme != LB_SCHEME_OPENCL &&
         (cfg->dtype != LB_F32 || cfg->bc == LB_BC_PERIODIC || cfg->west_edge != LB_EDGE_BOUNDARY ||
          cfg->east_edge != LB_EDGE_BOUNDARY || cfg->global_nx != cfg->nx))
-        return fail(nullptr, LB_ERR_INVALID, "lb_create: the cython schemes need dtype F32, bc PIPE and a single slab");
+        return fail(nullptr, LB_ERR_INVALID, "lb_create: the cython and opencl_old schemes need dtype F32, a non-periodic bc and a single slab");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         cudaGetLastError();
@@ -635,7 +656,7 @@ int lb_create(const lb_config *cfg, lb_sim **out)
     sim = new lb_sim();
     sim->cfg = *cfg;
     sim->elem = cfg->dtype == LB_F32 ? 4 : 8;
-    sim->uv_elem = cfg->scheme == LB_SCHEME_OPENCL ? sim->elem : 8;
+    sim->uv_elem = is_cython(sim) ? 8 : sim->elem;
     const int per512 = 512 / sim->elem;
     sim->pitch = (cfg->nx + per512 - 1) / per512 * per512;
     sim->plane = (long long)sim->pitch * cfg->ny;
@@ -662,6 +683,10 @@ int lb_create(const lb_config *cfg, lb_sim **out)
     CUC(cudaMemsetAsync(sim->u, 0, mom_uv, sim->stream));
     CUC(cudaMemsetAsync(sim->v, 0, mom_uv, sim->stream));
     CUC(cudaMalloc((void **)&sim->mass_scratch, sizeof(double) * cfg->ny));
+    if (is_oldcl(sim)) {
+        CUC(cudaMalloc((void **)&sim->frozen, sizeof(float) * oc_frozen_floats(cfg->nx, cfg->ny)));
+        CUC(cudaMemsetAsync(sim->frozen, 0, sizeof(float) * oc_frozen_floats(cfg->nx, cfg->ny), sim->stream));
+    }
     if (cfg->west_edge == LB_EDGE_HALO || cfg->east_edge == LB_EDGE_HALO) {
         sim->hl = halo_layout(cfg->ny, sim->elem);
         CUC(cudaMalloc((void **)&sim->halo, sim->hl.total));
@@ -683,7 +708,7 @@ int lb_destroy(lb_sim *sim)
         if (sim->peer[side] && sim->peer_ipc[side]) cudaIpcCloseMemHandle(sim->peer[side]);
     for (int i = 0; i < 2; ++i) cudaFree(sim->buf_base[i]);
     cudaFree(sim->rho); cudaFree(sim->u); cudaFree(sim->v); cudaFree(sim->feq);
-    cudaFree(sim->mask); cudaFree(sim->span_solid); cudaFree(sim->halo); cudaFree(sim->mass_scratch);
+    cudaFree(sim->mask); cudaFree(sim->span_solid); cudaFree(sim->halo); cudaFree(sim->mass_scratch); cudaFree(sim->frozen);
     if (sim->own_stream && sim->stream) cudaStreamDestroy(sim->stream);
     cudaGetLastError();
     delete sim;
@@ -727,7 +752,7 @@ int lb_set_mask(lb_sim *sim, const void *host_mask, int elem_bytes)
         const int32_t *m = (const int32_t *)host_mask;
         for (size_t i = 0; i < packed.size(); ++i) packed[i] = (m[i] == 1) ? 1 : 0;
     }
-    if (sim->cfg.bc == LB_BC_VELOCITY_YPERIODIC)
+    if (sim->cfg.bc == LB_BC_VELOCITY_YPERIODIC && is_cython(sim))      // lb_cython.cuh folds the row exchange into the pull
         for (int x = 0; x < nx; ++x)
             if (packed[x] || packed[(size_t)(ny - 1) * nx + x])
                 return fail(sim, LB_ERR_INVALID, "lb_set_mask: with LB_BC_VELOCITY_YPERIODIC the exchanged rows y=0 and y=ny-1 must be free of solid nodes");
@@ -775,6 +800,12 @@ int lb_upload_f(lb_sim *sim, const void *host_f)
     CU(cudaMemcpy2DAsync(sim->buf[sim->cur], dp, host_f, w, w, (size_t)9 * sim->cfg.ny, cudaMemcpyHostToDevice, sim->stream));
     // the reference seeds f_streamed with the same data (opencl_dim.py:324-327)
     CU(cudaMemcpyAsync(sim->buf_base[sim->cur ^ 1], sim->buf_base[sim->cur], sim->buf_bytes, cudaMemcpyDeviceToDevice, sim->stream));
+    if (is_oldcl(sim)) {
+        const int n = sim->cfg.nx > sim->cfg.ny ? sim->cfg.nx : sim->cfg.ny;
+        oc_capture_frozen_kernel<<<(n + 127) / 128, 128, 0, sim->stream>>>(sim->cfg.nx, sim->cfg.ny, sim->pitch, sim->plane,
+                                                                            (const float *)sim->buf[sim->cur], sim->frozen);
+        CU(cudaGetLastError());
+    }
     CU(cudaStreamSynchronize(sim->stream));
     sim->prestream_done = false;
     return LB_OK;
@@ -809,7 +840,7 @@ static int compute_feq(lb_sim *sim)
     int rc = ensure_feq(sim);
     if (rc) return rc;
     const int nx = sim->cfg.nx, ny = sim->cfg.ny;
-    if (sim->cfg.scheme != LB_SCHEME_OPENCL)
+    if (is_cython(sim))
         cy_feq_kernel<<<grid2d(sim), 128, 0, sim->stream>>>(nx, ny, sim->pitch, sim->plane, (const float *)sim->rho,
             (const double *)sim->u, (const double *)sim->v, (float *)sim->feq, cy_consts_of(sim));
     else if (sim->cfg.dtype == LB_F32)
@@ -859,6 +890,38 @@ static int cython_steps(lb_sim *sim, int n_steps)
     return LB_OK;
 }
 
+// scheme "opencl_old": see lb_oldcl.cuh for the fusion order
+static int oldcl_steps(lb_sim *sim, int n_steps)
+{
+    const int nx = sim->cfg.nx, ny = sim->cfg.ny;
+    OcParams p = oc_params_of(sim);
+    const unsigned row_blocks = (nx + 127) / 128;
+    if (!sim->prestream_done) {
+        oc_prestream_kernel<<<grid2d(sim), 128, 0, sim->stream>>>(p, (float *)sim->buf[sim->cur]);
+        oc_rows_kernel<<<row_blocks, 128, 0, sim->stream>>>(nx, ny, sim->pitch, sim->plane, (float *)sim->buf[sim->cur],
+                                                            sim->mask, sim->mask_pitch);
+        CU(cudaGetLastError());
+    }
+    constexpr int WX = 2, WY = 2;
+    const unsigned tiles_x = (sim->pitch + 128 * WX - 1) / (128 * WX), tiles_y = (ny + WY - 1) / WY;
+    const unsigned gy = tiles_y < 65535 ? tiles_y : 65535;
+    const dim3 grid(tiles_x, gy, (tiles_y + gy - 1) / gy);
+    for (int i = 0; i < n_steps; ++i) {
+        const bool last = (i == n_steps - 1);
+        p.src = (const float *)sim->buf[sim->cur];
+        p.dst = (float *)sim->buf[sim->cur ^ 1];
+        p.write_moments = last; p.apply_next_bc = !last;
+        fused_step_oldcl_kernel<WX, WY, 4><<<grid, 32 * WX * WY, 0, sim->stream>>>(p);
+        if (!last)
+            oc_rows_kernel<<<row_blocks, 128, 0, sim->stream>>>(nx, ny, sim->pitch, sim->plane, p.dst, sim->mask, sim->mask_pitch);
+        CU(cudaGetLastError());
+        sim->launches++;
+        sim->cur ^= 1; sim->state_index++;
+    }
+    sim->prestream_done = false;      // the last launch left plain post-collision populations
+    return LB_OK;
+}
+
 static const int GRAPH_LEN = 32;    // steps per captured graph (even: a graph returns to its start buffer)
 
 // (re)build the graph of GRAPH_LEN moment-free steps that starts from buffer `sim->cur`
@@ -896,6 +959,7 @@ int lb_step(lb_sim *sim, int n_steps)
             if (e == LB_EDGE_HALO && !sim->peer[side]) return fail(sim, LB_ERR_STATE, "lb_step: halo edge not connected");
         }
     }
+    if (is_oldcl(sim)) return oldcl_steps(sim, n_steps);
     if (sim->cfg.scheme != LB_SCHEME_OPENCL) return cython_steps(sim, n_steps);
     int remaining = n_steps - 1;            // all but the last step skip the moment stores
     const bool graphs_ok = !uses_halo(sim); // halo launches carry a per-step flag value
@@ -1034,7 +1098,7 @@ int lb_stage_zero_velocity(lb_sim *sim)
     if (!sim) return LB_ERR_INVALID;
     if (!sim->mask) return LB_OK;
     CU(cudaSetDevice(sim->cfg.device));
-    if (sim->cfg.scheme != LB_SCHEME_OPENCL) {
+    if (is_cython(sim)) {
         k_zero_velocity<double><<<grid2d(sim), 128, 0, sim->stream>>>(sim->cfg.nx, sim->cfg.ny, sim->pitch, sim->mask, sim->mask_pitch,
                                                                        (double *)sim->u, (double *)sim->v);
         CU(cudaGetLastError());

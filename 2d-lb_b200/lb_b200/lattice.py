@@ -21,7 +21,8 @@ two_cs4 = 2 * cs ** 4
 _BC = {"pipe": N.BC_PIPE, "periodic": N.BC_PERIODIC, "velocity_yperiodic": N.BC_VELOCITY_YPERIODIC}
 _MATH = {"strict": N.MATH_STRICT, "fast": N.MATH_FAST}
 _EDGE = {"boundary": N.EDGE_BOUNDARY, "wrap": N.EDGE_WRAP, "halo": N.EDGE_HALO}
-_SCHEME = {"opencl": N.SCHEME_OPENCL, "cython": N.SCHEME_CYTHON, "cython_old": N.SCHEME_CYTHON_OLD}
+_SCHEME = {"opencl": N.SCHEME_OPENCL, "cython": N.SCHEME_CYTHON, "cython_old": N.SCHEME_CYTHON_OLD,
+           "opencl_old": N.SCHEME_OPENCL_OLD}
 _FIELD = {"f": N.FIELD_F, "feq": N.FIELD_FEQ, "rho": N.FIELD_RHO, "u": N.FIELD_U, "v": N.FIELD_V}
 
 
@@ -37,7 +38,8 @@ class Lattice:
     classes; `lb_b200.dimensionless` builds on this.
 
     bc     'pipe' (pressure inlet/outlet + walls, D2Q9.cl:173-261), 'periodic', or 'velocity_yperiodic'
-           (imposed inlet/outlet velocity u_west/u_east, rows 0 and ny-1 exchanged; scheme 'cython_old')
+           (imposed inlet/outlet velocity u_west/u_east, rows 0 and ny-1 exchanged; schemes 'cython_old'
+           and 'opencl_old')
     math   'strict' (default: D2Q9.cl's arithmetic operation for operation, bit-identical to the CPU
            oracle, and HBM-bound like 'fast') or 'fast' (FMA + reciprocal constants, ~30% fewer
            instructions, agrees to rounding)
@@ -45,7 +47,8 @@ class Lattice:
     model  'd2q9' (D2Q9.cl) or 'd2q9i' (the incompressible variant D2Q9i.cl; scheme 'opencl', pipe flow)
     scheme 'opencl' (default: the step order of opencl_dim.py), 'cython' or
            'cython_old' (the reference's CPU classes, cython_dim.pyx / OLD/cython.pyx, including
-           their mixed-precision arithmetic; float32 populations, float64 u and v)
+           their mixed-precision arithmetic; float32 populations, float64 u and v), or 'opencl_old'
+           (D2Q9.cl's velocity-inlet kernels in the step order of OLD/opencl.py; float32 throughout)
     """
 
     def __init__(self, nx, ny, omega, inlet_rho=1.0, outlet_rho=1.0, mask=None, f0=None, bc="pipe",
@@ -150,7 +153,7 @@ class Lattice:
     @property
     def uv_dtype(self):
         """dtype of the u / v fields: float64 for the cython schemes (as in the reference)."""
-        return self.dtype if self.scheme == "opencl" else np.dtype(np.float64)
+        return np.dtype(np.float64) if self.scheme in ("cython", "cython_old") else self.dtype
 
     def field_dtype(self, field):
         return self.uv_dtype if field in ("u", "v") else self.dtype

@@ -19,7 +19,7 @@ EDGE_BOUNDARY, EDGE_WRAP, EDGE_HALO = 0, 1, 2
 SYNTH_PIPE_RAMP, SYNTH_SHEAR_LAYERS = 0, 1
 IPC_HANDLE_BYTES = 64
 ABI_VERSION = 3
-SCHEME_OPENCL, SCHEME_CYTHON, SCHEME_CYTHON_OLD = 0, 1, 2
+SCHEME_OPENCL, SCHEME_CYTHON, SCHEME_CYTHON_OLD, SCHEME_OPENCL_OLD = 0, 1, 2, 3
 MODEL_D2Q9, MODEL_D2Q9I = 0, 1
 
 # every symbol include/lb_d2q9.h declares (tests/test_abi.py checks the library exports them all)

@@ -53,7 +53,8 @@ enum lb_bc {
     LB_BC_PERIODIC = 1,
     /* imposed x-velocity u_west / u_east at inlet / outlet (Zou-He), rows y=0 and y=ny-1 exchange
      * their incoming populations -- LB_D2Q9/OLD/cython.pyx:268-360 (Pipe_Flow_PeriodicBC_VelocityInlet,
-     * the CPU twin of D2Q9.cl:263-374).  Available with LB_SCHEME_CYTHON_OLD. */
+     * the CPU twin of D2Q9.cl:263-374) with LB_SCHEME_CYTHON_OLD; the OpenCL kernels themselves
+     * (D2Q9.cl:263-374 as LB_D2Q9/OLD/opencl.py:281-371 drives them) with LB_SCHEME_OPENCL_OLD. */
     LB_BC_VELOCITY_YPERIODIC = 2
 };
 
@@ -74,8 +75,16 @@ enum lb_math { LB_MATH_STRICT = 0, LB_MATH_FAST = 1 };
  *                         reference.  dtype must be LB_F32, bc LB_BC_PIPE, single slab; the u and v
  *                         fields are float64 (as in the reference), rho/f/feq float32.
  *   LB_SCHEME_CYTHON_OLD  the same for LB_D2Q9/OLD/cython.pyx (no wall zeroing of u,v; omega and
- *                         inlet_rho are Python floats there, so those expressions are float32). */
-enum lb_scheme { LB_SCHEME_OPENCL = 0, LB_SCHEME_CYTHON = 1, LB_SCHEME_CYTHON_OLD = 2 };
+ *                         inlet_rho are Python floats there, so those expressions are float32).
+ *   LB_SCHEME_OPENCL_OLD  D2Q9.cl's kernels in the step order of LB_D2Q9/OLD/opencl.py:246-255
+ *                         (BCs -> bounce-back -> stream -> moments -> feq -> collide), for its
+ *                         velocity-inlet / y-periodic classes: bc must be LB_BC_VELOCITY_YPERIODIC,
+ *                         dtype LB_F32, single slab.  Populations without an upstream node keep the
+ *                         values of the last lb_upload_f (the reference's `move` never writes them);
+ *                         u, v, rho are float32; lb_upload_moments supplies the velocity entries the
+ *                         reference's update_hydro never rewrites (D2Q9.cl:357-371).  Bit-identical
+ *                         to the reference's own kernels (tests/golden/oldcl_*.npz). */
+enum lb_scheme { LB_SCHEME_OPENCL = 0, LB_SCHEME_CYTHON = 1, LB_SCHEME_CYTHON_OLD = 2, LB_SCHEME_OPENCL_OLD = 3 };
 
 /* Collision model.  LB_MODEL_D2Q9I is the reference's incompressible variant (LB_D2Q9/D2Q9i.cl behind
  * dimensionless/opencl_dim_D2Q9i.py): u, v are the raw momentum (no division by rho, D2Q9i.cl:92-94),

@@ -321,6 +321,104 @@ void FN(oracle_run)(int nx, int ny, int bc, int n_steps, REAL *f, REAL *f_stream
     }
 }
 
+/* == f-2, OpenCL flavour: the velocity-inlet / y-periodic family of LB_D2Q9/OLD/opencl.py ==========
+ *    Only that module launches D2Q9.cl's *_PeriodicBC_VelocityInlet kernels, in the OLD step order
+ *    (OLD/opencl.py:246-255):  move_bcs -> [bounce-back] -> move -> update_hydro -> [zero u,v in the
+ *    obstacle] -> update_feq -> collide.  The boundary pass therefore acts on POST-COLLISION
+ *    populations, and the slots `move` never writes (no upstream node) keep what f_streamed held when
+ *    it was created -- the initial populations -- for ever. */
+
+/* move_bcs_PeriodicBC_VelocityInlet, D2Q9.cl:263-321.  u_w, u_e arrive as np.float32
+ * (OLD/opencl.py:293-294); `1.`, `2./3.`, `1./2.`, `1./6.` are double literals, `2*` (inlet, :292) is
+ * an int and keeps that sum in REAL while `2.*` (outlet, :299) promotes it. */
+void FN(oracle_move_bcs_vin)(int nx, int ny, REAL *f, double u_w_d, double u_e_d)
+{
+    const REAL u_w = (REAL)u_w_d, u_e = (REAL)u_e_d;
+    const size_t plane = (size_t)nx * (size_t)ny;
+    /* the two row copies read populations no work-item of this kernel writes (4,8,7 of row 0;
+       2,6,5 of row ny-1), so the result does not depend on the execution order */
+    for (int y = 0; y < ny; ++y) {
+        for (int x = 0; x < nx; ++x) {
+            const size_t c = (size_t)y * nx + x;
+#define F(j) f[(size_t)(j) * plane + c]
+            const REAL f0 = F(0), f1 = F(1), f2 = F(2), f3 = F(3), f4 = F(4), f5 = F(5), f6 = F(6), f7 = F(7), f8 = F(8);
+            if (x == 0 && y >= 1 && y < ny - 1) {
+                const REAL rho_w = (REAL)((1. / (1. - (double)u_w)) * (double)(((f0 + f2) + f4) + (REAL)2 * ((f3 + f6) + f7)));
+                F(1) = (REAL)((double)f3 + ((2. / 3.) * (double)rho_w) * (double)u_w);
+                F(5) = (REAL)(((double)f7 - (1. / 2.) * (double)(f2 - f4)) + ((1. / 6.) * (double)rho_w) * (double)u_w);
+                F(8) = (REAL)(((double)f6 + (1. / 2.) * (double)(f2 - f4)) + ((1. / 6.) * (double)rho_w) * (double)u_w);
+            }
+            if (x == nx - 1 && y >= 1 && y < ny - 1) {
+                const REAL rho_e = (REAL)((1. / (1. + (double)u_e)) * ((double)((f0 + f2) + f4) + 2. * (double)((f1 + f5) + f8)));
+                F(3) = (REAL)((double)f1 - ((2. / 3.) * (double)rho_e) * (double)u_e);
+                F(6) = (REAL)(((double)f5 + (1. / 2.) * (double)(f2 - f4)) - ((1. / 6.) * (double)rho_e) * (double)u_e);
+                F(7) = (REAL)(((double)f8 - (1. / 2.) * (double)(f2 - f4)) - ((1. / 6.) * (double)rho_e) * (double)u_e);
+            }
+            if (y == ny - 1) {                                   /* "NORTH": takes 4, 8, 7 of row 0 */
+                F(4) = f[4 * plane + x];
+                F(8) = f[8 * plane + x];
+                F(7) = f[7 * plane + x];
+            }
+            if (y == 0) {                                        /* "SOUTH": takes 2, 6, 5 of row ny-1 */
+                F(2) = f[2 * plane + (size_t)(ny - 1) * nx + x];
+                F(6) = f[6 * plane + (size_t)(ny - 1) * nx + x];
+                F(5) = f[5 * plane + (size_t)(ny - 1) * nx + x];
+            }
+#undef F
+        }
+    }
+}
+
+/* update_hydro_PeriodicBC_VelocityInlet, D2Q9.cl:323-374: u, v are written for interior columns only;
+ * on x = 0 and x = nx-1 the rows 1..ny-2 get the boundary density and u_w / u_e, and everything else
+ * there (v; u in the four corners) keeps whatever the arrays held. */
+void FN(oracle_update_hydro_vin)(int nx, int ny, const REAL *f, REAL *rho, REAL *u, REAL *v,
+                                 double u_w_d, double u_e_d)
+{
+    const REAL u_w = (REAL)u_w_d, u_e = (REAL)u_e_d;
+    const size_t plane = (size_t)nx * (size_t)ny;
+    for (int y = 0; y < ny; ++y) {
+        for (int x = 0; x < nx; ++x) {
+            const size_t c = (size_t)y * nx + x;
+            REAL g[9];
+            for (int j = 0; j < 9; ++j) g[j] = f[(size_t)j * plane + c];
+            REAL r = g[0];
+            for (int j = 1; j < 9; ++j) r = r + g[j];
+            rho[c] = r;
+            const REAL inv = (REAL)(1.0 / (double)r);
+            if (x != 0 && x != nx - 1) {
+                u[c] = (((((g[1] - g[3]) + g[5]) - g[6]) - g[7]) + g[8]) * inv;
+                v[c] = (((((g[5] + g[2]) + g[6]) - g[7]) - g[4]) - g[8]) * inv;
+            }
+            if (x == 0 && y != 0 && y < ny - 1) {
+                rho[c] = (REAL)((1. / (1. - (double)u_w)) * ((double)((g[0] + g[2]) + g[4]) + 2. * (double)((g[3] + g[6]) + g[7])));
+                u[c] = u_w;
+            }
+            if (x == nx - 1 && y != 0 && y < ny - 1) {
+                rho[c] = (REAL)((1. / (1. + (double)u_e)) * ((double)((g[0] + g[2]) + g[4]) + 2. * (double)((g[1] + g[5]) + g[8])));
+                u[c] = u_e;
+            }
+        }
+    }
+}
+
+/* the step loop of OLD/opencl.py's velocity-inlet classes (:246-255, :290-327, :346-371);
+ * with a mask, u and v are zeroed in the obstacle after every update_hydro (:359-363). */
+void FN(oracle_run_oldcl_vin)(int nx, int ny, int n_steps, REAL *f, REAL *f_streamed,
+                              const int32_t *mask, REAL *rho, REAL *u, REAL *v, REAL *feq,
+                              double omega, double u_w, double u_e, double cs2, double cs22, double two_cs4)
+{
+    for (int it = 0; it < n_steps; ++it) {
+        FN(oracle_move_bcs_vin)(nx, ny, f, u_w, u_e);
+        if (mask) FN(oracle_bounceback)(nx, ny, mask, f);
+        FN(oracle_move)(nx, ny, f, f_streamed);
+        FN(oracle_update_hydro_vin)(nx, ny, f, rho, u, v, u_w, u_e);
+        if (mask) FN(oracle_zero_velocity)(nx, ny, mask, u, v);
+        FN(oracle_update_feq)(nx, ny, rho, u, v, feq, cs2, cs22, two_cs4);
+        FN(oracle_collide)(nx, ny, f, feq, omega);
+    }
+}
+
 #undef FN
 #undef CAT
 #undef CAT2

@@ -26,7 +26,7 @@ CX = np.array([0, 1, 0, -1, 0, 1, -1, -1, 1])
 CY = np.array([0, 0, 1, 0, -1, 1, 1, -1, -1])
 W = np.array([4. / 9.] + [1. / 9.] * 4 + [1. / 36.] * 4)
 
-BC_PIPE, BC_PERIODIC = 0, 1
+BC_PIPE, BC_PERIODIC, BC_VELOCITY_YPERIODIC = 0, 1, 2
 
 
 def build(force=False):
@@ -80,10 +80,16 @@ class OpenCLSchemeOracle:
     """State + stage methods of opencl_dim.Pipe_Flow[_Cylinder] on the CPU.
 
     f: (9, ny, nx) array (copied).  mask: (ny, nx) of {0,1} or None.
+
+    bc=BC_VELOCITY_YPERIODIC selects LB_D2Q9/OLD/opencl.py's Pipe_Flow[_Obstacles]_PeriodicBC_VelocityInlet:
+    D2Q9.cl's *_PeriodicBC_VelocityInlet kernels in the OLD step order (boundary pass BEFORE streaming);
+    u0, v0 are the initial velocity arrays (parts of them are never rewritten, D2Q9.cl:357-371) and with
+    a mask u, v are zeroed in the obstacle after every moment update (OLD/opencl.py:359-363).
     """
 
     def __init__(self, f0, omega, inlet_rho=1.0, outlet_rho=1.0, mask=None, bc=BC_PIPE,
-                 dtype=np.float32, zero_obstacle_velocity=False, incompressible=False):
+                 dtype=np.float32, zero_obstacle_velocity=False, incompressible=False,
+                 u_w=0.0, u_e=0.0, u0=None, v0=None):
         self.incompressible = bool(incompressible)      # D2Q9i.cl instead of D2Q9.cl
         self.dtype = np.dtype(dtype)
         self.sfx = "_f32" if self.dtype == np.float32 else "_f64"
@@ -100,6 +106,14 @@ class OpenCLSchemeOracle:
         self.u = np.zeros(shape2, self.dtype)
         self.v = np.zeros(shape2, self.dtype)
         self.feq = np.zeros_like(self.f)
+        self.u_w, self.u_e = float(u_w), float(u_e)
+        if bc == BC_VELOCITY_YPERIODIC:
+            assert not incompressible
+            self.zero_obstacle_velocity = self.mask is not None
+            if u0 is not None:
+                self.u[...] = u0
+            if v0 is not None:
+                self.v[...] = v0
 
     def _fn(self, name):
         return getattr(lib(), name + self.sfx)
@@ -112,6 +126,8 @@ class OpenCLSchemeOracle:
         self._fn(name)(*self._dims(), _p(self.f), _p(self.f_streamed))
 
     def move_bcs(self):
+        if self.bc == BC_VELOCITY_YPERIODIC:
+            self._fn("oracle_move_bcs_vin")(*self._dims(), _p(self.f), ct.c_double(self.u_w), ct.c_double(self.u_e))
         if self.bc == BC_PIPE:
             self._fn("oracle_move_bcs_i" if self.incompressible else "oracle_move_bcs")(*self._dims(), _p(self.f), ct.c_double(self.inlet_rho),
                                         ct.c_double(self.outlet_rho))
@@ -119,8 +135,12 @@ class OpenCLSchemeOracle:
             self._fn("oracle_bounceback")(*self._dims(), _p(self.mask), _p(self.f))
 
     def update_hydro(self):
-        self._fn("oracle_update_hydro_i" if self.incompressible else "oracle_update_hydro")(
-            *self._dims(), _p(self.f), _p(self.rho), _p(self.u), _p(self.v))
+        if self.bc == BC_VELOCITY_YPERIODIC:
+            self._fn("oracle_update_hydro_vin")(*self._dims(), _p(self.f), _p(self.rho), _p(self.u), _p(self.v),
+                                                ct.c_double(self.u_w), ct.c_double(self.u_e))
+        else:
+            self._fn("oracle_update_hydro_i" if self.incompressible else "oracle_update_hydro")(
+                *self._dims(), _p(self.f), _p(self.rho), _p(self.u), _p(self.v))
         if self.mask is not None and self.zero_obstacle_velocity:
             self._fn("oracle_zero_velocity")(*self._dims(), _p(self.mask), _p(self.u), _p(self.v))
 
@@ -135,6 +155,12 @@ class OpenCLSchemeOracle:
         self._fn("oracle_collide")(*self._dims(), _p(self.f), _p(self.feq), ct.c_double(self.omega))
 
     def run(self, n):
+        if self.bc == BC_VELOCITY_YPERIODIC:
+            self._fn("oracle_run_oldcl_vin")(*self._dims(), ct.c_int(int(n)), _p(self.f), _p(self.f_streamed),
+                                             _p(self.mask), _p(self.rho), _p(self.u), _p(self.v), _p(self.feq),
+                                             ct.c_double(self.omega), ct.c_double(self.u_w), ct.c_double(self.u_e),
+                                             ct.c_double(cs2), ct.c_double(cs22), ct.c_double(two_cs4))
+            return
         self._fn("oracle_run")(*self._dims(), ct.c_int(self.bc), ct.c_int(int(n)), _p(self.f),
                                _p(self.f_streamed), _p(self.mask), _p(self.rho), _p(self.u), _p(self.v),
                                _p(self.feq), ct.c_double(self.omega), ct.c_double(self.inlet_rho),

@@ -105,6 +105,41 @@ def test_old_opencl_pipe_is_the_same_kernels_in_the_old_order(orc):
             assert _same(getattr(o, k), orc.from_opencl_host(g[f"{k}_{s}"])), f"{k} after {s} steps"
 
 
+@pytest.mark.parametrize("name", ["oldcl_velocity_inlet_61x31.npz", "oldcl_velocity_inlet_obstacles_61x31.npz"])
+def test_old_opencl_velocity_inlet_matches_reference_golden_bitexact(orc, name):
+    """OLD/opencl.py's Pipe_Flow[_Obstacles]_PeriodicBC_VelocityInlet -- the only callers of D2Q9.cl:263-374 --
+    against the oracle's restatement (bc=BC_VELOCITY_YPERIODIC).  One obstacle of the second vector
+    touches the periodic row y = 0."""
+    g = _load(name)
+    mask = orc.from_opencl_host(g["mask"]).astype(np.int32) if "mask" in g.files else None
+    o = orc.OpenCLSchemeOracle(orc.from_opencl_host(g["f_0"]), np.float32(g["omega"]), mask=mask,
+                               bc=orc.BC_VELOCITY_YPERIODIC, u_w=np.float32(g["u_w"]), u_e=np.float32(g["u_e"]),
+                               u0=orc.from_opencl_host(g["u_0"]), v0=orc.from_opencl_host(g["v_0"]))
+    if mask is not None:
+        assert mask[0].any()
+    done = 0
+    for s in g["steps"]:
+        o.run(int(s) - done)
+        done = int(s)
+        for k in ("f", "rho", "u", "v"):
+            assert _same(getattr(o, k), orc.from_opencl_host(g[f"{k}_{s}"])), f"{k} after {s} steps"
+    assert _same(o.feq, orc.from_opencl_host(g[f"feq_{done}"]))
+    assert np.isfinite(o.f).all() and float(np.abs(o.u).max()) < 0.2
+
+
+def test_old_opencl_velocity_inlet_stages_equal_run(orc):
+    from util import pipe_case
+    f0, mask = pipe_case(orc, 45, 22, mask="touching", seed=5)
+    kw = dict(mask=mask.astype(np.int32), bc=orc.BC_VELOCITY_YPERIODIC, u_w=np.float32(0.04), u_e=np.float32(0.04),
+              u0=np.full((22, 45), np.float32(0.04)))
+    a = orc.OpenCLSchemeOracle(f0, np.float32(1.1), **kw)
+    b = orc.OpenCLSchemeOracle(f0, np.float32(1.1), **kw)
+    a.run(7)
+    for _ in range(7):
+        b.move_bcs(); b.move(); b.update_hydro(); b.update_feq(); b.collide_particles()
+    assert _same(a.f, b.f) and _same(a.u, b.u) and _same(a.rho, b.rho)
+
+
 # ------------------------------------------------------------------------------------------------
 # 2. the compiled kernels of D2Q9.cl, one by one, against the oracle's stage functions
 @pytest.fixture(scope="module")
@@ -171,6 +206,18 @@ def test_compiled_cl_kernels_equal_oracle_stages(orc, cl, d2q9, nx, ny, lsz):
         d2q9.collide_particles(None, g3, l3, f, feq, omega, i32(nx), i32(ny)).wait()
         o.collide_particles()
         assert _same(_read(cl, f, f0.shape), o.f), f"collide_particles, step {step}"
+    # the velocity-inlet pair (D2Q9.cl:263-374), on the state reached above
+    uw, ue = np.float32(0.05), np.float32(0.03)
+    ov = orc.OpenCLSchemeOracle(o.f, omega, bc=orc.BC_VELOCITY_YPERIODIC, u_w=uw, u_e=ue, u0=o.u, v0=o.v)
+    if ny >= 4:
+        d2q9.move_bcs_PeriodicBC_VelocityInlet(None, g2, lsz, f, u, uw, ue, i32(nx), i32(ny)).wait()
+        ov.move_bcs()
+        assert _same(_read(cl, f, f0.shape), ov.f), "move_bcs_PeriodicBC_VelocityInlet"
+        d2q9.update_hydro_PeriodicBC_VelocityInlet(None, g2, lsz, f, u, v, rho, uw, ue, i32(nx), i32(ny)).wait()
+        ov.update_hydro()
+        for b, want in ((rho, ov.rho), (u, ov.u), (v, ov.v)):
+            assert _same(_read(cl, b, (ny, nx)), want), "update_hydro_PeriodicBC_VelocityInlet"
+        o.u[...] = ov.u
     # set_zero_velocity_in_obstacle (D2Q9.cl:377-396)
     d2q9.set_zero_velocity_in_obstacle(None, g2, lsz, m, u, v, i32(nx), i32(ny)).wait()
     zu = o.u.copy()

@@ -719,3 +719,80 @@ def test_same_user_code_same_seed_same_bits_as_the_reference_opencl_path(gpu, na
         for k in ("f", "rho", "u", "v"):
             assert _same_bits(got[k], g[f"{k}_{s}"]), f"{k} after {s} steps"
     assert _same_bits(got["feq"], g[f"feq_{done}"])
+
+
+# ------------------------------------------------------------------------------------------------
+# scheme 'opencl_old': OLD/opencl.py's velocity-inlet classes on D2Q9.cl:263-374 (OpenCL flavour)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["oldcl_velocity_inlet_61x31.npz", "oldcl_velocity_inlet_obstacles_61x31.npz"])
+def test_opencl_old_scheme_matches_reference_golden_bitexact(gpu, orc, name):
+    """The fused kernel of lb_oldcl.cuh against vectors produced by the reference's own kernels under
+    its own host class (one obstacle touches the periodic row y = 0)."""
+    from lb_b200 import Lattice
+    g = _gold(name)
+    nx, ny = int(g["nx"]), int(g["ny"])
+    mask = orc.from_opencl_host(g["mask"]) if "mask" in g.files else None
+    with Lattice(nx, ny, float(g["omega"]), mask=mask, dtype=np.float32, bc="velocity_yperiodic", scheme="opencl_old",
+                 u_west=float(np.float32(g["u_w"])), u_east=float(np.float32(g["u_e"]))) as sim:
+        sim.upload_moments(orc.from_opencl_host(g["rho_0"]), orc.from_opencl_host(g["u_0"]), orc.from_opencl_host(g["v_0"]))
+        sim.upload_f(orc.from_opencl_host(g["f_0"]))
+        done = 0
+        for s in g["steps"]:
+            sim.run(int(s) - done)          # several run() calls: exercises the pre-stream prologue too
+            done = int(s)
+            for k in ("f", "rho", "u", "v"):
+                got = sim.download(k)
+                assert got.dtype == np.float32
+                assert _same_bits(got, orc.from_opencl_host(g[f"{k}_{s}"])), f"{k} after {s} steps"
+        assert _same_bits(sim.download("feq"), orc.from_opencl_host(g[f"feq_{done}"]))
+
+
+@pytest.mark.parametrize("shape", [(131, 37), (128, 8), (5, 4), (257, 19)])
+def test_opencl_old_scheme_matches_oracle_awkward_shapes(gpu, orc, shape):
+    """Solid nodes on the inlet/outlet columns, on both periodic rows and in the corners; widths that
+    are not a multiple of the vector width; run() split in pieces."""
+    from lb_b200 import Lattice
+    nx, ny = shape
+    f0, mask = pipe_case(orc, nx, ny, mask="touching", seed=nx + ny)
+    uw, ue = np.float32(0.06), np.float32(0.045)
+    rng = np.random.RandomState(1)
+    u0 = (0.05 + 0.01 * rng.rand(ny, nx)).astype(np.float32)
+    v0 = (0.01 * rng.randn(ny, nx)).astype(np.float32)
+    ref = orc.OpenCLSchemeOracle(f0, np.float32(1.45), mask=mask.astype(np.int32), bc=orc.BC_VELOCITY_YPERIODIC,
+                                 u_w=uw, u_e=ue, u0=u0, v0=v0)
+    with Lattice(nx, ny, 1.45, mask=mask, dtype=np.float32, bc="velocity_yperiodic", scheme="opencl_old",
+                 u_west=float(uw), u_east=float(ue)) as sim:
+        sim.upload_moments(np.ones((ny, nx), np.float32), u0, v0)
+        sim.upload_f(f0)
+        for n in (1, 2, 30):
+            ref.run(n)
+            sim.run(n)
+            for k in ("f", "rho", "u", "v"):
+                assert _same_bits(sim.download(k), getattr(ref, k)), (k, n)
+
+
+def test_old_opencl_velocity_inlet_classes_same_code_same_bits(gpu):
+    """`from LB_D2Q9.OLD import opencl`: the constructor calls that produced the golden vectors with the
+    reference's classes give the same fields with this repo's classes."""
+    import ast
+    from LB_D2Q9.OLD import opencl as old
+    for name, cls in (("oldcl_velocity_inlet_61x31.npz", old.Pipe_Flow_PeriodicBC_VelocityInlet),
+                      ("oldcl_velocity_inlet_obstacles_61x31.npz", old.Pipe_Flow_Obstacles_PeriodicBC_VelocityInlet)):
+        g = _gold(name)
+        kw = ast.literal_eval(str(g["ctor_kwargs"]))
+        if "mask" in g.files:
+            kw["obstacle_mask"] = g["mask"].astype(bool)
+        np.random.seed(int(g["seed"]))
+        sim = cls(**kw)
+        got = sim.get_fields_on_cpu()
+        for k in ("f", "feq", "rho", "u", "v"):
+            assert _same_bits(got[k], g[f"{k}_0"]), f"initial {k} ({name})"
+        done = 0
+        for s in g["steps"]:
+            sim.run(int(s) - done)
+            done = int(s)
+            got = sim.get_fields_on_cpu()
+            for k in ("f", "rho", "u", "v"):
+                assert got[k].flags.f_contiguous
+                assert _same_bits(got[k], g[f"{k}_{s}"]), f"{k} after {s} steps ({name})"
+        assert _same_bits(got["feq"], g[f"feq_{done}"])
