@@ -8,12 +8,12 @@
  * Two restatements live here:
  *   1. scheme "opencl"  (d2q9_oracle_impl.h, instantiated for float and double):
  *      the path being replaced -- LB_D2Q9/D2Q9.cl driven by
- *      LB_D2Q9/dimensionless/opencl_dim.py:372-387.  That path needs pyopencl
- *      and an OpenCL device, neither of which exists in this image, so it is
- *      pinned indirectly (tests/test_oracle.py): the Poiseuille known answer and
- *      the constructor printouts stored in docs/opencl_dimensionless_verification.ipynb,
- *      and a one-step interior cross-check against the compiled reference
- *      Cython module (oracle/_ref), whose interior update is the same algorithm.
+ *      LB_D2Q9/dimensionless/opencl_dim.py:372-387.  pyopencl and an OpenCL device
+ *      do not exist in this image, so the reference's kernel files are compiled as C
+ *      (oracle/clshim) and run on the CPU under the reference's own host classes; this
+ *      restatement is pinned to them BIT FOR BIT (tests/golden/opencl_*.npz, oldcl_*.npz,
+ *      tests/test_opencl_reference.py), besides the Poiseuille known answer and the
+ *      constructor printouts stored in docs/opencl_dimensionless_verification.ipynb.
  *   2. scheme "cython"  (below): LB_D2Q9/dimensionless/cython_dim.pyx:204-359
  *      and :459-513, i.e. the reference's own CPU path, including its mixed
  *      float32/float64 arithmetic as NumPy >= 2 evaluates it.  This one IS

@@ -17,6 +17,13 @@
  * (`1./rho`, `2./3.`, `.5*`), so that a GPU kernel which mirrors the same
  * order must agree BIT FOR BIT.
  *
+ * PINNED against the reference itself: the kernel files D2Q9.cl / D2Q9i.cl are
+ * compiled as C where they lie (oracle/clshim/opencl_c.h, oracle/build_ref.py)
+ * and run on the CPU under the reference's unmodified host classes
+ * (oracle/shims/pyopencl, oracle/refload.py); every function below reproduces
+ * them bit for bit -- golden vectors tests/golden/opencl_*.npz, oldcl_*.npz and
+ * the kernel-by-kernel checks of tests/test_opencl_reference.py.
+ *
  * Layout: f[9][ny][nx], x fastest (the reference's device layout,
  * D2Q9.cl:24-25 / opencl_dim.py:165), no row padding.
  */
@@ -217,8 +224,9 @@ void FN(oracle_zero_velocity)(int nx, int ny, const int32_t *mask, REAL *u, REAL
 /* ======================================================================== */
 /* Incompressible variant, LB_D2Q9/D2Q9i.cl.  Same kernels   */
 /* except: equilibrium (:58-59), moments (:90-94), pressure inlet/outlet      */
-/* (:195-205).  NOT pinned by any reference run or stored vector (needs       */
-/* pyopencl): parity for this variant is "unpinned restatement".              */
+/* (:195-205).  PINNED: bit-identical to the reference's own D2Q9i.cl compiled */
+/* through oracle/clshim and driven by opencl_dim_D2Q9i.py                    */
+/* (tests/golden/opencl_d2q9i_*.npz, tests/test_opencl_reference.py).         */
 /* ======================================================================== */
 void FN(oracle_update_feq_i)(int nx, int ny, const REAL *rho, const REAL *u, const REAL *v, REAL *feq)
 {

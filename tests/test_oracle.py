@@ -3,10 +3,11 @@
 1. scheme 'cython' restatement  == committed golden vectors, BIT FOR BIT.  The vectors were
    produced by the unmodified reference (tests/golden/make_golden.py -> compiled
    LB_D2Q9/dimensionless/cython_dim.pyx and LB_D2Q9/OLD/cython.pyx).
-2. scheme 'opencl' restatement (the path being replaced; needs pyopencl, cannot run here) is
-   pinned through (a) the interior update it shares with the Cython path, on the golden vectors,
-   (b) the reference's Poiseuille known answer and stored constructor printouts
-   (docs/opencl_dimensionless_verification.ipynb), (c) internal consistency properties.
+2. scheme 'opencl' restatement (the path being replaced) is pinned bit for bit against the
+   reference's own kernels in tests/test_opencl_reference.py; here: (a) the interior update it
+   shares with the Cython path, on the golden vectors, (b) the reference's Poiseuille known answer
+   and stored constructor printouts (docs/opencl_dimensionless_verification.ipynb), (c) internal
+   consistency properties.
 """
 import os
 
@@ -232,7 +233,7 @@ def test_d2q9i_equilibrium_as_shipped_sums_to_rho_squared(orc):
     """Documents the reference's incompressible variant as it is (D2Q9i.cl:58-59):
     feq_j = w_j * rho * (rho + 3 c.u + 4.5 (c.u)^2 - 1.5 u^2), whose zeroth moment is rho^2, not
     rho -- so rho = 1 is an unstable fixed point of its collision and long runs diverge.  The
-    restatement is literal (parity "unpinned": no reference run or stored vector exists for it)."""
+    restatement is literal and pinned to the compiled D2Q9i.cl (tests/test_opencl_reference.py)."""
     ny, nx = 8, 12
     rho = np.full((ny, nx), 1.05)
     u = np.full((ny, nx), 0.02)

@@ -31,7 +31,8 @@ import sys, time
 sys.path.insert(0, "2d-lb_b200")
 import numpy as np, torch
 from lb_b200 import Lattice
-for scheme, bc in (("cython", "pipe"), ("cython_old", "pipe"), ("cython_old", "velocity_yperiodic")):
+for scheme, bc in (("cython", "pipe"), ("cython_old", "pipe"), ("cython_old", "velocity_yperiodic"),
+                   ("opencl_old", "velocity_yperiodic")):
     s = torch.cuda.Stream()
     sim = Lattice(8192, 8192, 1.2, 1.01, 1.0, scheme=scheme, bc=bc, u_west=0.05, u_east=0.05, stream=s.cuda_stream)
     w = np.array([4/9] + [1/9]*4 + [1/36]*4, dtype=np.float32)
