@@ -311,17 +311,17 @@ __global__ void k_selftest_rcp(uint32_t first, uint32_t last, unsigned long long
     if (local) atomicAdd(bad, local);
 }
 
-// one flag byte per 32 cells of a row: does the group contain a solid node
+// one flag byte per 32 cells of a row: 0 = no solid node in the group, 1 = some, 2 = all 32 solid
 __global__ void k_span_solid(int nx, int ny, const uint8_t *mask, int mask_pitch, uint8_t *span_solid, int nspans)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (s >= nspans || y >= ny) return;
-    uint8_t any = 0;
+    int n = 0;
     for (int e = 0; e < 32; ++e) {
         const int x = s * 32 + e;
-        if (x < nx && mask[(long long)y * mask_pitch + x] == 1) any = 1;
+        if (x < nx && mask[(long long)y * mask_pitch + x] == 1) ++n;
     }
-    span_solid[(long long)y * nspans + s] = any;
+    span_solid[(long long)y * nspans + s] = n == 32 ? 2 : (n ? 1 : 0);
 }
 
 __global__ void k_mask_disk(int nx, int ny, int x_off, double cx, double cy, double r2, uint8_t *mask, int mask_pitch)

@@ -34,7 +34,7 @@ struct StepParams {
     int write_moments;        // store rho,u,v (last step of a run only)
     int zero_obstacle_velocity;
     const uint8_t *mask;      // [ny][mask_pitch], 1 = solid; nullptr = no obstacles
-    const uint8_t *span_solid;// [ny][nspans]: does this group of 32 cells of this row contain a solid node
+    const uint8_t *span_solid;// [ny][nspans]: per group of 32 cells of a row: 0 no solid node, 1 some, 2 all
     int mask_pitch, nspans;
     void *rho, *u, *v;        // [ny][pitch]
     Consts<float> cf;         // per-launch constants, precomputed on the host in both types
@@ -223,18 +223,44 @@ __device__ __forceinline__ void finish_row(const StepParams &p, const Consts<T> 
         }
     }
 
-    // --- obstacles: one flag byte per (row, 32 cells) says whether to look at the mask at all.
-    //     The vote makes the branch warp-uniform, so warps without solids issue nothing here.
+    // --- obstacles: one flag byte per (row, 32 cells): 0 = no solid node, 1 = some, 2 = all 32 solid.
+    //     Every lane of a warp reads the same SPAN/32 flags, so the branches below are warp-uniform:
+    //     warps without solids issue nothing here, and warps deep inside an obstacle (all flags 2) swap
+    //     whole register packs -- a compile-time renaming, no mask bytes loaded, no per-node selects.
     uint32_t solid_bits = 0;
+    bool all_solid = false;
     if (p.mask != nullptr) {
         const uint8_t *sf = p.span_solid + (long long)y * p.nspans + (span0 >> 5);
-        unsigned int any = 0;
+        uint32_t flags = 0, all = 0;
+        if (SPAN == 128) { flags = *reinterpret_cast<const uint32_t *>(sf); all = 0x02020202u; }
+        else if (SPAN == 64) { flags = *reinterpret_cast<const uint16_t *>(sf); all = 0x0202u; }
+        else {
 #pragma unroll
-        for (int k = 0; k < SPAN / 32; ++k) any |= sf[k];
-        if (__any_sync(0xffffffffu, any != 0)) {
+            for (int k = 0; k < SPAN / 32; ++k) { flags |= (uint32_t)sf[k] << (8 * (k & 3)); all |= 2u << (8 * (k & 3)); }
+            if (SPAN / 32 > 4) all = 0xffffffffu;        // wider spans: never take the all-solid shortcut
+        }
+        if (flags == all) {                               // D2Q9.cl:410-431 on every node of the warp
+            all_solid = true;
+            solid_bits = (1u << V) - 1u;
+            Pack<T, V> t;
+            t = q[1]; q[1] = q[3]; q[3] = t;
+            t = q[2]; q[2] = q[4]; q[4] = t;
+            t = q[5]; q[5] = q[7]; q[7] = t;
+            t = q[6]; q[6] = q[8]; q[8] = t;
+        } else if (flags != 0) {
+            const uint8_t *mrow = p.mask + (long long)y * p.mask_pitch + x0;   // bytes past nx are zero
+            if (V == 4) {
+                const uint32_t m = *reinterpret_cast<const uint32_t *>(mrow);
 #pragma unroll
-            for (int e = 0; e < V; ++e)
-                if (x0 + e < nx && p.mask[(long long)y * p.mask_pitch + x0 + e] == 1) solid_bits |= (1u << e);
+                for (int e = 0; e < V; ++e) if (((m >> (8 * e)) & 0xffu) == 1u) solid_bits |= (1u << e);
+            } else if (V == 2) {
+                const uint32_t m = *reinterpret_cast<const uint16_t *>(mrow);
+#pragma unroll
+                for (int e = 0; e < V; ++e) if (((m >> (8 * e)) & 0xffu) == 1u) solid_bits |= (1u << e);
+            } else {
+#pragma unroll
+                for (int e = 0; e < V; ++e) if (mrow[e] == 1) solid_bits |= (1u << e);
+            }
             if (__any_sync(0xffffffffu, solid_bits != 0)) {
 #pragma unroll
                 for (int e = 0; e < V; ++e) {
@@ -249,11 +275,21 @@ __device__ __forceinline__ void finish_row(const StepParams &p, const Consts<T> 
             }
         }
     }
-    // --- per node: moments + equilibrium + BGK relaxation, in registers.  Warps that hold a solid node
-    //     whose velocity must be zeroed take a copy of the loop with the per-node flag; all others run
-    //     the flag-free copy (warp-uniform choice).
+    // --- per node: moments + equilibrium + BGK relaxation, in registers.  Three warp-uniform copies of
+    //     the loop: no velocity to zero (the common one, flag-free); every node solid with zeroed
+    //     velocity (the equilibrium folds to w*rho at compile time); mixed warps with a per-node flag.
     Pack<T, V> mrho, mu, mv;
-    if (p.zero_obstacle_velocity && __any_sync(0xffffffffu, solid_bits != 0)) {
+    if (p.zero_obstacle_velocity && all_solid) {
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+            T g[9];
+#pragma unroll
+            for (int j = 0; j < 9; ++j) g[j] = q[j].v[e];
+            collide_node<T, MATH, MODEL>(c, g, mrho.v[e], mu.v[e], mv.v[e], true);
+#pragma unroll
+            for (int j = 0; j < 9; ++j) q[j].v[e] = g[j];
+        }
+    } else if (p.zero_obstacle_velocity && __any_sync(0xffffffffu, solid_bits != 0)) {
 #pragma unroll
         for (int e = 0; e < V; ++e) {
             T g[9];

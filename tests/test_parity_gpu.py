@@ -52,6 +52,35 @@ def test_strict_obstacles_bitexact(gpu, orc, dtype, mask, zero_vel):
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("zero_vel", [False, True])
+@pytest.mark.parametrize("math", ["strict", "fast"])
+def test_bulky_obstacle_takes_the_all_solid_shortcut(gpu, orc, dtype, zero_vel, math):
+    """Obstacles wider than a warp's span: the kernel swaps whole register packs there without reading
+    the mask (span flag 2) -- same bits as the per-node path, also across slab cuts through the body."""
+    from lb_b200 import Lattice
+    from lb_b200.lattice import LocalSlabs
+    nx, ny = 700, 41
+    f0, m = pipe_case(orc, nx, ny, dtype, mask="bulky", seed=11)
+    assert m[ny // 3, 128:512].all()
+    ref, got = _run_both(orc, Lattice, f0, m, 30, dtype, math, zero_vel=zero_vel, omega=1.2)
+    for k in ("f", "rho", "u", "v"):
+        if math == "strict":
+            assert np.array_equal(got[k], getattr(ref, k)), k
+        else:
+            assert np.abs(got[k] - getattr(ref, k)).max() <= (2e-5 if dtype == np.float32 else 1e-12), k
+    slabs = LocalSlabs(nx, ny, 3, omega=1.2, inlet_rho=1.01, outlet_rho=1.0, bc="pipe", dtype=dtype, math=math,
+                       zero_obstacle_velocity=zero_vel)
+    try:
+        slabs.set_mask(m)
+        slabs.upload_f(f0)
+        slabs.run(30)
+        for k in ("f", "rho", "u", "v"):
+            assert np.array_equal(slabs.download(k), got[k]), k
+    finally:
+        slabs.close()
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
 @pytest.mark.parametrize("shape", [(96, 40), (130, 67), (7, 5), (128, 128)])
 def test_strict_periodic_bitexact_and_mass(gpu, orc, shape, dtype):
     from lb_b200 import Lattice

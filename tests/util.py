@@ -21,6 +21,11 @@ def pipe_case(orc, nx, ny, dtype=np.float32, inlet_rho=1.01, outlet_rho=1.0, see
         m = (rng.rand(ny, nx) < 0.05).astype(np.uint8)
         m[0, :] = m[-1, :] = 0
         m[:, 0] = m[:, -1] = 0
+    elif mask == "bulky":             # a body wider than a warp's span: whole groups of 32 / 64 / 128 cells are solid
+        m = np.zeros((ny, nx), np.uint8)
+        m[ny // 5: ny - ny // 5, nx // 8: nx - nx // 6] = 1
+        m[ny // 2, nx // 3: nx // 3 + 40] = 0                      # a slit: mixed groups inside the body
+        m[1:3, :70] = 1                                            # and one hugging the inlet corner
     elif mask == "touching":          # solids on the walls, inlet and outlet columns and corners
         m = (rng.rand(ny, nx) < 0.05).astype(np.uint8)
         m[0, :3] = 1
