@@ -116,7 +116,7 @@ def run_published_config(args):
         "cpu_baseline": None,
         "checks": {"rho_finite": bool(np.isfinite(fields["rho"]).all())},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -281,13 +281,37 @@ def run_reference_arm(args, wl, rank):
         "e2e": {"value": mlups, "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------
 # the CUDA arm
 # ---------------------------------------------------------------------------------------------
+_RESULT_FD = None
+
+
+def _quiet_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version
+    banner on fd 1 when NCCL_DEBUG is set in the environment), so everything that is not the result goes
+    to stderr: fd 1 is pointed at fd 2 and the original stdout is kept for emit()."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    payload = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _RESULT_FD is None:
+        os.write(1, payload)
+    else:
+        os.write(_RESULT_FD, payload)
+
+
 def main():
+    _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
@@ -471,7 +495,7 @@ def main():
             "cpu_baseline": cpu,
             "checks": {"total_mass": mass, "mass_finite": bool(np.isfinite(mass))},
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     slab.close()
     if world > 1:
         dist.barrier()
