@@ -70,6 +70,9 @@ CL_PROGRAMS = [
     # (kernel file relative to the reference root, alias)
     ("LB_D2Q9/D2Q9.cl", "D2Q9"),
     ("LB_D2Q9/D2Q9i.cl", "D2Q9i"),
+    # the periodic-box semantic of BASELINE configs 3 and 5: float and double
+    ("LB_D2Q9/rocket_yeast/rocket_yeast.cl", "rocket_yeast"),
+    ("LB_D2Q9/multicomponent_multiphase/multi.cl", "multi"),
 ]
 
 

@@ -30,6 +30,7 @@ typedef unsigned short ushort;
 typedef unsigned int uint;
 typedef unsigned long ulong;
 
+#define cl_khr_fp64 1          /* what an fp64-capable device defines; multi.cl tests for it */
 #define CLK_LOCAL_MEM_FENCE 1
 #define CLK_GLOBAL_MEM_FENCE 2
 

@@ -29,6 +29,7 @@ CLSHIM = os.path.join(ORACLE, "clshim")
 CACHE = os.path.join(ORACLE, "_ref", "clshim")
 CFLAGS = ["-O2", "-std=gnu11", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-fno-strict-aliasing", "-w"]
 
+PARSER_VERSION = "2"          # part of the cache key: bump when parse_kernels / _trampolines change
 VERSION = (2015, 1)
 VERSION_TEXT = "clshim (gcc CPU emulation)"
 
@@ -230,8 +231,8 @@ _KERNEL_RE = re.compile(r"\b(?:__kernel|kernel)\s+void\s+(\w+)\s*\(([^)]*)\)\s*\
 
 
 def _strip_comments(src):
-    src = re.sub(r"/\*.*?\*/", " ", src, flags=re.S)
-    return re.sub(r"//[^\n]*", " ", src)
+    """One left-to-right pass, so that `//**** title ****` is a line comment, not the start of a block."""
+    return re.sub(r"//[^\n]*|/\*.*?\*/", " ", src, flags=re.S)
 
 
 def _matching_brace(text, open_pos):
@@ -300,6 +301,7 @@ def _support_digest():
         with open(os.path.join(CLSHIM, fn), "rb") as fh:
             h.update(fh.read())
     h.update(" ".join(CFLAGS).encode())
+    h.update(PARSER_VERSION.encode())
     return h
 
 

@@ -226,6 +226,76 @@ def test_compiled_cl_kernels_equal_oracle_stages(orc, cl, d2q9, nx, ny, lsz):
 
 
 # ------------------------------------------------------------------------------------------------
+# 2b. the periodic-box semantic (BASELINE configs 3 and 5) against the compiled
+#     rocket_yeast.cl (float) and multicomponent_multiphase/multi.cl (double), one population
+def _prog(cl, alias):
+    try:
+        return cl.Program.from_cache(cl.Context(), alias)
+    except cl.Error as exc:
+        pytest.skip(str(exc))
+
+
+def test_periodic_streaming_equals_compiled_move_periodic(orc, cl):
+    """`move_periodic` of rocket_yeast.cl:152-191 (float) and multi.cl:330-369 (double) == oracle_move_periodic,
+    bit for bit: direction convention, wrap-around, nothing dropped."""
+    from util import periodic_case
+    nx, ny = 37, 21
+    i32 = np.int32
+    cx, cy = _buf(cl, CX), _buf(cl, CY)
+    g2 = _gsize((nx, ny), (8, 4))
+    for dtype, alias in ((np.float32, "rocket_yeast"), (np.float64, "multi")):
+        prg = _prog(cl, alias)
+        f0 = periodic_case(orc, nx, ny, dtype, amplitude=1e-2, seed=3)
+        o = orc.OpenCLSchemeOracle(f0, 1.0, bc=orc.BC_PERIODIC, dtype=dtype)
+        f, fs = _buf(cl, f0), _buf(cl, np.zeros_like(f0))
+        for _ in range(3):
+            if dtype == np.float32:
+                prg.move_periodic(None, g2, (8, 4), f, fs, cx, cy, i32(nx), i32(ny), i32(1)).wait()
+            else:
+                prg.move_periodic(None, g2, (8, 4), f, fs, cx, cy, i32(nx), i32(ny), i32(0), i32(1), i32(9)).wait()
+            f, fs = fs, f
+            o.move()
+            assert _same(_read(cl, f, f0.shape, dtype), o.f)
+
+
+def test_periodic_fp64_step_agrees_with_compiled_multi_cl_to_rounding(orc, cl):
+    """BASELINE config 5 / the fp64 gate: the oracle evaluates D2Q9.cl's formulas in double; the
+    reference's only double-precision D2Q9 code is multi.cl (update_hydro_fluid :275-328, update_feq_fluid
+    :11-75 D2Q9 branch, collide_particles_fluid :77-131 with zero body force).  Same algorithm, different
+    association (loop-order sums, new_u/new_rho, pow(cs,4)): 300 steps of one against the other agree to
+    1e-13 relative in rho and u -- two orders inside north_star's 1e-12."""
+    from util import periodic_case
+    prg = _prog(cl, "multi")
+    nx, ny, omega = 48, 32, 1.7
+    f0 = periodic_case(orc, nx, ny, np.float64, u0=0.05, amplitude=1e-3, seed=9)
+    o = orc.OpenCLSchemeOracle(f0, omega, bc=orc.BC_PERIODIC, dtype=np.float64)
+    i32, f64 = np.int32, np.float64
+    Wd = np.array([4. / 9.] + [1. / 9.] * 4 + [1. / 36.] * 4)
+    f, fs, feq = _buf(cl, f0), _buf(cl, f0), _buf(cl, np.zeros_like(f0))
+    rho, u, v, gx, gy = (_buf(cl, np.zeros((ny, nx))) for _ in range(5))
+    w, cx, cy = _buf(cl, Wd), _buf(cl, CX), _buf(cl, CY)
+    cs = f64(1. / np.sqrt(3))
+    g2, l2 = _gsize((nx, ny), (8, 8)), (8, 8)
+    tail = (i32(nx), i32(ny), i32(0), i32(1), i32(9))
+    steps = 300
+    for _ in range(steps):           # multi.py:737-790: move, hydro, feq, collide
+        prg.move_periodic(None, g2, l2, f, fs, cx, cy, *tail).wait()
+        prg.copy_streamed_onto_f(None, g2, l2, fs, f, cx, cy, *tail).wait()
+        prg.update_hydro_fluid(None, g2, l2, f, rho, u, v, gx, gy, w, cx, cy, *tail).wait()
+        prg.update_feq_fluid(None, g2, l2, feq, rho, u, v, w, cx, cy, cs, *tail).wait()
+        prg.collide_particles_fluid(None, g2, l2, f, feq, rho, u, v, gx, gy, f64(omega), w, cx, cy, *tail, cs).wait()
+    o.run(steps)
+    r_ref, u_ref, v_ref = (_read(cl, b, (ny, nx), np.float64) for b in (rho, u, v))
+    assert np.isfinite(r_ref).all() and np.abs(u_ref).max() > 0.02
+    assert np.abs(o.rho - r_ref).max() / np.abs(r_ref).max() < 1e-13
+    assert np.abs(o.u - u_ref).max() / np.abs(u_ref).max() < 1e-13
+    assert np.abs(o.v - v_ref).max() / np.abs(u_ref).max() < 1e-13
+    assert np.abs(o.f - _read(cl, f, f0.shape, np.float64)).max() < 1e-14
+    # mass: both conserve it to round-off
+    assert abs(_read(cl, f, f0.shape, np.float64).sum() - f0.sum()) / f0.sum() < 1e-13
+
+
+# ------------------------------------------------------------------------------------------------
 # 3. the live host classes (build container only)
 def test_live_opencl_reference_if_mounted(orc):
     from oracle import refload
