@@ -825,3 +825,86 @@ def test_old_opencl_velocity_inlet_classes_same_code_same_bits(gpu):
                 assert got[k].flags.f_contiguous
                 assert _same_bits(got[k], g[f"{k}_{s}"]), f"{k} after {s} steps ({name})"
         assert _same_bits(got["feq"], g[f"feq_{done}"])
+
+
+def test_cuda_stages_and_fused_step_equal_the_compiled_reference_kernels(gpu, orc):
+    """No oracle in between: the reference's D2Q9.cl, compiled as C where it lay and shipped in
+    oracle/_ref/clshim, is launched kernel by kernel on the host; the C-ABI single stages
+    (lb_stage_*) and the fused step run on the GPU from the same populations.  Bit for bit."""
+    import os
+    import sys
+    shim = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "shims")
+    if shim not in sys.path:
+        sys.path.append(shim)
+    import pyopencl as cl
+    try:
+        prg = cl.Program.from_cache(cl.Context(), "D2Q9")
+    except cl.Error as exc:
+        pytest.skip(str(exc))
+    from lb_b200 import Lattice
+    nx, ny = 97, 41
+    f0, mask = pipe_case(orc, nx, ny, mask="touching", seed=21)
+    omega, rin, rout = np.float32(1.37), np.float32(1.02), np.float32(0.99)
+    i32 = np.int32
+
+    def buf(a):
+        return cl.Buffer(None, cl.mem_flags.READ_WRITE | cl.mem_flags.COPY_HOST_PTR, hostbuf=np.ascontiguousarray(a))
+
+    def read(b, shape):
+        out = np.empty(shape, np.float32)
+        cl.enqueue_copy(None, out, b)
+        return out
+
+    f, fs, feq = buf(f0), buf(f0), buf(np.zeros_like(f0))
+    u, v, rho = (buf(np.zeros((ny, nx), np.float32)) for _ in range(3))
+    m = buf(mask.astype(np.int32))
+    w = buf(np.array([4. / 9.] + [1. / 9.] * 4 + [1. / 36.] * 4, dtype=np.float32))
+    cx = buf(np.array([0, 1, 0, -1, 0, 1, -1, -1, 1], dtype=np.int32))
+    cy = buf(np.array([0, 0, 1, 0, -1, 1, 1, -1, -1], dtype=np.int32))
+    l2, l3 = (8, 8), (8, 8, 1)
+    g2 = tuple(-(-a // b) * b for a, b in zip((nx, ny), l2))
+    g3 = g2 + (9,)
+    loc = [cl.LocalMemory(4 * 64) for _ in range(3)]
+    cs = 1. / np.sqrt(3)
+
+    def reference_step(check=None):
+        prg.move(None, g3, l3, f, fs, cx, cy, i32(nx), i32(ny)).wait()
+        prg.copy_buffer(None, g3, l3, fs, f, i32(nx), i32(ny)).wait()
+        if check:
+            check("move")
+        prg.move_bcs(None, g2, l2, f, u, rin, rout, i32(nx), i32(ny)).wait()
+        prg.bounceback_in_obstacle(None, g2, l2, m, f, i32(nx), i32(ny)).wait()
+        if check:
+            check("move_bcs")
+        prg.update_hydro(None, g2, l2, f, u, v, rho, rin, rout, i32(nx), i32(ny)).wait()
+        if check:
+            check("update_hydro")
+        prg.update_feq(None, g3, l3, feq, u, v, rho, *loc, w, cx, cy, np.float32(cs), np.float32(cs ** 2),
+                       np.float32(2 * cs ** 2), np.float32(2 * cs ** 4), i32(nx), i32(ny)).wait()
+        if check:
+            check("update_feq")
+        prg.collide_particles(None, g3, l3, f, feq, omega, i32(nx), i32(ny)).wait()
+        if check:
+            check("collide_particles")
+
+    with Lattice(nx, ny, float(omega), float(rin), float(rout), mask=mask, f0=f0, math="strict") as sim:
+        def check(stage):
+            getattr(sim, stage)()
+            assert np.array_equal(sim.download("f"), read(f, f0.shape)), stage
+            if stage in ("update_hydro", "update_feq"):
+                assert np.array_equal(sim.download("rho"), read(rho, (ny, nx))), stage
+                assert np.array_equal(sim.download("u"), read(u, (ny, nx))), stage
+                assert np.array_equal(sim.download("v"), read(v, (ny, nx))), stage
+            if stage == "update_feq":
+                assert np.array_equal(sim.download("feq"), read(feq, f0.shape)), stage
+
+        for _ in range(2):
+            reference_step(check)
+    with Lattice(nx, ny, float(omega), float(rin), float(rout), mask=mask, f0=f0, math="strict") as sim:
+        for _ in range(25):                                # the reference buffers already hold step 2
+            reference_step()
+        sim.run(27)                                        # the fused kernel, 27 steps from the same f0
+        assert np.array_equal(sim.download("f"), read(f, f0.shape))
+        assert np.array_equal(sim.download("rho"), read(rho, (ny, nx)))
+        assert np.array_equal(sim.download("u"), read(u, (ny, nx)))
+        assert np.array_equal(sim.download("feq"), read(feq, f0.shape))
