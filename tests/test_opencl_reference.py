@@ -321,6 +321,31 @@ def test_live_opencl_reference_if_mounted(orc):
     assert np.isfinite(g["f"]).all() and np.abs(g["u"]).max() > 1e-3
 
 
+def test_committed_golden_vectors_are_what_the_reference_produces_if_mounted():
+    """Provenance: re-run the reference's own classes (same constructor calls, same seeds as
+    tests/golden/make_golden.py) and compare with the committed files."""
+    import ast
+    from oracle import refload
+    if not refload.opencl_host_available():
+        pytest.skip("reference tree not mounted")
+    ls = dict(two_d_local_size=(16, 16), three_d_local_size=(16, 16, 1))    # another work-group size on purpose
+    for name, mod, cls in (("opencl_pipe_65x33.npz", refload.opencl_dim(), "Pipe_Flow"),
+                           ("opencl_d2q9i_pipe_49x25.npz", refload.opencl_dim_D2Q9i(), "Pipe_Flow"),
+                           ("oldcl_velocity_inlet_61x31.npz", refload.old_opencl(), "Pipe_Flow_PeriodicBC_VelocityInlet")):
+        g = _load(name)
+        kw = ast.literal_eval(str(g["ctor_kwargs"]))
+        np.random.seed(int(g["seed"]))
+        with refload.quiet():
+            sim = getattr(mod, cls)(**kw, **ls)
+        get = sim.get_fields if hasattr(sim, "get_fields") else sim.get_fields_on_cpu
+        assert _same(get()["f"], g["f_0"]), name
+        s = int(g["steps"][1])
+        sim.run(s)
+        got = get()
+        for k in ("f", "rho", "u", "v"):
+            assert _same(got[k], g[f"{k}_{s}"]), (name, k)
+
+
 def test_live_single_stage_methods_if_mounted(orc):
     """The check notebooks call move(), move_bcs(), ... one by one (testing/Bryan/opencl_check_03.ipynb)."""
     from oracle import refload
