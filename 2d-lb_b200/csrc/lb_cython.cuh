@@ -251,6 +251,73 @@ __global__ void cy_prestream_kernel(int nx, int ny, int pitch, long long plane, 
     for (int j = 0; j < 9; ++j) f[j * plane + i] = g[j];
 }
 
+// ---- single stages (the Cython classes' move_bcs / move / update_hydro / collide_particles are plain
+//      methods a user can call one by one; cython_dim.pyx:204-344).  Per-node kernels, not hot. --------
+
+// row exchange of the velocity-inlet class, physically (OLD/cython.pyx:305-316); the fused kernel folds
+// it into the pull instead.  Idempotent: its sources are never its destinations.
+__global__ void cyv_rows_kernel(int nx, int ny, int pitch, long long plane, float *f)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= nx) return;
+    const long long s = x, n = (long long)(ny - 1) * pitch + x;
+    const float a4 = f[4 * plane + s], a8 = f[8 * plane + s], a7 = f[7 * plane + s];
+    const float b2 = f[2 * plane + n], b6 = f[6 * plane + n], b5 = f[5 * plane + n];
+    f[4 * plane + n] = a4; f[8 * plane + n] = a8; f[7 * plane + n] = a7;
+    f[2 * plane + s] = b2; f[6 * plane + s] = b6; f[5 * plane + s] = b5;
+}
+
+// `move` (cython_dim.pyx:271-299): the in-place sweeps as a pull from a snapshot; slots the sweeps never
+// write keep the node's own value (no upstream node, or one of the four non-streaming lines).
+__global__ void cy_stage_move_kernel(int nx, int ny, int pitch, long long plane, const float *src, float *dst)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= nx || y >= ny) return;
+    const int lx = nx - 1, ly = ny - 1;
+    const bool w_ = (x == 0), e_ = (x == lx), s_ = (y == 0), n_ = (y == ly);
+    const int cx[9] = {0, 1, 0, -1, 0, 1, -1, -1, 1}, cy[9] = {0, 0, 1, 0, -1, 1, 1, -1, -1};
+    const bool keep[9] = {true, w_ || s_, e_ || s_, e_ || n_, w_ || n_, w_ || s_, e_ || s_, e_ || n_, w_ || n_};
+    const long long i = (long long)y * pitch + x;
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+        const long long from = keep[j] ? i : (long long)(y - cy[j]) * pitch + (x - cx[j]);
+        dst[j * plane + i] = src[j * plane + from];
+    }
+}
+
+// `update_hydro` (+ the obstacle classes' zeroing override)
+template <bool OLD, bool VIN>
+__global__ void cy_stage_hydro_kernel(int nx, int ny, int pitch, long long plane, const float *f, float *rho, double *u,
+                                      double *v, const uint8_t *mask, int mask_pitch, CyConsts c)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= nx || y >= ny) return;
+    const long long i = (long long)y * pitch + x;
+    float g[9];
+#pragma unroll
+    for (int j = 0; j < 9; ++j) g[j] = f[j * plane + i];
+    const bool solid = mask && mask[(long long)y * mask_pitch + x] == 1;
+    float r;
+    double uu, vv;
+    if (VIN) cyv_moments(c, g, x, y, nx - 1, ny - 1, solid, r, uu, vv);
+    else cy_moments<OLD>(c, g, x, y, nx - 1, ny - 1, solid, r, uu, vv);
+    rho[i] = r; u[i] = uu; v[i] = vv;
+}
+
+// `collide_particles` (cython_dim.pyx:336-344; OLD/cython.pyx: float32 because omega is a Python float)
+template <bool OLD>
+__global__ void cy_stage_collide_kernel(int nx, int ny, int pitch, long long plane, float *f, const float *feq, CyConsts c)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= nx || y >= ny) return;
+    const long long i = (long long)y * pitch + x;
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+        const float a = f[j * plane + i], e = feq[j * plane + i];
+        f[j * plane + i] = OLD ? a * c.keep_f + c.om_f * e : (float)((double)a * c.keep + c.omega * (double)e);
+    }
+}
+
 // ---- the fused step -------------------------------------------------------------------------
 // VIN = true: OLD/cython.pyx's velocity-inlet / y-periodic family.  Its row exchange
 // (f4,f8,f7 of row ly <- row 0 ; f2,f6,f5 of row 0 <- row ly, before streaming) is folded into the

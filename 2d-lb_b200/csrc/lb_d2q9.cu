@@ -1063,9 +1063,18 @@ int lb_device_ptr(lb_sim *sim, int field, void **ptr, int64_t *pitch_elems)
 int lb_stage_move(lb_sim *sim)
 {
     if (!sim) return LB_ERR_INVALID;
-    if (sim->cfg.scheme != LB_SCHEME_OPENCL) return fail(sim, LB_ERR_STATE, "lb_stage_move: single stages exist for LB_SCHEME_OPENCL only");
     if (uses_halo(sim)) return fail(sim, LB_ERR_STATE, "single stages are not available on halo-connected slabs");
     CU(cudaSetDevice(sim->cfg.device));
+    if (is_cython(sim) || is_oldcl(sim)) {
+        const float *src = (const float *)sim->buf[sim->cur];
+        float *dst = (float *)sim->buf[sim->cur ^ 1];
+        if (is_cython(sim)) cy_stage_move_kernel<<<grid2d(sim), 128, 0, sim->stream>>>(sim->cfg.nx, sim->cfg.ny, sim->pitch, sim->plane, src, dst);
+        else oc_stage_move_kernel<<<grid2d(sim), 128, 0, sim->stream>>>(sim->cfg.nx, sim->cfg.ny, sim->pitch, sim->plane, src, dst, sim->frozen);
+        CU(cudaGetLastError());
+        sim->cur ^= 1;
+        sim->prestream_done = false;
+        return LB_OK;
+    }
     DISPATCH(k_stage_move, grid2d(sim), sim->cfg.nx, sim->cfg.ny, sim->pitch, sim->plane, sim->cfg.bc == LB_BC_PERIODIC,
              (const T *)sim->buf[sim->cur], (T *)sim->buf[sim->cur ^ 1]);
     sim->cur ^= 1;
@@ -1075,8 +1084,23 @@ int lb_stage_move(lb_sim *sim)
 int lb_stage_move_bcs(lb_sim *sim)
 {
     if (!sim) return LB_ERR_INVALID;
-    if (sim->cfg.scheme != LB_SCHEME_OPENCL) return fail(sim, LB_ERR_STATE, "lb_stage_move_bcs: single stages exist for LB_SCHEME_OPENCL only");
     CU(cudaSetDevice(sim->cfg.device));
+    if (is_cython(sim)) {          // cython_dim.pyx:204-269 (+ :468-513 with a mask), OLD/cython.pyx:278-316
+        const bool vin = sim->cfg.bc == LB_BC_VELOCITY_YPERIODIC;
+        cy_prestream_kernel<<<grid2d(sim), 128, 0, sim->stream>>>(sim->cfg.nx, sim->cfg.ny, sim->pitch, sim->plane,
+            (float *)sim->buf[sim->cur], (const double *)sim->u, sim->mask, sim->mask_pitch, cy_consts_of(sim), vin);
+        if (vin) cyv_rows_kernel<<<(sim->cfg.nx + 127) / 128, 128, 0, sim->stream>>>(sim->cfg.nx, sim->cfg.ny, sim->pitch, sim->plane,
+                                                                                       (float *)sim->buf[sim->cur]);
+        CU(cudaGetLastError());
+        return LB_OK;
+    }
+    if (is_oldcl(sim)) {           // D2Q9.cl:263-321 + :398-433 as OLD/opencl.py:290-297, :365-371 launches them
+        oc_prestream_kernel<<<grid2d(sim), 128, 0, sim->stream>>>(oc_params_of(sim), (float *)sim->buf[sim->cur]);
+        oc_rows_kernel<<<(sim->cfg.nx + 127) / 128, 128, 0, sim->stream>>>(sim->cfg.nx, sim->cfg.ny, sim->pitch, sim->plane,
+                                                                           (float *)sim->buf[sim->cur], sim->mask, sim->mask_pitch);
+        CU(cudaGetLastError());
+        return LB_OK;
+    }
     DISPATCH(k_stage_bcs, grid2d(sim), sim->cfg.nx, sim->cfg.ny, sim->pitch, sim->plane, sim->cfg.global_nx, sim->cfg.x_offset,
              sim->cfg.bc == LB_BC_PIPE, sim->mask, sim->mask_pitch, (T *)sim->buf[sim->cur], consts_of<T>(sim), sim->cfg.model);
     return LB_OK;
@@ -1085,8 +1109,27 @@ int lb_stage_move_bcs(lb_sim *sim)
 int lb_stage_update_hydro(lb_sim *sim)
 {
     if (!sim) return LB_ERR_INVALID;
-    if (sim->cfg.scheme != LB_SCHEME_OPENCL) return fail(sim, LB_ERR_STATE, "lb_stage_update_hydro: single stages exist for LB_SCHEME_OPENCL only");
     CU(cudaSetDevice(sim->cfg.device));
+    if (is_cython(sim)) {
+        const int nx = sim->cfg.nx, ny = sim->cfg.ny;
+        const float *f = (const float *)sim->buf[sim->cur];
+        float *rho = (float *)sim->rho;
+        double *u = (double *)sim->u, *v = (double *)sim->v;
+        const CyConsts c = cy_consts_of(sim);
+        if (sim->cfg.bc == LB_BC_VELOCITY_YPERIODIC)
+            cy_stage_hydro_kernel<true, true><<<grid2d(sim), 128, 0, sim->stream>>>(nx, ny, sim->pitch, sim->plane, f, rho, u, v, sim->mask, sim->mask_pitch, c);
+        else if (sim->cfg.scheme == LB_SCHEME_CYTHON_OLD)
+            cy_stage_hydro_kernel<true, false><<<grid2d(sim), 128, 0, sim->stream>>>(nx, ny, sim->pitch, sim->plane, f, rho, u, v, sim->mask, sim->mask_pitch, c);
+        else
+            cy_stage_hydro_kernel<false, false><<<grid2d(sim), 128, 0, sim->stream>>>(nx, ny, sim->pitch, sim->plane, f, rho, u, v, sim->mask, sim->mask_pitch, c);
+        CU(cudaGetLastError());
+        return LB_OK;
+    }
+    if (is_oldcl(sim)) {
+        oc_stage_hydro_kernel<<<grid2d(sim), 128, 0, sim->stream>>>(oc_params_of(sim), (const float *)sim->buf[sim->cur]);
+        CU(cudaGetLastError());
+        return LB_OK;
+    }
     DISPATCH(k_stage_hydro, grid2d(sim), sim->cfg.nx, sim->cfg.ny, sim->pitch, sim->plane, (const T *)sim->buf[sim->cur],
              (T *)sim->rho, (T *)sim->u, (T *)sim->v, sim->cfg.model);
     if (sim->cfg.zero_obstacle_velocity && sim->mask) return lb_stage_zero_velocity(sim);
@@ -1118,9 +1161,19 @@ int lb_stage_update_feq(lb_sim *sim)
 int lb_stage_collide(lb_sim *sim)
 {
     if (!sim) return LB_ERR_INVALID;
-    if (sim->cfg.scheme != LB_SCHEME_OPENCL) return fail(sim, LB_ERR_STATE, "lb_stage_collide: single stages exist for LB_SCHEME_OPENCL only");
     CU(cudaSetDevice(sim->cfg.device));
     if (!sim->feq) return fail(sim, LB_ERR_STATE, "lb_stage_collide: call lb_stage_update_feq first");
+    if (is_cython(sim)) {
+        if (sim->cfg.scheme == LB_SCHEME_CYTHON_OLD)
+            cy_stage_collide_kernel<true><<<grid2d(sim), 128, 0, sim->stream>>>(sim->cfg.nx, sim->cfg.ny, sim->pitch, sim->plane,
+                (float *)sim->buf[sim->cur], (const float *)sim->feq, cy_consts_of(sim));
+        else
+            cy_stage_collide_kernel<false><<<grid2d(sim), 128, 0, sim->stream>>>(sim->cfg.nx, sim->cfg.ny, sim->pitch, sim->plane,
+                (float *)sim->buf[sim->cur], (const float *)sim->feq, cy_consts_of(sim));
+        CU(cudaGetLastError());
+        sim->prestream_done = false;
+        return LB_OK;
+    }
     DISPATCH(k_stage_collide, grid2d(sim), sim->cfg.nx, sim->cfg.ny, sim->pitch, sim->plane, (T *)sim->buf[sim->cur],
              (const T *)sim->feq, consts_of<T>(sim));
     return LB_OK;

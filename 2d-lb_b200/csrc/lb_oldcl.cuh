@@ -121,6 +121,63 @@ __global__ void oc_rows_kernel(int nx, int ny, int pitch, long long plane, float
     for (int j = 1; j < 9; ++j) { f[j * plane + s] = a[j]; f[j * plane + n] = b[j]; }
 }
 
+// ---- single stages (OLD/opencl.py's move / update_hydro as separate calls; move_bcs is
+//      oc_prestream_kernel + oc_rows_kernel, update_feq and collide_particles are the opencl scheme's) ----
+
+// `move` + `copy_buffer` (D2Q9.cl:139-171, :123-137): slots without an upstream node take the frozen value
+__global__ void oc_stage_move_kernel(int nx, int ny, int pitch, long long plane, const float *src, float *dst,
+                                     const float *frozen)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= nx || y >= ny) return;
+    const int lx = nx - 1, ly = ny - 1;
+    const long long i = (long long)y * pitch + x;
+    float g[9];
+    const int cx[9] = {0, 1, 0, -1, 0, 1, -1, -1, 1}, cy[9] = {0, 0, 1, 0, -1, 1, 1, -1, -1};
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+        const int sx = x - cx[j], sy = y - cy[j];
+        g[j] = (sx >= 0 && sx <= lx && sy >= 0 && sy <= ly) ? src[j * plane + (long long)sy * pitch + sx] : 0.f;
+    }
+    const float *fw = oc_frozen_w(frozen, nx, ny), *fe = oc_frozen_e(frozen, nx, ny);
+    const float *fs = oc_frozen_s(frozen, nx, ny), *fn = oc_frozen_n(frozen, nx, ny);
+    if (x == 0) { g[1] = fw[y]; g[5] = fw[ny + y]; g[8] = fw[2 * ny + y]; }
+    if (x == lx) { g[3] = fe[y]; g[6] = fe[ny + y]; g[7] = fe[2 * ny + y]; }
+    if (y == 0) { g[2] = fs[x]; g[5] = fs[nx + x]; g[6] = fs[2 * nx + x]; }
+    if (y == ly) { g[4] = fn[x]; g[7] = fn[nx + x]; g[8] = fn[2 * nx + x]; }
+#pragma unroll
+    for (int j = 0; j < 9; ++j) dst[j * plane + i] = g[j];
+}
+
+// update_hydro_PeriodicBC_VelocityInlet (D2Q9.cl:323-374) [+ set_zero_velocity_in_obstacle with a mask]
+__global__ void oc_stage_hydro_kernel(OcParams p, const float *f)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= p.nx || y >= p.ny) return;
+    const int lx = p.nx - 1, ly = p.ny - 1;
+    const long long i = (long long)y * p.pitch + x;
+    float g[9];
+#pragma unroll
+    for (int j = 0; j < 9; ++j) g[j] = f[j * p.plane + i];
+    float rho, u, v;
+    moments<float, MATH_STRICT>(g, rho, u, v);
+    if (x == 0 || x == lx) {
+        u = p.u[i]; v = p.v[i];
+        if (y != 0 && y < ly) {
+            if (x == 0) {
+                rho = (float)(p.kw * ((double)((g[0] + g[2]) + g[4]) + 2. * (double)((g[3] + g[6]) + g[7])));
+                u = p.u_w;
+            }
+            if (x == lx) {
+                rho = (float)(p.ke * ((double)((g[0] + g[2]) + g[4]) + 2. * (double)((g[1] + g[5]) + g[8])));
+                u = p.u_e;
+            }
+        }
+    }
+    if (p.mask && p.mask[(long long)y * p.mask_pitch + x] == 1) { u = 0.f; v = 0.f; }
+    p.rho[i] = rho; p.u[i] = u; p.v[i] = v;
+}
+
 // ---- the fused step ---------------------------------------------------------------------------
 template <int WX, int WY, int MINB>
 __global__ void __launch_bounds__(32 * WX * WY, MINB) fused_step_oldcl_kernel(const OcParams p)

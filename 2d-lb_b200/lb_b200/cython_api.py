@@ -74,10 +74,19 @@ class Pipe_Flow(_dim.Pipe_Flow):
     u = property(lambda self: _host(self.sim.download("u")))
     v = property(lambda self: _host(self.sim.download("v")))
 
-    def _single_stage(self, *_):
-        raise NotImplementedError("single stages are fused on the GPU for the Cython-order scheme; use run()")
+    # the single steps of cython_dim.pyx:204-344, individually callable like the reference's methods
+    # (run() is the same sequence fused into one kernel per step)
+    def move_bcs(self):
+        self.sim.move_bcs()
 
-    move = move_bcs = update_hydro = collide_particles = _single_stage
+    def move(self):
+        self.sim.move()
+
+    def update_hydro(self):
+        self.sim.update_hydro()
+
+    def collide_particles(self):
+        self.sim.collide_particles()
 
     def get_fields(self):
         """cython_dim.pyx:361-372"""

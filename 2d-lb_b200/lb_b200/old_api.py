@@ -146,10 +146,6 @@ class Pipe_Flow_PeriodicBC_VelocityInlet(Pipe_Flow):
         v_host = np.zeros((nx, ny)).astype(np.float32, order='F')
         self.sim.upload_moments(rho_host.T, u_host.T, v_host.T)
 
-    def _no_single_stage(self, *a, **k):
-        raise NotImplementedError("scheme 'opencl_old' runs fused steps only; use run(n)")
-
-    move_bcs = move = update_hydro = collide_particles = _no_single_stage
 
 
 class Pipe_Flow_Obstacles_PeriodicBC_VelocityInlet(Pipe_Flow_PeriodicBC_VelocityInlet):

@@ -63,6 +63,19 @@ class Pipe_Flow(object):
     def run(self, num_iterations):
         self.sim.run(int(num_iterations))
 
+    # the single steps (OLD/cython.pyx:97-256), individually callable like the reference's methods
+    def move_bcs(self):
+        self.sim.move_bcs()
+
+    def move(self):
+        self.sim.move()
+
+    def update_hydro(self):
+        self.sim.update_hydro()
+
+    def collide_particles(self):
+        self.sim.collide_particles()
+
     f = property(lambda self: _host(self.sim.download("f")))
     feq = property(lambda self: _host(self.sim.download("feq")))
     rho = property(lambda self: _host(self.sim.download("rho")))

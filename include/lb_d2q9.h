@@ -178,7 +178,13 @@ int lb_download_strided(lb_sim *sim, int field, int stride_x, int stride_y, void
  *    update_hydro    = `update_hydro`                          (:355-362)
  *    update_feq      = `update_feq`                            (:295-306)
  *    collide         = `collide_particles`                     (:364-370)
- *    zero_velocity   = `set_zero_velocity_in_obstacle`         (:506-508) */
+ *    zero_velocity   = `set_zero_velocity_in_obstacle`         (:506-508)
+ *    With the other schemes the same five calls are the methods of the class the scheme mirrors:
+ *    LB_SCHEME_CYTHON[_OLD]: move_bcs / move / update_hydro / update_feq / collide_particles of
+ *    cython_dim.pyx:204-344 (OLD/cython.pyx:97-360), obstacle swap and velocity zeroing included when a
+ *    mask is set; LB_SCHEME_OPENCL_OLD: D2Q9.cl's move_bcs_PeriodicBC_VelocityInlet (+ bounce-back),
+ *    move + copy_buffer, update_hydro_PeriodicBC_VelocityInlet (+ zeroing), update_feq, collide_particles
+ *    as OLD/opencl.py:189-255, :290-371 launches them. */
 int lb_stage_move(lb_sim *sim);
 int lb_stage_move_bcs(lb_sim *sim);
 int lb_stage_update_hydro(lb_sim *sim);

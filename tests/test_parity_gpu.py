@@ -908,3 +908,73 @@ def test_cuda_stages_and_fused_step_equal_the_compiled_reference_kernels(gpu, or
         assert np.array_equal(sim.download("rho"), read(rho, (ny, nx)))
         assert np.array_equal(sim.download("u"), read(u, (ny, nx)))
         assert np.array_equal(sim.download("feq"), read(feq, f0.shape))
+
+
+# ------------------------------------------------------------------------------------------------
+# single steps of the other schemes: the reference classes expose move_bcs(), move(), update_hydro(),
+# update_feq(), collide_particles() as methods; so do the drop-in classes
+# ------------------------------------------------------------------------------------------------
+STAGES = ("move_bcs", "move", "update_hydro", "update_feq", "collide_particles")
+
+
+def test_cython_single_steps_match_live_reference_step_by_step(gpu, orc):
+    """cython_dim.Pipe_Flow_Cylinder and OLD/cython classes: every single step of the compiled reference
+    against the same call on the drop-in class, then run() against the sequence of single steps."""
+    from oracle import refload
+    if not refload.available():
+        pytest.skip("oracle/_ref not built")
+    from lb_b200 import cython_api, old_cython_api
+    cd, old = refload.cython_dim(), refload.old_cython()
+    mask = np.zeros((61, 31), dtype=bool)
+    mask[15:20, 10:18] = True
+    cases = [
+        (cd.Pipe_Flow_Cylinder, cython_api.Pipe_Flow_Cylinder,
+         dict(cylinder_center=[0.75, 0.5], cylinder_radius=0.1, diameter=1., rho=1., viscosity=1., pressure_grad=-10.,
+              pipe_length=3., N=4), dict(verbose=False)),
+        (old.Pipe_Flow_Obstacles, old_cython_api.Pipe_Flow_Obstacles,
+         dict(lx=60, ly=30, omega=1.2, deltaP=-0.02, obstacle_mask=mask), {}),
+        (old.Pipe_Flow_Obstacles_PeriodicBC_VelocityInlet, old_cython_api.Pipe_Flow_Obstacles_PeriodicBC_VelocityInlet,
+         dict(lx=60, ly=30, omega=1.3, deltaP=-0.0, u_w=0.05, obstacle_mask=mask), {}),
+    ]
+    for ref_cls, my_cls, kw, extra in cases:
+        np.random.seed(31)
+        with refload.quiet():
+            ref = ref_cls(**kw)
+        np.random.seed(31)
+        mine = my_cls(**kw, **extra)
+        assert np.array_equal(np.asarray(ref.f), mine.f)
+        for _ in range(3):
+            for stage in STAGES:
+                getattr(ref, stage)()
+                getattr(mine, stage)()
+                assert np.array_equal(np.asarray(ref.f), mine.f), (ref_cls.__name__, stage, "f")
+                assert np.array_equal(np.asarray(ref.u), mine.u), (ref_cls.__name__, stage, "u")
+                assert np.array_equal(np.asarray(ref.rho), mine.rho), (ref_cls.__name__, stage, "rho")
+            assert np.array_equal(np.asarray(ref.feq), mine.feq), ref_cls.__name__
+        ref.run(20)
+        mine.run(20)                    # the fused kernel continues from a state reached by single steps
+        assert np.array_equal(np.asarray(ref.f), mine.f) and np.array_equal(np.asarray(ref.v), mine.v), ref_cls.__name__
+
+
+def test_opencl_old_single_steps_match_oracle_and_run(gpu, orc):
+    from lb_b200 import Lattice
+    nx, ny = 131, 37
+    f0, mask = pipe_case(orc, nx, ny, mask="touching", seed=77)
+    uw = ue = np.float32(0.05)
+    u0 = np.full((ny, nx), uw, np.float32)
+    kw = dict(mask=mask.astype(np.int32), bc=orc.BC_VELOCITY_YPERIODIC, u_w=uw, u_e=ue, u0=u0)
+    ref = orc.OpenCLSchemeOracle(f0, np.float32(1.3), **kw)
+    with Lattice(nx, ny, 1.3, mask=mask, dtype=np.float32, bc="velocity_yperiodic", scheme="opencl_old",
+                 u_west=float(uw), u_east=float(ue)) as sim:
+        sim.upload_moments(np.ones((ny, nx), np.float32), u0, np.zeros((ny, nx), np.float32))
+        sim.upload_f(f0)
+        for _ in range(3):
+            for stage in STAGES:
+                getattr(ref, stage)()
+                getattr(sim, stage)()
+                for k in ("f", "rho", "u", "v"):
+                    assert _same_bits(sim.download(k), getattr(ref, k)), (stage, k)
+            assert _same_bits(sim.download("feq"), ref.feq)
+        ref.run(15)
+        sim.run(15)
+        assert _same_bits(sim.download("f"), ref.f) and _same_bits(sim.download("u"), ref.u)
