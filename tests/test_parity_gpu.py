@@ -964,6 +964,7 @@ def test_opencl_old_single_steps_match_oracle_and_run(gpu, orc):
     u0 = np.full((ny, nx), uw, np.float32)
     kw = dict(mask=mask.astype(np.int32), bc=orc.BC_VELOCITY_YPERIODIC, u_w=uw, u_e=ue, u0=u0)
     ref = orc.OpenCLSchemeOracle(f0, np.float32(1.3), **kw)
+    ref.rho[...] = 1                    # the density array the class uploads before the first update_hydro
     with Lattice(nx, ny, 1.3, mask=mask, dtype=np.float32, bc="velocity_yperiodic", scheme="opencl_old",
                  u_west=float(uw), u_east=float(ue)) as sim:
         sim.upload_moments(np.ones((ny, nx), np.float32), u0, np.zeros((ny, nx), np.float32))
