@@ -324,6 +324,23 @@ __global__ void k_span_solid(int nx, int ny, const uint8_t *mask, int mask_pitch
     span_solid[(long long)y * nspans + s] = n == 32 ? 2 : (n ? 1 : 0);
 }
 
+// arithmetic-free twin of the fused kernel's memory traffic (see lb_selftest_copy in the header)
+template <typename T, int V>
+__global__ void __launch_bounds__(128, 6) k_copy_pattern(const T *__restrict__ src, T *__restrict__ dst, int pitch, int ny, long long plane)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int x0 = ((blockIdx.x * 2 + (warp & 1)) * 32 + lane) * V;
+    const int y = (blockIdx.z * gridDim.y + blockIdx.y) * 2 + (warp >> 1);
+    if (x0 >= pitch || y >= ny) return;
+    const int ym = y > 0 ? y - 1 : ny - 1, yp = y < ny - 1 ? y + 1 : 0;
+    const int rows[9] = {y, y, ym, y, yp, ym, ym, yp, yp};
+    Pack<T, V> q[9];
+#pragma unroll
+    for (int j = 0; j < 9; ++j) q[j] = load_pack<T, V, 1>(src + j * plane + (long long)rows[j] * pitch + x0);
+#pragma unroll
+    for (int j = 0; j < 9; ++j) store_pack<T, V, 0>(dst + j * plane + (long long)y * pitch + x0, q[j]);
+}
+
 __global__ void k_mask_disk(int nx, int ny, int x_off, double cx, double cy, double r2, uint8_t *mask, int mask_pitch)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
@@ -604,6 +621,35 @@ int lb_selftest_rcp(int device, uint32_t first_bits, uint32_t last_bits, uint64_
     cudaFree(d);
     if (e != cudaSuccess) return LB_ERR_CUDA;
     *mismatches = h;
+    return LB_OK;
+}
+
+int lb_selftest_copy(lb_sim *sim, int reps, double *ms_per_launch)
+{
+    if (!sim || !ms_per_launch || reps < 1) return fail(sim, LB_ERR_INVALID, "lb_selftest_copy: bad argument");
+    CU(cudaSetDevice(sim->cfg.device));
+    const int ny = sim->cfg.ny;
+    const int span = sim->elem == 4 ? 128 : 64;
+    const unsigned tx = (sim->pitch + 2 * span - 1) / (2 * span), ty = (ny + 1) / 2;
+    const unsigned gy = ty < 65535 ? ty : 65535;
+    const dim3 grid(tx, gy, (ty + gy - 1) / gy);
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    auto launch = [&]() {
+        if (sim->elem == 4) k_copy_pattern<float, 4><<<grid, 128, 0, sim->stream>>>((const float *)sim->buf[sim->cur], (float *)sim->buf[sim->cur ^ 1], sim->pitch, ny, sim->plane);
+        else k_copy_pattern<double, 2><<<grid, 128, 0, sim->stream>>>((const double *)sim->buf[sim->cur], (double *)sim->buf[sim->cur ^ 1], sim->pitch, ny, sim->plane);
+    };
+    launch();                                            // warm-up
+    cudaEventRecord(e0, sim->stream);
+    for (int r = 0; r < reps; ++r) launch();
+    cudaEventRecord(e1, sim->stream);
+    cudaError_t e = cudaStreamSynchronize(sim->stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    float ms = 0.f;
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    CU(e);
+    *ms_per_launch = (double)ms / reps;
     return LB_OK;
 }
 

@@ -227,6 +227,13 @@ class Lattice:
         self._call("lb_total_mass", ct.byref(out))
         return out.value
 
+    def copy_ceiling_ms(self, reps=10):
+        """ms per launch of an arithmetic-free kernel with the fused step's memory access pattern (the
+        practical HBM ceiling of this device for this lattice; populations are left untouched)."""
+        out = ct.c_double()
+        self._call("lb_selftest_copy", int(reps), ct.byref(out))
+        return out.value
+
     def checksum(self):
         """Order-independent exact checksum of the populations (64-bit sum of their bit patterns)."""
         out = ct.c_uint64()

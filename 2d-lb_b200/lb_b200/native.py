@@ -18,7 +18,7 @@ WEST, EAST = 0, 1
 EDGE_BOUNDARY, EDGE_WRAP, EDGE_HALO = 0, 1, 2
 SYNTH_PIPE_RAMP, SYNTH_SHEAR_LAYERS = 0, 1
 IPC_HANDLE_BYTES = 64
-ABI_VERSION = 3
+ABI_VERSION = 4
 SCHEME_OPENCL, SCHEME_CYTHON, SCHEME_CYTHON_OLD, SCHEME_OPENCL_OLD = 0, 1, 2, 3
 MODEL_D2Q9, MODEL_D2Q9I = 0, 1
 
@@ -28,7 +28,7 @@ SYMBOLS = [
     "lb_set_mask", "lb_upload_f", "lb_upload_moments", "lb_step", "lb_sync", "lb_download", "lb_download_strided",
     "lb_stage_move", "lb_stage_move_bcs", "lb_stage_update_hydro", "lb_stage_update_feq",
     "lb_stage_collide", "lb_stage_zero_velocity", "lb_init_synthetic", "lb_set_mask_disk",
-    "lb_total_mass", "lb_checksum", "lb_selftest_rcp", "lb_launch_count", "lb_set_variant", "lb_variant_count", "lb_variant_name",
+    "lb_total_mass", "lb_checksum", "lb_selftest_rcp", "lb_selftest_copy", "lb_launch_count", "lb_set_variant", "lb_variant_count", "lb_variant_name",
     "lb_device_ptr", "lb_stream", "lb_halo_ipc_handle", "lb_halo_connect_ipc", "lb_halo_connect_local",
     "lb_halo_prime",
 ]
@@ -87,6 +87,7 @@ def _declare(lib):
         "lb_total_mass": (i, [vp, ct.POINTER(d)]),
         "lb_checksum": (i, [vp, ct.POINTER(ct.c_uint64)]),
         "lb_selftest_rcp": (i, [i, ct.c_uint32, ct.c_uint32, ct.POINTER(ct.c_uint64)]),
+        "lb_selftest_copy": (i, [vp, i, ct.POINTER(ct.c_double)]),
         "lb_launch_count": (ct.c_int64, [vp]),
         "lb_set_variant": (i, [vp, i]),
         "lb_variant_count": (i, []),

@@ -431,6 +431,21 @@ def main():
     achieved = cells_local * bytes_per_lu / (launch_ms * 1e-3) / 1e9
     peak, peak_src = measured_peak()
 
+    # ---- what an arithmetic-free kernel with the same access pattern reaches, here and now ---------
+    ceiling = None
+    try:
+        barrier()
+        c_ms = lat.copy_ceiling_ms(10)
+        if world > 1:
+            t = torch.tensor([c_ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            c_ms = float(t.item())
+        ceiling = {"GB/s": cells_local * bytes_per_lu / (c_ms * 1e-3) / 1e9, "ms_per_launch": c_ms,
+                   "how": "lb_selftest_copy: 9 x 128-bit loads (D2Q9 row offsets) + 9 x 128-bit stores per thread, "
+                          "the fused kernel's thread mapping, no arithmetic; same buffers, 10 launches, CUDA events"}
+    except Exception as exc:                      # a diagnostic: never fails the bench
+        ceiling = {"GB/s": None, "error": repr(exc)}
+
     # ---- end to end through the C-ABI with host buffers ----------------------------------------
     e2e = None
     if not args.no_e2e:
@@ -491,7 +506,9 @@ def main():
             "gpu_launches": int(launches) * world,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0,
-                         "bytes_per_lattice_update": bytes_per_lu, "per": "GPU, kernel fused_step_kernel"},
+                         "bytes_per_lattice_update": bytes_per_lu, "per": "GPU, kernel fused_step_kernel",
+                         "pattern_copy_ceiling": ceiling,
+                         "frac_of_pattern_copy_ceiling": (achieved / ceiling["GB/s"]) if ceiling and ceiling.get("GB/s") else None},
             "cpu_baseline": cpu,
             "checks": {"total_mass": mass, "mass_finite": bool(np.isfinite(mass))},
         }

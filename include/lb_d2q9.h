@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define LB_ABI_VERSION 3
+#define LB_ABI_VERSION 4
 
 typedef struct lb_sim lb_sim; /* opaque */
 
@@ -206,6 +206,13 @@ int lb_set_mask_disk(lb_sim *sim, double cx, double cy, double r);
  * division for every float whose bit pattern lies in [first_bits, last_bits]; returns the count of
  * mismatches in *mismatches. */
 int lb_selftest_rcp(int device, uint32_t first_bits, uint32_t last_bits, uint64_t *mismatches);
+/* Practical HBM ceiling of the step's access pattern on THIS device, now: `reps` launches of an
+ * arithmetic-free kernel with the fused kernel's thread mapping (nine 128-bit loads with the D2Q9 row
+ * offsets, nine 128-bit stores) from the handle's current buffer into its scratch buffer, timed with
+ * CUDA events on the handle's stream; *ms_per_launch gets the average.  The populations are not
+ * modified (the scratch buffer is the other half of the ping-pong pair, rewritten by the next step).
+ * bench.py reports it beside the roofline; tools/stream_ceiling*.cu are the stand-alone versions. */
+int lb_selftest_copy(lb_sim *sim, int reps, double *ms_per_launch);
 /* sum over all populations and cells of this slab, accumulated in double (mass check) */
 int lb_total_mass(lb_sim *sim, double *out);
 /* order-independent exact checksum of the populations: the 64-bit wrap-around sum of the raw bit

@@ -979,3 +979,20 @@ def test_opencl_old_single_steps_match_oracle_and_run(gpu, orc):
         ref.run(15)
         sim.run(15)
         assert _same_bits(sim.download("f"), ref.f) and _same_bits(sim.download("u"), ref.u)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_copy_ceiling_diagnostic_leaves_the_state_untouched(gpu, orc, dtype):
+    """lb_selftest_copy (bench.py's `pattern_copy_ceiling`) times an arithmetic-free kernel on the handle's
+    own buffers: the populations, and the run that follows, must be unaffected."""
+    from lb_b200 import Lattice
+    f0, m = pipe_case(orc, 300, 70, dtype, mask="blocks", seed=2)
+    ref, _ = _run_both(orc, Lattice, f0, m, 12, dtype, "strict")
+    with Lattice(300, 70, 1.3, 1.01, 1.0, mask=m, f0=f0, dtype=dtype, math="strict") as sim:
+        sim.run(5)
+        before = sim.download("f")
+        ms = sim.copy_ceiling_ms(3)
+        assert ms > 0
+        assert np.array_equal(sim.download("f"), before)
+        sim.run(7)
+        assert np.array_equal(sim.download("f"), ref.f)
