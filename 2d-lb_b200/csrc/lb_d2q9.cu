@@ -7,6 +7,7 @@
 #include "lb_cython.cuh"
 #include "lb_oldcl.cuh"
 #include "lb_tma.cuh"
+#include "lb_tb2.cuh"
 
 #include <cstdio>
 #include <cstring>
@@ -47,6 +48,7 @@ struct lb_sim {
     int uv_elem = 4;              // bytes per u / v value (8 for the cython schemes: float64 like the reference)
     bool prestream_done = false;  // cython / opencl_old schemes: is the next step's BC + swap already applied to `cur`
     float *frozen = nullptr;      // opencl_old: the populations `move` never writes (lb_oldcl.cuh)
+    int tb2_shape = 0;            // temporal blocking: 0 = off, else index into g_tb2_shapes (lb_tb2.cuh)
     int pitch = 0;                // row pitch in elements (multiple of 512 B)
     long long plane = 0;          // elements per plane
     size_t buf_bytes = 0;         // bytes of one guarded 9-plane buffer
@@ -593,10 +595,90 @@ static int launch_step(lb_sim *sim, int src_idx, int write_moments, uint32_t sta
     return LB_OK;
 }
 
+// ---- temporal blocking (lb_tb2.cuh): two steps per launch ------------------------------------------
+struct Tb2Shape {
+    const char *name;
+    int bx, by, nt;
+    void (*launch[2][2])(const Tb2Params &, dim3, size_t, cudaStream_t);   // [dtype][math]
+};
+
+template <typename T, int MATH, int BX, int BY, int NT, int MINB>
+static void launch_tb2(const Tb2Params &p, dim3 grid, size_t smem, cudaStream_t st)
+{
+    static bool configured = false;                   // one opt-in per instantiation (dynamic smem > 48 KB)
+    if (!configured) {
+        cudaFuncSetAttribute(fused_two_step_kernel<T, MATH, BX, BY, NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = true;
+    }
+    fused_two_step_kernel<T, MATH, BX, BY, NT, MINB><<<grid, NT, smem, st>>>(p);
+}
+#define TB2(BX, BY, NT, MINB)                                                                          \
+    {#BX "x" #BY ".t" #NT, BX, BY, NT,                                                                     \
+     {{launch_tb2<float, MATH_STRICT, BX, BY, NT, MINB>, launch_tb2<float, MATH_FAST, BX, BY, NT, MINB>},  \
+      {launch_tb2<double, MATH_STRICT, BX, BY, NT, MINB>, launch_tb2<double, MATH_FAST, BX, BY, NT, MINB>}}}
+static const Tb2Shape g_tb2_shapes[] = {
+    {"off", 0, 0, 0, {{nullptr, nullptr}, {nullptr, nullptr}}},
+    TB2(128, 16, 256, 2),
+    TB2(64, 32, 256, 2),
+    TB2(128, 8, 256, 4),
+    TB2(256, 8, 256, 2),
+    TB2(128, 32, 512, 1),
+    TB2(64, 16, 256, 3),
+    TB2(64, 8, 128, 6),
+};
+static const int g_ntb2 = (int)(sizeof(g_tb2_shapes) / sizeof(g_tb2_shapes[0]));
+
+static size_t tb2_smem_bytes(const lb_sim *sim, int shape)
+{
+    const Tb2Shape &t = g_tb2_shapes[shape];
+    return (size_t)9 * (t.bx + 2) * (t.by + 2) * sim->elem;
+}
+
+static bool tb2_eligible(const lb_sim *sim)
+{
+    return sim->tb2_shape > 0 && sim->cfg.scheme == LB_SCHEME_OPENCL && sim->cfg.model == LB_MODEL_D2Q9 && !uses_halo(sim) &&
+           sim->cfg.global_nx == sim->cfg.nx;
+}
+
+// two moment-free steps: reads buffer src_idx, writes the other one
+static int launch_two_steps(lb_sim *sim, int src_idx)
+{
+    const Tb2Shape &t = g_tb2_shapes[sim->tb2_shape];
+    Tb2Params p{};
+    p.src = sim->buf[src_idx]; p.dst = sim->buf[src_idx ^ 1];
+    p.plane = sim->plane; p.nx = sim->cfg.nx; p.ny = sim->cfg.ny; p.pitch = sim->pitch;
+    p.bc = sim->cfg.bc == LB_BC_PERIODIC ? BC_PERIODIC : BC_PIPE;
+    p.zero_obstacle_velocity = sim->cfg.zero_obstacle_velocity;
+    p.mask = sim->mask; p.mask_pitch = sim->mask_pitch;
+    p.cf = consts_of<float>(sim); p.cd = consts_of<double>(sim);
+    const dim3 grid((sim->cfg.nx + t.bx - 1) / t.bx, (sim->cfg.ny + t.by - 1) / t.by);
+    t.launch[sim->cfg.dtype == LB_F64][sim->cfg.math == LB_MATH_FAST](p, grid, tb2_smem_bytes(sim, sim->tb2_shape), sim->stream);
+    CU(cudaGetLastError());
+    sim->launches++;
+    return LB_OK;
+}
+
 // =====================================================================================
 // C ABI
 // =====================================================================================
 extern "C" {
+
+int lb_tb2_shape_count(void) { return g_ntb2; }
+const char *lb_tb2_shape_name(int shape) { return (shape >= 0 && shape < g_ntb2) ? g_tb2_shapes[shape].name : nullptr; }
+
+int lb_set_temporal_blocking(lb_sim *sim, int shape)
+{
+    if (!sim) return LB_ERR_INVALID;
+    if (shape < 0 || shape >= g_ntb2) return fail(sim, LB_ERR_INVALID, "lb_set_temporal_blocking: unknown tile shape");
+    if (shape > 0) {
+        if (sim->cfg.scheme != LB_SCHEME_OPENCL || sim->cfg.model != LB_MODEL_D2Q9 || uses_halo(sim) || sim->cfg.global_nx != sim->cfg.nx)
+            return fail(sim, LB_ERR_INVALID, "lb_set_temporal_blocking: serves single-slab LB_SCHEME_OPENCL / LB_MODEL_D2Q9 lattices");
+        if (sim->cfg.ny > 65535 * g_tb2_shapes[shape].by) return fail(sim, LB_ERR_INVALID, "lb_set_temporal_blocking: lattice too tall for this tile");
+        if (tb2_smem_bytes(sim, shape) > 227 * 1024) return fail(sim, LB_ERR_INVALID, "lb_set_temporal_blocking: tile does not fit shared memory for this dtype");
+    }
+    sim->tb2_shape = shape;
+    return LB_OK;
+}
 
 int lb_abi_version(void) { return LB_ABI_VERSION; }
 
@@ -1008,6 +1090,13 @@ int lb_step(lb_sim *sim, int n_steps)
     if (is_oldcl(sim)) return oldcl_steps(sim, n_steps);
     if (sim->cfg.scheme != LB_SCHEME_OPENCL) return cython_steps(sim, n_steps);
     int remaining = n_steps - 1;            // all but the last step skip the moment stores
+    if (tb2_eligible(sim)) {                // temporal blocking: moment-free steps two at a time
+        for (; remaining >= 2; remaining -= 2) {
+            int rc = launch_two_steps(sim, sim->cur);
+            if (rc) return rc;
+            sim->cur ^= 1; sim->state_index += 2;
+        }
+    }
     const bool graphs_ok = !uses_halo(sim); // halo launches carry a per-step flag value
     while (graphs_ok && remaining >= GRAPH_LEN) {
         int rc = ensure_graph(sim);

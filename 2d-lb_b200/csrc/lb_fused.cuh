@@ -400,7 +400,7 @@ __global__ void __launch_bounds__(32 * WX * WY, MINB) fused_step_kernel(const St
     const T *__restrict__ src = static_cast<const T *>(p.src);
     T *__restrict__ dst = static_cast<T *>(p.dst);
     const long long plane = p.plane;
-    const int nx = p.nx, ny = p.ny, pitch = p.pitch;
+    const int ny = p.ny, pitch = p.pitch;
     const Consts<T> &c = consts_in<T>(p);
     const bool periodic = (p.bc == BC_PERIODIC);
 

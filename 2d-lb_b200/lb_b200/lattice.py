@@ -227,6 +227,14 @@ class Lattice:
         self._call("lb_total_mass", ct.byref(out))
         return out.value
 
+    def set_temporal_blocking(self, shape):
+        """Two lattice updates per pass through HBM (csrc/lb_tb2.cuh): `shape` is 0 (off), a tile index or a
+        tile name such as '128x16.t256'.  Bit-identical results; single-slab 'opencl' scheme only."""
+        if isinstance(shape, str):
+            names = [N.lib().lb_tb2_shape_name(k).decode() for k in range(N.lib().lb_tb2_shape_count())]
+            shape = names.index(shape)
+        self._call("lb_set_temporal_blocking", int(shape))
+
     def copy_ceiling_ms(self, reps=10):
         """ms per launch of an arithmetic-free kernel with the fused step's memory access pattern (the
         practical HBM ceiling of this device for this lattice; populations are left untouched)."""

@@ -201,6 +201,16 @@ int lb_init_synthetic(lb_sim *sim, int kind, double u0, double amplitude, uint64
 /* solid disk in GLOBAL coordinates (centre cx,cy, radius r): mask = (gx-cx)^2+(y-cy)^2 < r^2 */
 int lb_set_mask_disk(lb_sim *sim, double cx, double cy, double r);
 
+/* -- temporal blocking: TWO lattice updates per pass through HBM (csrc/lb_tb2.cuh).  With a tile shape
+ *    selected, lb_step runs the moment-free steps of a run two at a time -- the intermediate time level
+ *    stays in shared memory -- and the one-step kernel only for an odd step and for the last one.  Results
+ *    are bit-identical to the one-step path in both math modes.  shape 0 = off (default); shapes
+ *    1 .. lb_tb2_shape_count()-1 are tile geometries "BXxBY.tNT" (lb_tb2_shape_name).  Serves single-slab
+ *    LB_SCHEME_OPENCL / LB_MODEL_D2Q9 lattices (pipe or periodic); other handles return LB_ERR_INVALID. */
+int lb_set_temporal_blocking(lb_sim *sim, int shape);
+int lb_tb2_shape_count(void);
+const char *lb_tb2_shape_name(int shape);
+
 /* -- diagnostics */
 /* Device self-test of the branch-free reciprocal used by STRICT fp32 math: compares it with IEEE
  * division for every float whose bit pattern lies in [first_bits, last_bits]; returns the count of

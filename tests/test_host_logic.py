@@ -183,3 +183,57 @@ def test_class_parameter_algebra_equals_the_reference_opencl_classes(name):
     assert float(s.outlet_rho) == float(g["outlet_rho"])
     if "mask" in g.files:
         assert np.array_equal(s.obstacle_mask_host, g["mask"])
+
+
+def _tb2_host():
+    """tools/libtb2_host.so: the two phases of the temporally blocked kernel compiled for the host."""
+    import ctypes as ct
+    import shutil
+    import subprocess
+    so = os.path.join(ROOT, "tools", "libtb2_host.so")
+    src = os.path.join(ROOT, "tools", "tb2_host.cu")
+    deps = [src] + [os.path.join(ROOT, "2d-lb_b200", "csrc", n) for n in ("lb_tb2.cuh", "lb_device.cuh")]
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        if not shutil.which("nvcc"):
+            pytest.skip("nvcc not available to build the host replay")
+        subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-std=c++17", "--shared",
+                        "-Xcompiler", "-fPIC", "-o", so, src], check=True, capture_output=True)
+    return ct.CDLL(so)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_temporal_blocking_tile_logic_on_cpu(dtype):
+    """csrc/lb_tb2.cuh's phases are host-callable: every CTA is replayed on the CPU (shared memory
+    poisoned with NaN first) and the result must equal TWO steps of the oracle bit for bit -- pipe flow
+    with obstacles on every edge, periodic boxes down to 2 x 2, five tile shapes, odd thread counts."""
+    import ctypes as ct
+    from oracle import oracle as orc
+    from util import periodic_case, pipe_case
+    orc.build()
+    L = _tb2_host()
+
+    def replay(f0, mask, bc, shape, nthreads, omega, zero_vel=0):
+        _, ny, nx = f0.shape
+        out = np.full_like(f0, np.nan)
+        m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+        rc = L.tb2_host_run(nx, ny, bc, int(dtype == np.float64), f0.ctypes.data_as(ct.c_void_p),
+                            out.ctypes.data_as(ct.c_void_p), None if m is None else m.ctypes.data_as(ct.c_void_p),
+                            ct.c_double(omega), ct.c_double(1.01), ct.c_double(1.0), ct.c_double(orc.cs2),
+                            ct.c_double(orc.cs22), ct.c_double(orc.two_cs4), zero_vel, shape, nthreads)
+        assert rc == 0
+        return out
+
+    for (nx, ny) in ((97, 41), (256, 34), (5, 4), (2, 2), (129, 17)):
+        for maskk in ("none", "touching"):
+            f0, m = pipe_case(orc, nx, ny, dtype, mask=maskk if nx > 8 else "none", seed=nx)
+            for zv in ((0, 1) if m is not None else (0,)):
+                ref = orc.OpenCLSchemeOracle(f0, 1.3, 1.01, 1.0, mask=m, dtype=dtype, zero_obstacle_velocity=bool(zv))
+                ref.run(2)
+                for shape, nt in ((0, 256), (1, 64), (2, 33), (3, 7), (4, 1)):
+                    assert np.array_equal(replay(f0, m, 0, shape, nt, 1.3, zv), ref.f), (nx, ny, maskk, zv, shape)
+    for (nx, ny) in ((96, 40), (130, 67), (7, 5), (3, 3), (2, 2)):
+        f0 = periodic_case(orc, nx, ny, dtype, amplitude=1e-3, seed=ny)
+        ref = orc.OpenCLSchemeOracle(f0, 1.7, bc=orc.BC_PERIODIC, dtype=dtype)
+        ref.run(2)
+        for shape, nt in ((0, 256), (1, 64), (3, 5), (4, 2)):
+            assert np.array_equal(replay(f0, None, 1, shape, nt, 1.7), ref.f), (nx, ny, shape)

@@ -996,3 +996,72 @@ def test_copy_ceiling_diagnostic_leaves_the_state_untouched(gpu, orc, dtype):
         assert np.array_equal(sim.download("f"), before)
         sim.run(7)
         assert np.array_equal(sim.download("f"), ref.f)
+
+
+# ------------------------------------------------------------------------------------------------
+# temporal blocking: two lattice updates per pass through HBM (csrc/lb_tb2.cuh)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("math", ["strict", "fast"])
+def test_temporal_blocking_is_bit_identical(gpu, orc, dtype, math):
+    """Every tile shape, pipe (obstacles on every edge, velocity zeroing on and off) and periodic boxes,
+    widths that are not a multiple of anything, odd and even step counts, several run() calls: the same
+    bits as the one-step kernel -- and, in STRICT math, as the oracle."""
+    from lb_b200 import Lattice, native
+    L = native.lib()
+    shapes = [L.lb_tb2_shape_name(k).decode() for k in range(1, L.lb_tb2_shape_count())]
+    assert len(shapes) >= 4
+    cases = []
+    for (nx, ny) in ((301, 77), (130, 35), (5, 4), (2, 2), (512, 64)):
+        f0, m = pipe_case(orc, nx, ny, dtype, mask="touching" if nx > 8 else "none", seed=nx)
+        cases.append(("pipe", f0, m, False))
+        if m is not None:
+            cases.append(("pipe", f0, m, True))
+    for (nx, ny) in ((96, 40), (131, 67), (3, 3)):
+        cases.append(("periodic", periodic_case(orc, nx, ny, dtype, amplitude=1e-3, seed=ny), None, False))
+    f0, m = pipe_case(orc, 700, 41, dtype, mask="bulky", seed=11)
+    cases.append(("pipe", f0, m, True))
+    for bc, f0, m, zv in cases:
+        _, ny, nx = f0.shape
+        kw = dict(mask=m, f0=f0, bc=bc, dtype=dtype, math=math, zero_obstacle_velocity=zv)
+        with Lattice(nx, ny, 1.4, 1.01, 1.0, **kw) as plain:
+            want = {}
+            done = 0
+            for n in (1, 2, 5, 8):
+                plain.run(n)
+                done += n
+                want[done] = plain.fields()
+        if math == "strict":
+            ref = orc.OpenCLSchemeOracle(f0, 1.4, 1.01, 1.0, mask=m, bc=orc.BC_PERIODIC if bc == "periodic" else orc.BC_PIPE,
+                                         dtype=dtype, zero_obstacle_velocity=zv)
+            ref.run(16)
+            assert np.array_equal(want[16]["f"], ref.f)
+        for shape in shapes:
+            with Lattice(nx, ny, 1.4, 1.01, 1.0, **kw) as sim:
+                try:
+                    sim.set_temporal_blocking(shape)
+                except native.LBError:
+                    assert dtype == np.float64          # only the largest tiles, only in double
+                    continue
+                done = 0
+                for n in (1, 2, 5, 8):
+                    sim.run(n)
+                    done += n
+                    got = sim.fields()
+                    for k in ("f", "rho", "u", "v"):
+                        assert np.array_equal(got[k], want[done][k]), (bc, nx, ny, zv, shape, done, k)
+
+
+def test_temporal_blocking_refuses_what_it_does_not_serve(gpu):
+    from lb_b200 import Lattice, native
+    with Lattice(64, 32, 1.0, scheme="cython") as sim:
+        with pytest.raises(native.LBError):
+            sim.set_temporal_blocking(1)
+    with Lattice(64, 32, 1.0, 1.01, 1.0, model="d2q9i") as sim:
+        with pytest.raises(native.LBError):
+            sim.set_temporal_blocking(1)
+    with Lattice(64, 32, 1.0) as sim:
+        with pytest.raises(native.LBError):
+            sim.set_temporal_blocking(99)
+        sim.set_temporal_blocking(1)
+        sim.set_temporal_blocking(0)

@@ -1,0 +1,59 @@
+#!/usr/bin/env python
+"""Throughput of the temporally blocked kernel (csrc/lb_tb2.cuh) per tile shape, against the one-step kernel.
+
+    python tools/tb2_sweep.py [--nx 16384 --ny 16384 --dtype f32 --math strict --steps 41 --bc pipe]
+"""
+import argparse
+import os
+import sys
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "2d-lb_b200"))
+import numpy as np
+import torch
+from lb_b200 import Lattice, native
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--nx", type=int, default=16384)
+    ap.add_argument("--ny", type=int, default=16384)
+    ap.add_argument("--dtype", default="f32")
+    ap.add_argument("--math", default="strict")
+    ap.add_argument("--bc", default="pipe")
+    ap.add_argument("--steps", type=int, default=41)
+    ap.add_argument("--no-mask", action="store_true")
+    a = ap.parse_args()
+    dtype = np.float32 if a.dtype == "f32" else np.float64
+    elem = 4 if a.dtype == "f32" else 8
+    L = native.lib()
+    names = [L.lb_tb2_shape_name(k).decode() for k in range(L.lb_tb2_shape_count())]
+    s = torch.cuda.Stream()
+    sim = Lattice(a.nx, a.ny, 1.7, 1.003, 1.0, bc=a.bc, dtype=dtype, math=a.math, stream=s.cuda_stream)
+    if a.bc == "pipe" and not a.no_mask:
+        sim.set_mask_disk(a.nx / 4.0, a.ny / 2.0, a.ny / 10.0)
+    sim.init_synthetic("pipe_ramp" if a.bc == "pipe" else "shear_layers", u0=0.05, amplitude=1e-3, seed=2015)
+    print(f"# {a.nx}x{a.ny} {a.dtype} {a.math} {a.bc}, {a.steps} steps per run (temporal blocking covers all but the last)")
+    base = None
+    for k, name in enumerate(names):
+        try:
+            sim.set_temporal_blocking(k)
+        except native.LBError as exc:
+            print(f"{name:14s} not available: {exc}")
+            continue
+        sim.run(a.steps)
+        best = 1e30
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(s):
+                e0.record(); sim.run(a.steps, sync=False); e1.record()
+            sim.sync()
+            best = min(best, e0.elapsed_time(e1) / a.steps)
+        mlups = a.nx * a.ny / best / 1e3
+        base = base or mlups
+        print(f"{name:14s} {best:8.4f} ms/step {mlups:9.0f} MLUPS  x{mlups / base:5.3f}  "
+              f"({mlups * 1e6 * 18 * elem / 1e9:7.0f} GB/s-equivalent at {18 * elem} B/LU)   mass {sim.total_mass():.6f}", flush=True)
+    sim.close()
+
+
+if __name__ == "__main__":
+    main()
