@@ -124,7 +124,7 @@ static void launch_variant(const StepParams &p_in, cudaStream_t st)
     StepParams p = p_in;
     constexpr int SPAN = 32 * V;
     p.tiles_x = (p.pitch + SPAN * WX - 1) / (SPAN * WX);
-    p.tiles_y = (p.ny + WY * R - 1) / (WY * R);
+    p.tiles_y = (p.y_end - p.y_begin + WY * R - 1) / (WY * R);
     dim3 grid;
     if (p.edge_first) {
         p.edge_rows = 16;
@@ -523,6 +523,7 @@ static void fill_params(lb_sim *s, StepParams &p, int src_idx, int write_moments
     p.rho = s->rho; p.u = s->u; p.v = s->v;
     p.cf = consts_of<float>(s);
     p.cd = consts_of<double>(s);
+    p.y_begin = 0; p.y_end = s->cfg.ny;
     if (uses_halo(s)) {
         const int rp = state_index & 1, wp = (state_index + 1) & 1;
         const HaloLayout &h = s->hl;
@@ -1110,6 +1111,53 @@ int lb_step(lb_sim *sim, int n_steps)
         int rc = launch_step(sim, sim->cur, 0, sim->state_index);
         if (rc) return rc;
         sim->cur ^= 1; sim->state_index++;
+    }
+    int rc = launch_step(sim, sim->cur, 1, sim->state_index);
+    if (rc) return rc;
+    sim->cur ^= 1; sim->state_index++;
+    return LB_OK;
+}
+
+// ---- L2-level temporal blocking (experimental) ---------------------------------
+// `depth` consecutive steps travel down the lattice together: step s works on row band b - s, each band
+// shifted up by s rows, so stream order alone satisfies "row y of step s+1 needs rows y-1..y+1 of step s" and
+// "step s+1 may overwrite a row of the buffer step s reads only after step s is done with it".  What step s
+// wrote is read by step s+1 a band later, while it is still in L2, and the intermediate time levels are
+// overwritten in L2 (the ping-pong buffers alias them) before they are ever written back.
+int lb_step_banded(lb_sim *sim, int n_steps, int band_rows, int depth)
+{
+    if (!sim) return LB_ERR_INVALID;
+    if (n_steps < 0 || band_rows < 1 || depth < 1) return fail(sim, LB_ERR_INVALID, "lb_step_banded: bad argument");
+    if (sim->cfg.scheme != LB_SCHEME_OPENCL || uses_halo(sim) || sim->cfg.bc == LB_BC_PERIODIC || g_variants[sim->variant].launch_tma)
+        return fail(sim, LB_ERR_INVALID, "lb_step_banded: serves single-slab, non-periodic LB_SCHEME_OPENCL lattices (register-shuffle kernel)");
+    if (n_steps == 0) return LB_OK;
+    CU(cudaSetDevice(sim->cfg.device));
+    const int ny = sim->cfg.ny;
+    int remaining = n_steps - 1;                       // the last step stores the moments: whole-lattice launch
+    const Variant &var = g_variants[sim->variant];
+    while (remaining > 0) {
+        const int k = remaining < depth ? remaining : depth;
+        const int nb = (ny + k + band_rows - 1) / band_rows;          // bands of the most shifted step reach row ny
+        for (int b = 0; b < nb + k - 1; ++b) {
+            for (int s = 0; s < k; ++s) {
+                const int band = b - s;
+                if (band < 0 || band >= nb) continue;
+                int y0 = band * band_rows - s, y1 = y0 + band_rows;
+                if (y0 < 0) y0 = 0;
+                if (y1 > ny) y1 = ny;
+                if (band == nb - 1) y1 = ny;
+                if (y0 >= y1) continue;
+                StepParams p;
+                fill_params(sim, p, sim->cur ^ (s & 1), 0, sim->state_index + s);
+                p.y_begin = y0; p.y_end = y1;
+                var.launch(p, sim->stream);
+                sim->launches++;
+            }
+        }
+        CU(cudaGetLastError());
+        sim->cur ^= (k & 1);
+        sim->state_index += k;
+        remaining -= k;
     }
     int rc = launch_step(sim, sim->cur, 1, sim->state_index);
     if (rc) return rc;

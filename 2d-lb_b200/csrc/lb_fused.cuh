@@ -53,6 +53,7 @@ struct StepParams {
     int edge_first;           // 1-D grid with the two edge tile columns first (halo overlap); else 2-D/3-D grid
     int edge_rows;            // rows per warp in an edge tile (tall tiles: few participants in the hand-shake)
     int edge_tiles_y;         // edge tiles per side
+    int y_begin, y_end;       // rows this launch updates (whole lattice: 0, ny); band launches of lb_step_banded
 };
 
 template <typename T> __device__ __forceinline__ const Consts<T> &consts_in(const StepParams &p);
@@ -394,7 +395,7 @@ __global__ void __launch_bounds__(32 * WX * WY, MINB) fused_step_kernel(const St
 
     const int span0 = (bx * WX + wx) * SPAN;          // first cell of this warp's span
     const int x0 = span0 + lane * V;                  // first cell of this thread
-    const int ybase = (by * WY + wy) * rows;
+    const int ybase = p.y_begin + (by * WY + wy) * rows;
     const bool warp_active = span0 < p.pitch;         // warp-uniform (pitch is a multiple of SPAN)
 
     const T *__restrict__ src = static_cast<const T *>(p.src);
@@ -407,7 +408,7 @@ __global__ void __launch_bounds__(32 * WX * WY, MINB) fused_step_kernel(const St
     if (warp_active) {
         for (int r = 0; r < rows; ++r) {
             const int y = ybase + r;
-            if (y >= ny) break;                       // warp-uniform (also guards by >= tiles_y)
+            if (y >= p.y_end) break;                  // warp-uniform (also guards by >= tiles_y)
             int ym = y - 1, yp = y + 1;               // source rows of the cy=+1 / cy=-1 populations
             if (periodic) { if (ym < 0) ym = ny - 1; if (yp >= ny) yp = 0; }
             const long long rc = (long long)y * pitch + x0;

@@ -227,6 +227,13 @@ class Lattice:
         self._call("lb_total_mass", ct.byref(out))
         return out.value
 
+    def run_banded(self, n, band_rows, depth, sync=True):
+        """run(n) with the steps issued `depth` at a time as skewed row-band launches (L2-level temporal
+        blocking, experimental).  Same bits as run(n)."""
+        self._call("lb_step_banded", int(n), int(band_rows), int(depth))
+        if sync:
+            self.sync()
+
     def set_temporal_blocking(self, shape):
         """Two lattice updates per pass through HBM (csrc/lb_tb2.cuh): `shape` is 0 (off), a tile index or a
         tile name such as '128x16.t256'.  Bit-identical results; single-slab 'opencl' scheme only."""

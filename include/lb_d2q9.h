@@ -211,6 +211,12 @@ int lb_set_temporal_blocking(lb_sim *sim, int shape);
 int lb_tb2_shape_count(void);
 const char *lb_tb2_shape_name(int shape);
 
+/* -- L2-level temporal blocking, EXPERIMENTAL: the same result as lb_step(n_steps), with
+ *    the moment-free steps issued `depth` at a time as row-band launches of `band_rows` rows in a skewed
+ *    order, so that each step reads what the previous one wrote while it is still in the 126 MB L2.
+ *    Single-slab, non-periodic LB_SCHEME_OPENCL lattices. */
+int lb_step_banded(lb_sim *sim, int n_steps, int band_rows, int depth);
+
 /* -- diagnostics */
 /* Device self-test of the branch-free reciprocal used by STRICT fp32 math: compares it with IEEE
  * division for every float whose bit pattern lies in [first_bits, last_bits]; returns the count of
