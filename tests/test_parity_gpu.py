@@ -1065,3 +1065,22 @@ def test_temporal_blocking_refuses_what_it_does_not_serve(gpu):
             sim.set_temporal_blocking(99)
         sim.set_temporal_blocking(1)
         sim.set_temporal_blocking(0)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_banded_schedule_is_bit_identical(gpu, orc, dtype):
+    """lb_step_banded (skewed row-band launches, L2-level temporal blocking): any band height and depth
+    gives the bits of lb_step."""
+    from lb_b200 import Lattice
+    for (nx, ny, mask) in ((301, 77, "touching"), (130, 35, "none"), (700, 41, "bulky"), (64, 3, "none")):
+        f0, m = pipe_case(orc, nx, ny, dtype, mask=mask, seed=nx)
+        with Lattice(nx, ny, 1.4, 1.01, 1.0, mask=m, f0=f0, dtype=dtype, math="strict", zero_obstacle_velocity=True) as plain:
+            plain.run(13)
+            want = plain.fields()
+        for band_rows, depth in ((1, 1), (1, 5), (2, 3), (7, 2), (16, 4), (64, 12), (5, 20)):
+            with Lattice(nx, ny, 1.4, 1.01, 1.0, mask=m, f0=f0, dtype=dtype, math="strict", zero_obstacle_velocity=True) as sim:
+                sim.run_banded(6, band_rows, depth)
+                sim.run_banded(7, band_rows, depth)
+                got = sim.fields()
+                for k in ("f", "rho", "u", "v"):
+                    assert np.array_equal(got[k], want[k]), (nx, ny, band_rows, depth, k)
