@@ -8,6 +8,7 @@
 #include "lb_oldcl.cuh"
 #include "lb_tma.cuh"
 #include "lb_tb2.cuh"
+#include "lb_tb2v.cuh"
 
 #include <cstdio>
 #include <cstring>
@@ -599,8 +600,9 @@ static int launch_step(lb_sim *sim, int src_idx, int write_moments, uint32_t sta
 // ---- temporal blocking (lb_tb2.cuh): two steps per launch ------------------------------------------
 struct Tb2Shape {
     const char *name;
-    int bx, by, nt;
-    void (*launch[2][2])(const Tb2Params &, dim3, size_t, cudaStream_t);   // [dtype][math]
+    int bx, by, nt;            // bx == 0: the row-per-warp version (lb_tb2v.cuh), tile width = 32*V
+    void (*launch[2][2])(const Tb2Params &, dim3, size_t, cudaStream_t);    // [dtype][math], lb_tb2.cuh
+    void (*launch_v[2][2])(const StepParams &, dim3, size_t, cudaStream_t); // [dtype][math], lb_tb2v.cuh
 };
 
 template <typename T, int MATH, int BX, int BY, int NT, int MINB>
@@ -613,12 +615,27 @@ static void launch_tb2(const Tb2Params &p, dim3 grid, size_t smem, cudaStream_t 
     }
     fused_two_step_kernel<T, MATH, BX, BY, NT, MINB><<<grid, NT, smem, st>>>(p);
 }
+template <typename T, int V, int MATH, int BY, int NW, int MINB>
+static void launch_tb2v(const StepParams &p, dim3 grid, size_t smem, cudaStream_t st)
+{
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(fused_two_step_v2_kernel<T, V, MATH, BY, NW, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = true;
+    }
+    fused_two_step_v2_kernel<T, V, MATH, BY, NW, MINB><<<grid, 32 * NW, smem, st>>>(p);
+}
 #define TB2(BX, BY, NT, MINB)                                                                          \
     {#BX "x" #BY ".t" #NT, BX, BY, NT,                                                                     \
      {{launch_tb2<float, MATH_STRICT, BX, BY, NT, MINB>, launch_tb2<float, MATH_FAST, BX, BY, NT, MINB>},  \
-      {launch_tb2<double, MATH_STRICT, BX, BY, NT, MINB>, launch_tb2<double, MATH_FAST, BX, BY, NT, MINB>}}}
+      {launch_tb2<double, MATH_STRICT, BX, BY, NT, MINB>, launch_tb2<double, MATH_FAST, BX, BY, NT, MINB>}}, \
+     {{nullptr, nullptr}, {nullptr, nullptr}}}
+#define TB2V(BY, NW, MINB)                                                                             \
+    {"rows" #BY ".w" #NW, 0, BY, 32 * NW, {{nullptr, nullptr}, {nullptr, nullptr}},                         \
+     {{launch_tb2v<float, 4, MATH_STRICT, BY, NW, MINB>, launch_tb2v<float, 4, MATH_FAST, BY, NW, MINB>},  \
+      {launch_tb2v<double, 2, MATH_STRICT, BY, NW, MINB>, launch_tb2v<double, 2, MATH_FAST, BY, NW, MINB>}}}
 static const Tb2Shape g_tb2_shapes[] = {
-    {"off", 0, 0, 0, {{nullptr, nullptr}, {nullptr, nullptr}}},
+    {"off", 0, 0, 0, {{nullptr, nullptr}, {nullptr, nullptr}}, {{nullptr, nullptr}, {nullptr, nullptr}}},
     TB2(128, 16, 256, 2),
     TB2(64, 32, 256, 2),
     TB2(128, 8, 256, 4),
@@ -626,12 +643,24 @@ static const Tb2Shape g_tb2_shapes[] = {
     TB2(128, 32, 512, 1),
     TB2(64, 16, 256, 3),
     TB2(64, 8, 128, 6),
+    TB2V(6, 8, 3),
+    TB2V(14, 8, 2),
+    TB2V(22, 8, 1),
+    TB2V(30, 8, 1),
+    TB2V(6, 4, 6),
+    TB2V(14, 4, 4),
 };
 static const int g_ntb2 = (int)(sizeof(g_tb2_shapes) / sizeof(g_tb2_shapes[0]));
+
+static inline bool tb2_is_rows(int shape) { return shape > 0 && g_tb2_shapes[shape].bx == 0; }
 
 static size_t tb2_smem_bytes(const lb_sim *sim, int shape)
 {
     const Tb2Shape &t = g_tb2_shapes[shape];
+    if (tb2_is_rows(shape)) {
+        const int off = 16 / sim->elem, span = sim->elem == 4 ? 128 : 64;
+        return (size_t)9 * (span + 2 * off) * (t.by + 2) * sim->elem;
+    }
     return (size_t)9 * (t.bx + 2) * (t.by + 2) * sim->elem;
 }
 
@@ -645,15 +674,25 @@ static bool tb2_eligible(const lb_sim *sim)
 static int launch_two_steps(lb_sim *sim, int src_idx)
 {
     const Tb2Shape &t = g_tb2_shapes[sim->tb2_shape];
-    Tb2Params p{};
-    p.src = sim->buf[src_idx]; p.dst = sim->buf[src_idx ^ 1];
-    p.plane = sim->plane; p.nx = sim->cfg.nx; p.ny = sim->cfg.ny; p.pitch = sim->pitch;
-    p.bc = sim->cfg.bc == LB_BC_PERIODIC ? BC_PERIODIC : BC_PIPE;
-    p.zero_obstacle_velocity = sim->cfg.zero_obstacle_velocity;
-    p.mask = sim->mask; p.mask_pitch = sim->mask_pitch;
-    p.cf = consts_of<float>(sim); p.cd = consts_of<double>(sim);
-    const dim3 grid((sim->cfg.nx + t.bx - 1) / t.bx, (sim->cfg.ny + t.by - 1) / t.by);
-    t.launch[sim->cfg.dtype == LB_F64][sim->cfg.math == LB_MATH_FAST](p, grid, tb2_smem_bytes(sim, sim->tb2_shape), sim->stream);
+    const size_t smem = tb2_smem_bytes(sim, sim->tb2_shape);
+    const int di = sim->cfg.dtype == LB_F64, mi = sim->cfg.math == LB_MATH_FAST;
+    if (tb2_is_rows(sim->tb2_shape)) {
+        StepParams p;
+        fill_params(sim, p, src_idx, 0, sim->state_index);
+        const int span = sim->elem == 4 ? 128 : 64;
+        const dim3 grid(sim->pitch / span, (sim->cfg.ny + t.by - 1) / t.by);
+        t.launch_v[di][mi](p, grid, smem, sim->stream);
+    } else {
+        Tb2Params p{};
+        p.src = sim->buf[src_idx]; p.dst = sim->buf[src_idx ^ 1];
+        p.plane = sim->plane; p.nx = sim->cfg.nx; p.ny = sim->cfg.ny; p.pitch = sim->pitch;
+        p.bc = sim->cfg.bc == LB_BC_PERIODIC ? BC_PERIODIC : BC_PIPE;
+        p.zero_obstacle_velocity = sim->cfg.zero_obstacle_velocity;
+        p.mask = sim->mask; p.mask_pitch = sim->mask_pitch;
+        p.cf = consts_of<float>(sim); p.cd = consts_of<double>(sim);
+        const dim3 grid((sim->cfg.nx + t.bx - 1) / t.bx, (sim->cfg.ny + t.by - 1) / t.by);
+        t.launch[di][mi](p, grid, smem, sim->stream);
+    }
     CU(cudaGetLastError());
     sim->launches++;
     return LB_OK;
@@ -676,6 +715,8 @@ int lb_set_temporal_blocking(lb_sim *sim, int shape)
             return fail(sim, LB_ERR_INVALID, "lb_set_temporal_blocking: serves single-slab LB_SCHEME_OPENCL / LB_MODEL_D2Q9 lattices");
         if (sim->cfg.ny > 65535 * g_tb2_shapes[shape].by) return fail(sim, LB_ERR_INVALID, "lb_set_temporal_blocking: lattice too tall for this tile");
         if (tb2_smem_bytes(sim, shape) > 227 * 1024) return fail(sim, LB_ERR_INVALID, "lb_set_temporal_blocking: tile does not fit shared memory for this dtype");
+        if (tb2_is_rows(shape) && sim->cfg.bc == LB_BC_PERIODIC && sim->cfg.nx % (sim->elem == 4 ? 128 : 64))
+            return fail(sim, LB_ERR_INVALID, "lb_set_temporal_blocking: the row-per-warp tiles need nx to be a multiple of the tile width on a periodic box");
     }
     sim->tb2_shape = shape;
     return LB_OK;

@@ -161,7 +161,12 @@ __device__ __forceinline__ void wait_flag(const unsigned int *flag, unsigned int
 // ---- everything after the nine shifted populations of a thread's V nodes are in registers:
 //      slab-edge fix-ups, boundary closure, obstacles, collision, stores, halo publication.
 //      Shared by the register-shuffle kernel below and the TMA kernel (lb_tma.cuh).
-template <typename T, int V, int MATH, int STP, int MODEL>
+//      ROLE (temporal blocking, lb_tb2.cuh): ROW_FULL = everything; ROW_TO_REGISTERS = stop after the
+//      collision, the caller keeps q (phase 1 stores it to shared memory); ROW_FROM_TILE = the populations
+//      came from a shared-memory tile whose rim already holds the wrapped / ghost values, so the slab-edge
+//      fix-up from `src` is skipped (phase 2).
+enum : int { ROW_FULL = 0, ROW_TO_REGISTERS = 1, ROW_FROM_TILE = 2 };
+template <typename T, int V, int MATH, int STP, int MODEL, int ROLE = ROW_FULL>
 __device__ __forceinline__ void finish_row(const StepParams &p, const Consts<T> &c, Pack<T, V> (&q)[9],
                                            const T *__restrict__ src, T *__restrict__ dst,
                                            int x0, int span0, int y, int ym, int yp)
@@ -179,7 +184,7 @@ __device__ __forceinline__ void finish_row(const StepParams &p, const Consts<T> 
     //     fix-up (wrap, ghost column) and the boundary closure, behind ONE branch
     const bool row_is_wall = (!periodic) && (y == 0 || y == ny - 1);
     if (has_west || has_east || row_is_wall) {
-        if (has_west && p.west != EDGE_BOUNDARY) {
+        if (ROLE != ROW_FROM_TILE && has_west && p.west != EDGE_BOUNDARY) {
             T a1, a5, a8;
             if (p.west == EDGE_WRAP) {
                 a1 = src[1 * plane + (long long)y * pitch + (nx - 1)];
@@ -193,7 +198,7 @@ __device__ __forceinline__ void finish_row(const StepParams &p, const Consts<T> 
             }
             q[1].v[0] = a1; q[5].v[0] = a5; q[8].v[0] = a8;
         }
-        if (has_east && p.east != EDGE_BOUNDARY) {
+        if (ROLE != ROW_FROM_TILE && has_east && p.east != EDGE_BOUNDARY) {
             T a3, a6, a7;
             if (p.east == EDGE_WRAP) {
                 a3 = src[3 * plane + (long long)y * pitch];
@@ -311,6 +316,8 @@ __device__ __forceinline__ void finish_row(const StepParams &p, const Consts<T> 
             for (int j = 0; j < 9; ++j) q[j].v[e] = g[j];
         }
     }
+
+    if (ROLE == ROW_TO_REGISTERS) return;
 
     // --- stores: aligned vectors; the one thread straddling column nx-1 goes scalar ---
     if (x0 + V <= nx) {

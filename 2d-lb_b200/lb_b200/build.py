@@ -6,7 +6,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(os.path.dirname(PKG), "csrc")
 LIB = os.path.join(CSRC, "liblb_d2q9.so")
 SOURCES = ["lb_d2q9.cu"]
-HEADERS = ["lb_device.cuh", "lb_fused.cuh", "lb_cython.cuh", "lb_oldcl.cuh", "lb_tma.cuh", "lb_tb2.cuh", os.path.join("..", "..", "include", "lb_d2q9.h")]
+HEADERS = ["lb_device.cuh", "lb_fused.cuh", "lb_cython.cuh", "lb_oldcl.cuh", "lb_tma.cuh", "lb_tb2.cuh", "lb_tb2v.cuh", os.path.join("..", "..", "include", "lb_d2q9.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

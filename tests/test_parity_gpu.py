@@ -1017,7 +1017,7 @@ def test_temporal_blocking_is_bit_identical(gpu, orc, dtype, math):
         cases.append(("pipe", f0, m, False))
         if m is not None:
             cases.append(("pipe", f0, m, True))
-    for (nx, ny) in ((96, 40), (131, 67), (3, 3)):
+    for (nx, ny) in ((96, 40), (131, 67), (3, 3), (256, 37), (128, 5)):
         cases.append(("periodic", periodic_case(orc, nx, ny, dtype, amplitude=1e-3, seed=ny), None, False))
     f0, m = pipe_case(orc, 700, 41, dtype, mask="bulky", seed=11)
     cases.append(("pipe", f0, m, True))
@@ -1041,7 +1041,9 @@ def test_temporal_blocking_is_bit_identical(gpu, orc, dtype, math):
                 try:
                     sim.set_temporal_blocking(shape)
                 except native.LBError:
-                    assert dtype == np.float64          # only the largest tiles, only in double
+                    # the largest tiles do not fit shared memory in double; the row-per-warp tiles need a
+                    # periodic box whose width is a multiple of the tile width
+                    assert dtype == np.float64 or (shape.startswith("rows") and bc == "periodic" and nx % 128)
                     continue
                 done = 0
                 for n in (1, 2, 5, 8):
