@@ -49,7 +49,7 @@ struct lb_sim {
     int uv_elem = 4;              // bytes per u / v value (8 for the cython schemes: float64 like the reference)
     bool prestream_done = false;  // cython / opencl_old schemes: is the next step's BC + swap already applied to `cur`
     float *frozen = nullptr;      // opencl_old: the populations `move` never writes (lb_oldcl.cuh)
-    int tb2_shape = 0;            // temporal blocking: 0 = off, else index into g_tb2_shapes (lb_tb2.cuh)
+    int tb2_shape = -1;           // temporal blocking: -1 = automatic, 0 = off, else index into g_tb2_shapes
     int pitch = 0;                // row pitch in elements (multiple of 512 B)
     long long plane = 0;          // elements per plane
     size_t buf_bytes = 0;         // bytes of one guarded 9-plane buffer
@@ -597,7 +597,9 @@ static int launch_step(lb_sim *sim, int src_idx, int write_moments, uint32_t sta
     return LB_OK;
 }
 
-// ---- temporal blocking (lb_tb2.cuh): two steps per launch ------------------------------------------
+// ---- temporal blocking (lb_tb2.cuh, lb_tb2v.cuh): two steps per launch ---------------------------------
+#define LB_TB2_AUTO_F32 "rows14.w8"
+#define LB_TB2_AUTO_F64 "rows14.w8"
 struct Tb2Shape {
     const char *name;
     int bx, by, nt;            // bx == 0: the row-per-warp version (lb_tb2v.cuh), tile width = 32*V
@@ -664,19 +666,44 @@ static size_t tb2_smem_bytes(const lb_sim *sim, int shape)
     return (size_t)9 * (t.bx + 2) * (t.by + 2) * sim->elem;
 }
 
-static bool tb2_eligible(const lb_sim *sim)
+static bool tb2_servable(const lb_sim *sim)
 {
-    return sim->tb2_shape > 0 && sim->cfg.scheme == LB_SCHEME_OPENCL && sim->cfg.model == LB_MODEL_D2Q9 && !uses_halo(sim) &&
+    return sim->cfg.scheme == LB_SCHEME_OPENCL && sim->cfg.model == LB_MODEL_D2Q9 && !uses_halo(sim) &&
            sim->cfg.global_nx == sim->cfg.nx;
 }
 
-// two moment-free steps: reads buffer src_idx, writes the other one
-static int launch_two_steps(lb_sim *sim, int src_idx)
+static int tb2_find(const char *name)
 {
-    const Tb2Shape &t = g_tb2_shapes[sim->tb2_shape];
-    const size_t smem = tb2_smem_bytes(sim, sim->tb2_shape);
+    for (int k = 1; k < g_ntb2; ++k)
+        if (!strcmp(g_tb2_shapes[k].name, name)) return k;
+    return 0;
+}
+
+// The tile used when the caller did not choose (tb2_shape == -1): the measured best on B200
+// (profiles/README.md section 7) for lattices large enough to be HBM-bound; small lattices keep the
+// graph-batched one-step kernel.  0 = one-step kernel.
+static int tb2_auto_shape(const lb_sim *sim)
+{
+    if (!tb2_servable(sim) || g_variants[sim->variant].launch_tma) return 0;
+    if ((long long)sim->cfg.nx * sim->cfg.ny < (1ll << 22) || sim->cfg.ny < 64) return 0;
+    const int span = sim->elem == 4 ? 128 : 64;
+    if (sim->cfg.bc == LB_BC_PERIODIC && sim->cfg.nx % span) return 0;
+    return tb2_find(sim->elem == 4 ? LB_TB2_AUTO_F32 : LB_TB2_AUTO_F64);
+}
+
+static int tb2_effective_shape(const lb_sim *sim)
+{
+    if (sim->tb2_shape >= 0) return tb2_servable(sim) ? sim->tb2_shape : 0;
+    return tb2_auto_shape(sim);
+}
+
+// two moment-free steps: reads buffer src_idx, writes the other one
+static int launch_two_steps(lb_sim *sim, int src_idx, int shape)
+{
+    const Tb2Shape &t = g_tb2_shapes[shape];
+    const size_t smem = tb2_smem_bytes(sim, shape);
     const int di = sim->cfg.dtype == LB_F64, mi = sim->cfg.math == LB_MATH_FAST;
-    if (tb2_is_rows(sim->tb2_shape)) {
+    if (tb2_is_rows(shape)) {
         StepParams p;
         fill_params(sim, p, src_idx, 0, sim->state_index);
         const int span = sim->elem == 4 ? 128 : 64;
@@ -703,12 +730,14 @@ static int launch_two_steps(lb_sim *sim, int src_idx)
 // =====================================================================================
 extern "C" {
 
+int lb_temporal_blocking(const lb_sim *sim) { return sim ? tb2_effective_shape(sim) : 0; }
 int lb_tb2_shape_count(void) { return g_ntb2; }
 const char *lb_tb2_shape_name(int shape) { return (shape >= 0 && shape < g_ntb2) ? g_tb2_shapes[shape].name : nullptr; }
 
 int lb_set_temporal_blocking(lb_sim *sim, int shape)
 {
     if (!sim) return LB_ERR_INVALID;
+    if (shape == -1) { sim->tb2_shape = -1; return LB_OK; }
     if (shape < 0 || shape >= g_ntb2) return fail(sim, LB_ERR_INVALID, "lb_set_temporal_blocking: unknown tile shape");
     if (shape > 0) {
         if (sim->cfg.scheme != LB_SCHEME_OPENCL || sim->cfg.model != LB_MODEL_D2Q9 || uses_halo(sim) || sim->cfg.global_nx != sim->cfg.nx)
@@ -888,6 +917,7 @@ int lb_destroy(lb_sim *sim)
 int lb_set_variant(lb_sim *sim, int variant)
 {
     if (!sim) return LB_ERR_INVALID;
+    const bool back_to_default = variant < 0;
     if (variant < 0) variant = default_variant(sim->cfg.dtype, sim->cfg.math, sim->cfg.model);
     if (variant >= g_nvariants || g_variants[variant].dtype != sim->cfg.dtype || g_variants[variant].math != sim->cfg.math ||
         g_variants[variant].model != sim->cfg.model)
@@ -895,6 +925,8 @@ int lb_set_variant(lb_sim *sim, int variant)
     if (g_variants[variant].launch_tma && (uses_halo(sim) || sim->cfg.bc == LB_BC_PERIODIC || sim->cfg.scheme != LB_SCHEME_OPENCL))
         return fail(sim, LB_ERR_INVALID, "lb_set_variant: the TMA-staged kernel serves single-slab, non-periodic lattices");
     sim->variant = variant;
+    if (back_to_default) sim->tb2_shape = -1;
+    else if (sim->tb2_shape < 0) sim->tb2_shape = 0; // a hand-picked one-step variant is what runs
     drop_graphs(sim);
     return LB_OK;
 }
@@ -1132,9 +1164,9 @@ int lb_step(lb_sim *sim, int n_steps)
     if (is_oldcl(sim)) return oldcl_steps(sim, n_steps);
     if (sim->cfg.scheme != LB_SCHEME_OPENCL) return cython_steps(sim, n_steps);
     int remaining = n_steps - 1;            // all but the last step skip the moment stores
-    if (tb2_eligible(sim)) {                // temporal blocking: moment-free steps two at a time
+    if (const int tb2 = tb2_effective_shape(sim)) {   // temporal blocking: moment-free steps two at a time
         for (; remaining >= 2; remaining -= 2) {
-            int rc = launch_two_steps(sim, sim->cur);
+            int rc = launch_two_steps(sim, sim->cur, tb2);
             if (rc) return rc;
             sim->cur ^= 1; sim->state_index += 2;
         }

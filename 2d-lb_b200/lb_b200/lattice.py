@@ -235,12 +235,22 @@ class Lattice:
             self.sync()
 
     def set_temporal_blocking(self, shape):
-        """Two lattice updates per pass through HBM (csrc/lb_tb2.cuh): `shape` is 0 (off), a tile index or a
-        tile name such as '128x16.t256'.  Bit-identical results; single-slab 'opencl' scheme only."""
+        """Two lattice updates per pass through HBM (csrc/lb_tb2*.cuh): `shape` is 'auto' / -1 (default:
+        the measured-best tile on large lattices), 'off' / 0, a tile index or a tile name such as
+        'rows14.w8'.  Bit-identical results; single-slab 'opencl' scheme only."""
         if isinstance(shape, str):
-            names = [N.lib().lb_tb2_shape_name(k).decode() for k in range(N.lib().lb_tb2_shape_count())]
-            shape = names.index(shape)
+            if shape == "auto":
+                shape = -1
+            else:
+                names = [N.lib().lb_tb2_shape_name(k).decode() for k in range(N.lib().lb_tb2_shape_count())]
+                shape = names.index(shape)
         self._call("lb_set_temporal_blocking", int(shape))
+
+    @property
+    def temporal_blocking(self):
+        """Name of the two-step tile run() uses on this lattice ('off' = the one-step kernel)."""
+        k = N.lib().lb_temporal_blocking(self._h)
+        return N.lib().lb_tb2_shape_name(k).decode()
 
     def copy_ceiling_ms(self, reps=10):
         """ms per launch of an arithmetic-free kernel with the fused step's memory access pattern (the

@@ -201,13 +201,18 @@ int lb_init_synthetic(lb_sim *sim, int kind, double u0, double amplitude, uint64
 /* solid disk in GLOBAL coordinates (centre cx,cy, radius r): mask = (gx-cx)^2+(y-cy)^2 < r^2 */
 int lb_set_mask_disk(lb_sim *sim, double cx, double cy, double r);
 
-/* -- temporal blocking: TWO lattice updates per pass through HBM (csrc/lb_tb2.cuh).  With a tile shape
- *    selected, lb_step runs the moment-free steps of a run two at a time -- the intermediate time level
- *    stays in shared memory -- and the one-step kernel only for an odd step and for the last one.  Results
- *    are bit-identical to the one-step path in both math modes.  shape 0 = off (default); shapes
- *    1 .. lb_tb2_shape_count()-1 are tile geometries "BXxBY.tNT" (lb_tb2_shape_name).  Serves single-slab
- *    LB_SCHEME_OPENCL / LB_MODEL_D2Q9 lattices (pipe or periodic); other handles return LB_ERR_INVALID. */
+/* -- temporal blocking: TWO lattice updates per pass through HBM (csrc/lb_tb2.cuh, lb_tb2v.cuh).  lb_step
+ *    runs the moment-free steps of a run two at a time -- the intermediate time level stays in shared
+ *    memory -- and the one-step kernel only for an odd step and for the last one.  Results are
+ *    bit-identical to the one-step path in both math modes.
+ *    shape -1 = automatic (default): the measured-best tile for lattices of at least 2^22 nodes, the
+ *    one-step kernel below that; 0 = off; 1 .. lb_tb2_shape_count()-1 = a tile geometry by index
+ *    (lb_tb2_shape_name: "BXxBY.tNT" cell-per-thread tiles, "rowsBY.wNW" row-per-warp tiles).  Serves
+ *    single-slab LB_SCHEME_OPENCL / LB_MODEL_D2Q9 lattices (pipe; periodic boxes whose width is a
+ *    multiple of the 128-/64-cell tile for the row-per-warp tiles); halo-connected slabs always run the
+ *    one-step kernel.  lb_temporal_blocking returns the tile index lb_step will use (0 = one-step kernel). */
 int lb_set_temporal_blocking(lb_sim *sim, int shape);
+int lb_temporal_blocking(const lb_sim *sim);
 int lb_tb2_shape_count(void);
 const char *lb_tb2_shape_name(int shape);
 

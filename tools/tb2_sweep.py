@@ -22,6 +22,8 @@ def main():
     ap.add_argument("--bc", default="pipe")
     ap.add_argument("--steps", type=int, default=41)
     ap.add_argument("--no-mask", action="store_true")
+    ap.add_argument("--shapes", default="", help="comma-separated tile names (default: all)")
+    ap.add_argument("--reps", type=int, default=3)
     a = ap.parse_args()
     dtype = np.float32 if a.dtype == "f32" else np.float64
     elem = 4 if a.dtype == "f32" else 8
@@ -34,7 +36,10 @@ def main():
     sim.init_synthetic("pipe_ramp" if a.bc == "pipe" else "shear_layers", u0=0.05, amplitude=1e-3, seed=2015)
     print(f"# {a.nx}x{a.ny} {a.dtype} {a.math} {a.bc}, {a.steps} steps per run (temporal blocking covers all but the last)")
     base = None
+    wanted = [w for w in a.shapes.split(",") if w]
     for k, name in enumerate(names):
+        if wanted and name != "off" and name not in wanted:
+            continue
         try:
             sim.set_temporal_blocking(k)
         except native.LBError as exc:
@@ -42,7 +47,7 @@ def main():
             continue
         sim.run(a.steps)
         best = 1e30
-        for _ in range(3):
+        for _ in range(a.reps):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             with torch.cuda.stream(s):
                 e0.record(); sim.run(a.steps, sync=False); e1.record()
