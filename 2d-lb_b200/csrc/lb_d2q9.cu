@@ -598,8 +598,8 @@ static int launch_step(lb_sim *sim, int src_idx, int write_moments, uint32_t sta
 }
 
 // ---- temporal blocking (lb_tb2.cuh, lb_tb2v.cuh): two steps per launch ---------------------------------
-#define LB_TB2_AUTO_F32 "rows14.w8"
-#define LB_TB2_AUTO_F64 "rows14.w8"
+#define LB_TB2_AUTO_F32 "rows6.w8"
+#define LB_TB2_AUTO_F64 "rows6.w8"
 struct Tb2Shape {
     const char *name;
     int bx, by, nt;            // bx == 0: the row-per-warp version (lb_tb2v.cuh), tile width = 32*V
