@@ -610,20 +610,24 @@ struct Tb2Shape {
 template <typename T, int MATH, int BX, int BY, int NT, int MINB>
 static void launch_tb2(const Tb2Params &p, dim3 grid, size_t smem, cudaStream_t st)
 {
-    static bool configured = false;                   // one opt-in per instantiation (dynamic smem > 48 KB)
-    if (!configured) {
+    static bool configured[64] = {};                  // one opt-in per instantiation and device (dynamic smem > 48 KB)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!configured[dev & 63]) {
         cudaFuncSetAttribute(fused_two_step_kernel<T, MATH, BX, BY, NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = true;
+        configured[dev & 63] = true;
     }
     fused_two_step_kernel<T, MATH, BX, BY, NT, MINB><<<grid, NT, smem, st>>>(p);
 }
 template <typename T, int V, int MATH, int BY, int NW, int MINB>
 static void launch_tb2v(const StepParams &p, dim3 grid, size_t smem, cudaStream_t st)
 {
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!configured[dev & 63]) {
         cudaFuncSetAttribute(fused_two_step_v2_kernel<T, V, MATH, BY, NW, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = true;
+        configured[dev & 63] = true;
     }
     fused_two_step_v2_kernel<T, V, MATH, BY, NW, MINB><<<grid, 32 * NW, smem, st>>>(p);
 }
