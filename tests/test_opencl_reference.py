@@ -366,6 +366,38 @@ def test_live_single_stage_methods_if_mounted(orc):
     assert _same(orc.from_opencl_host(g["u"]), o.u)
 
 
+def test_the_references_own_cross_check_if_mounted():
+    """testing/Bryan/opencl_check_03.ipynb builds a Cython sim and an OpenCL sim with identical arguments,
+    calls one method on each and looks at |a-b| > 1e-6; its notes say "the corners are definitely different
+    though.  And the walls."  Both implementations run here, so the procedure can be repeated: identical
+    initial populations, interiors that agree to 1e-6 after the first boundary pass and the first
+    streaming pass, and differences confined to boundary nodes -- the reference's two implementations are
+    two algorithms, which is why this repo carries one scheme (and one oracle) per implementation."""
+    from oracle import refload
+    if not (refload.opencl_host_available() and refload.available()):
+        pytest.skip("reference tree not mounted")
+    oc, ol = refload.old_cython(), refload.old_opencl()
+    kw = dict(omega=1.0, lx=48, ly=24, deltaP=-0.01)
+    np.random.seed(0)
+    a = oc.Pipe_Flow(**kw)
+    np.random.seed(0)
+    with refload.quiet():
+        b = ol.Pipe_Flow(**kw, two_d_local_size=(8, 8), three_d_local_size=(8, 8, 1))
+
+    def both():
+        return np.asarray(a.f), np.rollaxis(b.get_fields_on_cpu()["f"], 2, 0)      # cell 34's `check_variable`
+
+    fa, fb = both()
+    assert np.array_equal(fa, fb)
+    for stage in ("move_bcs", "move"):
+        getattr(a, stage)()
+        getattr(b, stage)()
+        fa, fb = both()
+        differ = (np.abs(fa - fb) > 1e-6).any(axis=0)                                 # (nx, ny)
+        assert differ.any(), stage                                                    # they do disagree ...
+        assert not differ[1:-1, 1:-1].any(), stage                                    # ... on boundary nodes only
+
+
 # ------------------------------------------------------------------------------------------------
 # 4. the emulation layer
 TOY = """
