@@ -389,13 +389,13 @@ def test_the_references_own_cross_check_if_mounted():
 
     fa, fb = both()
     assert np.array_equal(fa, fb)
-    for stage in ("move_bcs", "move"):
+    for stage, rim in (("move_bcs", 1), ("move", 2)):        # streaming carries a boundary difference one node inwards
         getattr(a, stage)()
         getattr(b, stage)()
         fa, fb = both()
         differ = (np.abs(fa - fb) > 1e-6).any(axis=0)                                 # (nx, ny)
         assert differ.any(), stage                                                    # they do disagree ...
-        assert not differ[1:-1, 1:-1].any(), stage                                    # ... on boundary nodes only
+        assert not differ[rim:-rim, rim:-rim].any(), stage                            # ... next to the boundary only
 
 
 # ------------------------------------------------------------------------------------------------
