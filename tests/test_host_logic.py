@@ -237,3 +237,55 @@ def test_temporal_blocking_tile_logic_on_cpu(dtype):
         ref.run(2)
         for shape, nt in ((0, 256), (1, 64), (3, 5), (4, 2)):
             assert np.array_equal(replay(f0, None, 1, shape, nt, 1.7), ref.f), (nx, ny, shape)
+
+
+@pytest.mark.parametrize("parts", [2, 3])
+def test_two_update_halo_protocol_is_sufficient(parts):
+    """Design check for the next step of the multi-GPU path: a slab that advances TWO
+    updates per exchange needs, per interior face and row, populations {0,2,4} and the three incoming ones of
+    the neighbour's boundary column plus the three incoming ones of the column behind it (and the mask of the
+    boundary column) -- nothing else.  Model: every slab is advanced two oracle steps on its own columns
+    extended by two ghost columns that hold exactly those values and NaN everywhere else; its own columns
+    must come out NaN-free and bit-identical to the undivided lattice."""
+    from oracle import oracle as orc
+    from util import pipe_case
+    orc.build()
+    nx, ny = 96, 33
+    f0, mask = pipe_case(orc, nx, ny, np.float32, mask="touching", seed=5)
+    mask[ny // 2 - 3: ny // 2 + 3, nx // parts - 2: nx // parts + 3] = 1          # a body across the first cut
+    whole = orc.OpenCLSchemeOracle(f0, 1.3, 1.01, 1.0, mask=mask)
+    cuts = [round(k * nx / parts) for k in range(parts + 1)]
+    slabs = [f0[:, :, cuts[k]:cuts[k + 1]].copy() for k in range(parts)]
+    east_in, west_in = (1, 5, 8), (3, 6, 7)                                          # populations moving +x / -x
+    for _ in range(3):                                                               # three exchanges = six updates
+        whole.run(2)
+        new = []
+        for k, own in enumerate(slabs):
+            x0, x1 = cuts[k], cuts[k + 1]
+            gw = 2 if k > 0 else 0
+            ge = 2 if k < parts - 1 else 0
+            ext = np.full((9, ny, gw + (x1 - x0) + ge), np.nan, np.float32)
+            ext[:, :, gw:gw + (x1 - x0)] = own
+            if gw:                                                                   # from the west neighbour
+                nb = slabs[k - 1]
+                for j in (0, 2, 4) + east_in:
+                    ext[j, :, 1] = nb[j, :, -1]                                      # its boundary column
+                for j in east_in:
+                    ext[j, :, 0] = nb[j, :, -2]                                      # the column behind it
+            if ge:
+                nb = slabs[k + 1]
+                for j in (0, 2, 4) + west_in:
+                    ext[j, :, -2] = nb[j, :, 0]
+                for j in west_in:
+                    ext[j, :, -1] = nb[j, :, 1]
+            m = np.zeros((ny, ext.shape[2]), np.uint8)
+            lo, hi = x0 - min(gw, 1), x1 + min(ge, 1)                                 # mask: own columns + one ghost column
+            m[:, gw - min(gw, 1): gw + (x1 - x0) + min(ge, 1)] = mask[:, lo:hi]
+            sub = orc.OpenCLSchemeOracle(ext, 1.3, 1.01, 1.0, mask=m)
+            with np.errstate(all="ignore"):
+                sub.run(2)
+            got = sub.f[:, :, gw:gw + (x1 - x0)]
+            assert np.isfinite(got).all(), (k, "a value outside the exchanged set was needed")
+            new.append(got.copy())
+        slabs = new
+        assert np.array_equal(np.concatenate(slabs, axis=2), whole.f)
