@@ -692,7 +692,9 @@ static int tb2_auto_shape(const lb_sim *sim)
     if ((long long)sim->cfg.nx * sim->cfg.ny < (1ll << 22) || sim->cfg.ny < 64) return 0;
     const int span = sim->elem == 4 ? 128 : 64;
     if (sim->cfg.bc == LB_BC_PERIODIC && sim->cfg.nx % span) return 0;
-    return tb2_find(sim->elem == 4 ? LB_TB2_AUTO_F32 : LB_TB2_AUTO_F64);
+    const int k = tb2_find(sim->elem == 4 ? LB_TB2_AUTO_F32 : LB_TB2_AUTO_F64);
+    if (k > 0 && sim->cfg.ny > 65535 * g_tb2_shapes[k].by) return 0;      // grid.y limit: one-step kernel (3-D grid)
+    return k;
 }
 
 static int tb2_effective_shape(const lb_sim *sim)
