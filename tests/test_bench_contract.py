@@ -37,3 +37,19 @@ def test_gpu_arm_refuses_to_run_without_a_device():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "3"], capture_output=True, text=True,
                          timeout=300, cwd=ROOT)
     assert out.returncode != 0 and "no CPU fallback" in out.stderr
+
+
+def test_every_evidence_file_named_in_the_profiles_readme_exists():
+    """profiles/README.md is what the numbers in DESIGN.md / README.md point to: a file it names must be there."""
+    import re
+    prof = os.path.join(ROOT, "profiles")
+    text = open(os.path.join(prof, "README.md")).read()
+    names = set(re.findall(r"`((?:history/)?r1_[A-Za-z0-9_.\-]+\.(?:txt|json|csv))`", text))
+    assert len(names) > 30
+    missing = sorted(n for n in names if not os.path.exists(os.path.join(prof, n)))
+    assert not missing, missing
+    traffic = json.load(open(os.path.join(prof, "traffic.json")))
+    for key in ("f32", "f64", "f32_tb2"):
+        assert traffic[key]["dram_bytes_per_lattice_update"] > 0
+        src = traffic[key]["source"].split(" ")[0]
+        assert os.path.exists(os.path.join(ROOT, src)), src
