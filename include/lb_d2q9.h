@@ -240,10 +240,12 @@ int lb_total_mass(lb_sim *sim, double *out);
  * patterns of all 9*nx*ny values (fp32 patterns are zero-extended).  Equal checksums under a
  * re-decomposition into slabs or a periodic shift of the lattice mean bit-identical multisets. */
 int lb_checksum(lb_sim *sim, uint64_t *out);
-/* number of fused-kernel launches issued by this handle since creation */
+/* number of fused-kernel launches issued by this handle since creation (a two-update launch counts once) */
 int64_t lb_launch_count(const lb_sim *sim);
-/* choose one of the compiled tile configurations of the fused kernel (-1 = default);
- * lb_variant_count/lb_variant_name enumerate them.  Tuning only: results do not change. */
+/* choose one of the compiled tile configurations of the one-update fused kernel (-1 = default);
+ * lb_variant_count/lb_variant_name enumerate them.  Tuning only: results do not change.  Picking a
+ * variant by hand also switches automatic temporal blocking off (the chosen kernel is what runs);
+ * -1 restores both defaults. */
 int lb_set_variant(lb_sim *sim, int variant);
 int lb_variant_count(void);
 const char *lb_variant_name(int variant);
