@@ -215,7 +215,7 @@ __device__ __forceinline__ void cy_collide(const CyConsts &c, float (&g)[9], flo
 __global__ void cy_feq_kernel(int nx, int ny, int pitch, long long plane, const float *rho, const double *u,
                               const double *v, float *feq, CyConsts c)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = lb_grid_row();
     if (x >= nx || y >= ny) return;
     const long long i = (long long)y * pitch + x;
     float g[9];
@@ -233,7 +233,7 @@ __global__ void cy_feq_kernel(int nx, int ny, int pitch, long long plane, const 
 __global__ void cy_prestream_kernel(int nx, int ny, int pitch, long long plane, float *f, const double *u,
                                     const uint8_t *mask, int mask_pitch, CyConsts c, int velocity_inlet)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = lb_grid_row();
     if (x >= nx || y >= ny) return;
     const bool solid = mask && mask[(long long)y * mask_pitch + x] == 1;
     const bool bnd = (x == 0 || x == nx - 1 || y == 0 || y == ny - 1);
@@ -271,7 +271,7 @@ __global__ void cyv_rows_kernel(int nx, int ny, int pitch, long long plane, floa
 // write keep the node's own value (no upstream node, or one of the four non-streaming lines).
 __global__ void cy_stage_move_kernel(int nx, int ny, int pitch, long long plane, const float *src, float *dst)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = lb_grid_row();
     if (x >= nx || y >= ny) return;
     const int lx = nx - 1, ly = ny - 1;
     const bool w_ = (x == 0), e_ = (x == lx), s_ = (y == 0), n_ = (y == ly);
@@ -290,7 +290,7 @@ template <bool OLD, bool VIN>
 __global__ void cy_stage_hydro_kernel(int nx, int ny, int pitch, long long plane, const float *f, float *rho, double *u,
                                       double *v, const uint8_t *mask, int mask_pitch, CyConsts c)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = lb_grid_row();
     if (x >= nx || y >= ny) return;
     const long long i = (long long)y * pitch + x;
     float g[9];
@@ -308,7 +308,7 @@ __global__ void cy_stage_hydro_kernel(int nx, int ny, int pitch, long long plane
 template <bool OLD>
 __global__ void cy_stage_collide_kernel(int nx, int ny, int pitch, long long plane, float *f, const float *feq, CyConsts c)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = lb_grid_row();
     if (x >= nx || y >= ny) return;
     const long long i = (long long)y * pitch + x;
 #pragma unroll

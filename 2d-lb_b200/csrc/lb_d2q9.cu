@@ -3,13 +3,11 @@
 // peer-memory halo plumbing.  Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false
 // (see __graft_entry__.build()).
 #include "../../include/lb_d2q9.h"
-#include "lb_fused.cuh"
+#include "lb_host.h"
 #include "lb_cython.cuh"
 #include "lb_oldcl.cuh"
-#include "lb_tma.cuh"
-#include "lb_tb2.cuh"
-#include "lb_tb2v.cuh"
 
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -21,8 +19,10 @@ using namespace lb;
 // handle
 // =====================================================================================
 struct HaloLayout {
-    size_t ghost_bytes;     // one ghost column: 3*(ny+2) elements, rounded to 256 B
+    size_t ghost_bytes;     // one ghost column: GHOST_SLOTS*(ny+2) elements, rounded to 256 B
+    size_t mask_bytes;      // one mask column: ny bytes, rounded to 256 B
     size_t off_ghost_w[2], off_ghost_e[2];
+    size_t off_mask_w, off_mask_e;
     size_t off_flag_w, off_flag_e, off_done_w, off_done_e, off_error;
     size_t total;
 };
@@ -30,10 +30,13 @@ struct HaloLayout {
 static HaloLayout halo_layout(int ny, int elem)
 {
     HaloLayout h;
-    h.ghost_bytes = (((size_t)3 * (ny + 2) * elem) + 255) / 256 * 256;
+    h.ghost_bytes = (((size_t)GHOST_SLOTS * (ny + 2) * elem) + 255) / 256 * 256;
+    h.mask_bytes = ((size_t)ny + 255) / 256 * 256;
     size_t o = 0;
     for (int p = 0; p < 2; ++p) { h.off_ghost_w[p] = o; o += h.ghost_bytes; }
     for (int p = 0; p < 2; ++p) { h.off_ghost_e[p] = o; o += h.ghost_bytes; }
+    h.off_mask_w = o; o += h.mask_bytes;
+    h.off_mask_e = o; o += h.mask_bytes;
     h.off_flag_w = o; o += 128;
     h.off_flag_e = o; o += 128;
     h.off_done_w = o; o += 128;
@@ -47,9 +50,10 @@ struct lb_sim {
     lb_config cfg;
     int elem = 4;                 // bytes per population value
     int uv_elem = 4;              // bytes per u / v value (8 for the cython schemes: float64 like the reference)
+    bool seed_pending = false;    // lb_upload_f happened and the other ping-pong buffer has not been seeded yet (lb_stage_move)
     bool prestream_done = false;  // cython / opencl_old schemes: is the next step's BC + swap already applied to `cur`
     float *frozen = nullptr;      // opencl_old: the populations `move` never writes (lb_oldcl.cuh)
-    int tb2_shape = -1;           // temporal blocking: -1 = automatic, 0 = off, else index into g_tb2_shapes
+    int tb2_shape = -1;           // two updates per launch: -1 = automatic, 0 = off, else index into g_tb_shapes
     int pitch = 0;                // row pitch in elements (multiple of 512 B)
     long long plane = 0;          // elements per plane
     size_t buf_bytes = 0;         // bytes of one guarded 9-plane buffer
@@ -63,7 +67,11 @@ struct lb_sim {
     bool own_stream = false;
     int variant = -1;
     int64_t launches = 0;
-    uint32_t state_index = 0;     // number of fused steps taken (halo parity / flag value)
+    uint32_t state_index = 0;     // number of fused steps taken
+    uint32_t halo_epoch = 0;      // number of halo-exchanging launches taken (ghost parity / flag value)
+    bool peer_has_mask[2] = {false, false};   // did the last lb_halo_prime find a mask on the neighbour slab
+    unsigned long long halo_timeout_ns = 30000000000ull;   // bound of the in-kernel wait for a neighbour
+    int edge_rows = 16;           // rows per warp of the one-update kernel's edge tiles
     // CUDA graphs of `graph_len` moment-free steps starting from buffer `cur` == index
     cudaGraphExec_t graph[2] = {nullptr, nullptr};
     int graph_len[2] = {0, 0};
@@ -93,101 +101,6 @@ static int fail(lb_sim *s, int code, const std::string &msg)
             return fail(sim, LB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));    \
     } while (0)
 
-// =====================================================================================
-// fused kernel variants
-// =====================================================================================
-struct Variant {
-    const char *name;
-    int dtype, math, model, V, WX, WY, R;
-    void (*launch)(const StepParams &, cudaStream_t);
-    bool is_default;
-    void (*launch_tma)(const CUtensorMap &, const CUtensorMap &, const StepParams &, cudaStream_t);   // non-null: TMA-staged kernel
-    int tma_ty;                                                                   // its box height
-};
-
-template <typename T, int V, int MATH, int TY, int MINB, int STP, int MODEL>
-static void launch_tma_variant(const CUtensorMap &map_n, const CUtensorMap &map_w, const StepParams &p_in, cudaStream_t st)
-{
-    StepParams p = p_in;
-    p.tiles_x = (p.pitch + 32 * V - 1) / (32 * V);
-    p.tiles_y = (p.ny + TY - 1) / TY;
-    const unsigned gy = p.tiles_y < 65535 ? p.tiles_y : 65535;
-    const dim3 grid((unsigned)p.tiles_x, gy, ((unsigned)p.tiles_y + gy - 1) / gy);
-    fused_step_tma_kernel<T, V, MATH, TY, MINB, STP, MODEL><<<grid, 32 * TY, 0, st>>>(map_n, map_w, p);
-}
-#define VART(T, TN, DT, V, M, MN, TY, MINB)                                                         \
-    {TN "." MN ".tma.v" #V ".ty" #TY ".b" #MINB, DT, M, MODEL_D2Q9, V, 1, TY, 1, nullptr, false,       \
-     &launch_tma_variant<T, V, M, TY, MINB, 0, MODEL_D2Q9>, TY}
-
-template <typename T, int V, int MATH, int WX, int WY, int R, int MINB, int LDP, int STP, int MODEL = MODEL_D2Q9>
-static void launch_variant(const StepParams &p_in, cudaStream_t st)
-{
-    StepParams p = p_in;
-    constexpr int SPAN = 32 * V;
-    p.tiles_x = (p.pitch + SPAN * WX - 1) / (SPAN * WX);
-    p.tiles_y = (p.y_end - p.y_begin + WY * R - 1) / (WY * R);
-    dim3 grid;
-    if (p.edge_first) {
-        p.edge_rows = 16;
-        p.edge_tiles_y = (p.ny + WY * p.edge_rows - 1) / (WY * p.edge_rows);
-        const unsigned n_edge = (p.tiles_x < 2 ? 1u : 2u) * (unsigned)p.edge_tiles_y;
-        const unsigned n_int = p.tiles_x > 2 ? (unsigned)(p.tiles_x - 2) * (unsigned)p.tiles_y : 0u;
-        grid = dim3(n_edge + n_int, 1, 1);
-    }
-    else {
-        const unsigned gy = p.tiles_y < 65535 ? p.tiles_y : 65535;
-        grid = dim3((unsigned)p.tiles_x, gy, ((unsigned)p.tiles_y + gy - 1) / gy);
-    }
-    fused_step_kernel<T, V, MATH, WX, WY, R, MINB, LDP, STP, MODEL><<<grid, 32 * WX * WY, 0, st>>>(p);
-}
-
-#define VAR(T, TN, DT, V, M, MN, WX, WY, R, MINB, LDP, STP, DEF)                                    \
-    {TN "." MN ".v" #V ".wx" #WX ".wy" #WY ".r" #R ".b" #MINB ".ld" #LDP ".st" #STP, DT, M, MODEL_D2Q9, V, \
-     WX, WY, R, &launch_variant<T, V, M, WX, WY, R, MINB, LDP, STP>, DEF, nullptr, 0}
-// incompressible model (D2Q9i.cl): the default tile configuration only
-#define VARI(T, TN, DT, V, M, MN)                                                                   \
-    {TN "." MN ".d2q9i.v" #V ".wx2.wy2.r1.b6.ld1.st0", DT, M, MODEL_D2Q9I, V, 2, 2, 1,               \
-     &launch_variant<T, V, M, 2, 2, 1, 6, 1, 0, MODEL_D2Q9I>, true, nullptr, 0}
-
-#define VARS_FOR(T, TN, DT, VMAX, VHALF)                                                            \
-    VAR(T, TN, DT, VMAX, MATH_FAST, "fast", 2, 2, 1, 6, 1, 0, true),                                \
-    VAR(T, TN, DT, VMAX, MATH_FAST, "fast", 2, 2, 1, 4, 1, 0, false),                               \
-    VAR(T, TN, DT, VMAX, MATH_FAST, "fast", 2, 2, 1, 5, 1, 0, false),                               \
-    VAR(T, TN, DT, VMAX, MATH_FAST, "fast", 2, 2, 1, 7, 1, 0, false),                               \
-    VAR(T, TN, DT, VMAX, MATH_FAST, "fast", 2, 2, 1, 8, 1, 0, false),                               \
-    VAR(T, TN, DT, VMAX, MATH_FAST, "fast", 4, 1, 1, 6, 1, 0, false),                               \
-    VAR(T, TN, DT, VMAX, MATH_FAST, "fast", 4, 1, 1, 4, 1, 0, false),                               \
-    VAR(T, TN, DT, VMAX, MATH_FAST, "fast", 2, 4, 1, 2, 1, 0, false),                               \
-    VAR(T, TN, DT, VMAX, MATH_FAST, "fast", 2, 4, 1, 3, 1, 0, false),                               \
-    VAR(T, TN, DT, VMAX, MATH_FAST, "fast", 2, 4, 1, 4, 1, 0, false),                               \
-    VAR(T, TN, DT, VMAX, MATH_FAST, "fast", 4, 2, 1, 4, 1, 0, false),                               \
-    VAR(T, TN, DT, VMAX, MATH_FAST, "fast", 2, 2, 1, 6, 0, 0, false),                               \
-    VAR(T, TN, DT, VMAX, MATH_FAST, "fast", 2, 2, 1, 6, 2, 1, false),                               \
-    VAR(T, TN, DT, VMAX, MATH_FAST, "fast", 2, 2, 1, 6, 1, 1, false),                               \
-    VAR(T, TN, DT, VHALF, MATH_FAST, "fast", 2, 2, 1, 8, 1, 0, false),                              \
-    VAR(T, TN, DT, VHALF, MATH_FAST, "fast", 4, 2, 1, 4, 1, 0, false),                              \
-    VAR(T, TN, DT, VMAX, MATH_STRICT, "strict", 2, 2, 1, 6, 1, 0, true),                            \
-    VAR(T, TN, DT, VMAX, MATH_STRICT, "strict", 2, 2, 1, 5, 1, 0, false),                           \
-    VAR(T, TN, DT, VMAX, MATH_STRICT, "strict", 2, 2, 1, 4, 1, 0, false),                           \
-    VAR(T, TN, DT, VMAX, MATH_STRICT, "strict", 2, 4, 1, 3, 1, 0, false),                           \
-    VAR(T, TN, DT, VMAX, MATH_STRICT, "strict", 4, 1, 1, 6, 1, 0, false),                           \
-    VAR(T, TN, DT, VHALF, MATH_STRICT, "strict", 2, 2, 1, 8, 1, 0, false),                          \
-    VAR(T, TN, DT, VHALF, MATH_STRICT, "strict", 2, 2, 2, 6, 1, 0, false)
-
-static const Variant g_variants[] = {
-    VARS_FOR(float, "f32", LB_F32, 4, 2),
-    VARS_FOR(double, "f64", LB_F64, 2, 1),
-    VARI(float, "f32", LB_F32, 4, MATH_STRICT, "strict"), VARI(float, "f32", LB_F32, 4, MATH_FAST, "fast"),
-    VARI(double, "f64", LB_F64, 2, MATH_STRICT, "strict"), VARI(double, "f64", LB_F64, 2, MATH_FAST, "fast"),
-    VART(float, "f32", LB_F32, 4, MATH_STRICT, "strict", 4, 6), VART(float, "f32", LB_F32, 4, MATH_STRICT, "strict", 4, 4),
-    VART(float, "f32", LB_F32, 4, MATH_STRICT, "strict", 8, 3), VART(float, "f32", LB_F32, 4, MATH_STRICT, "strict", 8, 2),
-    VART(float, "f32", LB_F32, 4, MATH_STRICT, "strict", 2, 8), VART(float, "f32", LB_F32, 4, MATH_FAST, "fast", 4, 6),
-    VART(float, "f32", LB_F32, 4, MATH_FAST, "fast", 8, 3),
-    VART(double, "f64", LB_F64, 2, MATH_STRICT, "strict", 4, 6), VART(double, "f64", LB_F64, 2, MATH_STRICT, "strict", 8, 3),
-    VART(double, "f64", LB_F64, 2, MATH_FAST, "fast", 4, 6),
-};
-static const int g_nvariants = (int)(sizeof(g_variants) / sizeof(g_variants[0]));
-
 static int default_variant(int dtype, int math, int model)
 {
     for (int i = 0; i < g_nvariants; ++i)
@@ -203,7 +116,7 @@ template <typename T>
 __global__ void k_feq_from_moments(int nx, int ny, int pitch, long long plane, const T *rho, const T *u,
                                    const T *v, T *feq, Consts<T> c, int model)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = lb_grid_row();
     if (x >= nx || y >= ny) return;
     const long long i = (long long)y * pitch + x;
     T e[9];
@@ -218,7 +131,7 @@ __global__ void k_feq_from_moments(int nx, int ny, int pitch, long long plane, c
 template <typename T>
 __global__ void k_stage_move(int nx, int ny, int pitch, long long plane, int periodic, const T *src, T *dst)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = lb_grid_row();
     if (x >= nx || y >= ny) return;
     const int ex[9] = {0, 1, 0, -1, 0, 1, -1, -1, 1}, ey[9] = {0, 0, 1, 0, -1, 1, 1, -1, -1};
 #pragma unroll
@@ -238,7 +151,7 @@ template <typename T>
 __global__ void k_stage_bcs(int nx, int ny, int pitch, long long plane, int gnx, int x_off, int do_pipe,
                             const uint8_t *mask, int mask_pitch, T *f, Consts<T> c, int model)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = lb_grid_row();
     if (x >= nx || y >= ny) return;
     const long long i = (long long)y * pitch + x;
     const bool solid = mask && mask[(long long)y * mask_pitch + x] == 1;
@@ -260,7 +173,7 @@ __global__ void k_stage_bcs(int nx, int ny, int pitch, long long plane, int gnx,
 template <typename T>
 __global__ void k_stage_hydro(int nx, int ny, int pitch, long long plane, const T *f, T *rho, T *u, T *v, int model)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = lb_grid_row();
     if (x >= nx || y >= ny) return;
     const long long i = (long long)y * pitch + x;
     T g[9];
@@ -275,7 +188,7 @@ __global__ void k_stage_hydro(int nx, int ny, int pitch, long long plane, const 
 template <typename T>
 __global__ void k_stage_collide(int nx, int ny, int pitch, long long plane, T *f, const T *feq, Consts<T> c)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = lb_grid_row();
     if (x >= nx || y >= ny) return;
     const long long i = (long long)y * pitch + x;
 #pragma unroll
@@ -285,7 +198,7 @@ __global__ void k_stage_collide(int nx, int ny, int pitch, long long plane, T *f
 template <typename T>
 __global__ void k_zero_velocity(int nx, int ny, int pitch, const uint8_t *mask, int mask_pitch, T *u, T *v)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = lb_grid_row();
     if (x >= nx || y >= ny) return;
     if (mask[(long long)y * mask_pitch + x] == 1) {
         u[(long long)y * pitch + x] = (T)0;
@@ -296,7 +209,7 @@ __global__ void k_zero_velocity(int nx, int ny, int pitch, const uint8_t *mask, 
 template <typename T>
 __global__ void k_subsample(int nx, int ny, int pitch, int sx, int sy, int ox, const T *src, T *dst)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, j = lb_grid_row();
     if (i >= ox) return;
     dst[(long long)j * ox + i] = src[(long long)(j * sy) * pitch + (long long)i * sx];
 }
@@ -314,10 +227,19 @@ __global__ void k_selftest_rcp(uint32_t first, uint32_t last, unsigned long long
     if (local) atomicAdd(bad, local);
 }
 
+// host mask rows (uint8 or int32, any values) -> device mask bytes: 1 where the host value is exactly 1 (D2Q9.cl:410)
+template <typename M>
+__global__ void k_mask_pack(int nx, int rows, const M *staged, size_t staged_pitch, uint8_t *mask, int mask_pitch)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = lb_grid_row();
+    if (x >= nx || y >= rows) return;
+    mask[(long long)y * mask_pitch + x] = staged[(size_t)y * staged_pitch + x] == (M)1 ? 1 : 0;
+}
+
 // one flag byte per 32 cells of a row: 0 = no solid node in the group, 1 = some, 2 = all 32 solid
 __global__ void k_span_solid(int nx, int ny, const uint8_t *mask, int mask_pitch, uint8_t *span_solid, int nspans)
 {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    const int s = blockIdx.x * blockDim.x + threadIdx.x, y = lb_grid_row();
     if (s >= nspans || y >= ny) return;
     int n = 0;
     for (int e = 0; e < 32; ++e) {
@@ -346,7 +268,7 @@ __global__ void __launch_bounds__(128, 6) k_copy_pattern(const T *__restrict__ s
 
 __global__ void k_mask_disk(int nx, int ny, int x_off, double cx, double cy, double r2, uint8_t *mask, int mask_pitch)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = lb_grid_row();
     if (x >= nx || y >= ny) return;
     const double dx = (double)(x_off + x) - cx, dy = (double)y - cy;
     mask[(long long)y * mask_pitch + x] = (dx * dx + dy * dy < r2) ? 1 : 0;
@@ -373,7 +295,7 @@ __global__ void k_init_synth(int nx, int ny, int pitch, long long plane, int gnx
                              double amplitude, unsigned long long seed, double inlet_rho, double outlet_rho,
                              const uint8_t *mask, int mask_pitch, T *f0, T *f1, T *rho, T *u, T *v, Consts<T> c, int model)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = lb_grid_row();
     if (x >= nx || y >= ny) return;
     const long long i = (long long)y * pitch + x;
     const int gx = x_off + x;
@@ -440,24 +362,43 @@ __global__ void k_checksum(int nx, int ny, int pitch, long long plane, const T *
     if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
 }
 
-// copies the current boundary columns into the neighbours' ghost columns and publishes the flag
+// copies the current state's two outermost columns (nine-slot layout, lb_fused.cuh StepParams) and the
+// obstacle mask of the boundary column into the neighbours' arenas, then publishes the flag
 template <typename T>
-__global__ void k_halo_prime(int nx, int ny, int pitch, long long plane, const T *f, T *out_w, T *out_e,
-                             unsigned int *flag_w_remote, unsigned int *flag_e_remote, unsigned int value)
+__global__ void k_halo_prime(int nx, int ny, int pitch, long long plane, const T *f, const uint8_t *mask, int mask_pitch,
+                             T *out_w, T *out_e, uint8_t *mask_w, uint8_t *mask_e,
+                             unsigned int *flag_w_remote, unsigned int *flag_e_remote, unsigned int *error_word, unsigned int value)
 {
+    const int gs = ny + 2;
+    const int c1 = nx > 1 ? 1 : 0, c2 = nx > 1 ? nx - 2 : 0;
     for (int y = threadIdx.x; y < ny; y += blockDim.x) {
         const long long row = (long long)y * pitch;
         if (out_w) {
-            out_w[0 * (ny + 2) + y + 1] = f[3 * plane + row];
-            out_w[1 * (ny + 2) + y + 1] = f[6 * plane + row];
-            out_w[2 * (ny + 2) + y + 1] = f[7 * plane + row];
+            out_w[0 * gs + y + 1] = f[3 * plane + row];
+            out_w[1 * gs + y + 1] = f[6 * plane + row];
+            out_w[2 * gs + y + 1] = f[7 * plane + row];
+            out_w[3 * gs + y + 1] = f[0 * plane + row];
+            out_w[4 * gs + y + 1] = f[2 * plane + row];
+            out_w[5 * gs + y + 1] = f[4 * plane + row];
+            out_w[6 * gs + y + 1] = f[3 * plane + row + c1];
+            out_w[7 * gs + y + 1] = f[6 * plane + row + c1];
+            out_w[8 * gs + y + 1] = f[7 * plane + row + c1];
+            mask_w[y] = mask ? mask[(long long)y * mask_pitch] : 0;
         }
         if (out_e) {
-            out_e[0 * (ny + 2) + y + 1] = f[1 * plane + row + nx - 1];
-            out_e[1 * (ny + 2) + y + 1] = f[5 * plane + row + nx - 1];
-            out_e[2 * (ny + 2) + y + 1] = f[8 * plane + row + nx - 1];
+            out_e[0 * gs + y + 1] = f[1 * plane + row + nx - 1];
+            out_e[1 * gs + y + 1] = f[5 * plane + row + nx - 1];
+            out_e[2 * gs + y + 1] = f[8 * plane + row + nx - 1];
+            out_e[3 * gs + y + 1] = f[0 * plane + row + nx - 1];
+            out_e[4 * gs + y + 1] = f[2 * plane + row + nx - 1];
+            out_e[5 * gs + y + 1] = f[4 * plane + row + nx - 1];
+            out_e[6 * gs + y + 1] = f[1 * plane + row + c2];
+            out_e[7 * gs + y + 1] = f[5 * plane + row + c2];
+            out_e[8 * gs + y + 1] = f[8 * plane + row + c2];
+            mask_e[y] = mask ? mask[(long long)y * mask_pitch + nx - 1] : 0;
         }
     }
+    if (threadIdx.x == 0) *error_word = 0u;           // a re-primed handle starts from a clean slate
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -469,7 +410,13 @@ __global__ void k_halo_prime(int nx, int ny, int pitch, long long plane, const T
 // =====================================================================================
 // helpers
 // =====================================================================================
-static inline dim3 grid2d(const lb_sim *s, int bx = 128) { return dim3((s->cfg.nx + bx - 1) / bx, s->cfg.ny); }
+// (columns / bx) x rows, rows beyond the 65535 limit of gridDim.y folded over gridDim.z (kernels: lb_grid_row())
+static inline dim3 rows_grid(unsigned nbx, int rows)
+{
+    const unsigned gy = rows < 65535 ? (unsigned)rows : 65535u;
+    return dim3(nbx, gy, ((unsigned)rows + gy - 1) / gy);
+}
+static inline dim3 grid2d(const lb_sim *s, int bx = 128) { return rows_grid((s->cfg.nx + bx - 1) / bx, s->cfg.ny); }
 
 template <typename T>
 static Consts<T> consts_of(const lb_sim *s)
@@ -509,7 +456,7 @@ static void drop_graphs(lb_sim *s)
 
 static bool uses_halo(const lb_sim *s) { return s->cfg.west_edge == LB_EDGE_HALO || s->cfg.east_edge == LB_EDGE_HALO; }
 
-static void fill_params(lb_sim *s, StepParams &p, int src_idx, int write_moments, uint32_t state_index)
+static void fill_params(lb_sim *s, StepParams &p, int src_idx, int write_moments)
 {
     memset(&p, 0, sizeof(p));
     p.src = s->buf[src_idx];
@@ -524,17 +471,25 @@ static void fill_params(lb_sim *s, StepParams &p, int src_idx, int write_moments
     p.rho = s->rho; p.u = s->u; p.v = s->v;
     p.cf = consts_of<float>(s);
     p.cd = consts_of<double>(s);
+    p.c2 = pack_consts(p.cf);
     p.y_begin = 0; p.y_end = s->cfg.ny;
+    p.edge_rows = s->edge_rows;
     if (uses_halo(s)) {
-        const int rp = state_index & 1, wp = (state_index + 1) & 1;
+        // launch number `halo_epoch` reads the ghost columns of parity epoch&1 once the flag says epoch+1,
+        // writes the neighbours' columns of the other parity and publishes epoch+2 there
+        const uint32_t epoch = s->halo_epoch;
+        const int rp = epoch & 1, wp = (epoch + 1) & 1;
         const HaloLayout &h = s->hl;
         p.ghost_w = s->halo + h.off_ghost_w[rp];
         p.ghost_e = s->halo + h.off_ghost_e[rp];
+        p.gmask_w = s->peer_has_mask[LB_WEST] ? (const uint8_t *)(s->halo + h.off_mask_w) : nullptr;
+        p.gmask_e = s->peer_has_mask[LB_EAST] ? (const uint8_t *)(s->halo + h.off_mask_e) : nullptr;
         p.flag_w_local = (unsigned int *)(s->halo + h.off_flag_w);
         p.flag_e_local = (unsigned int *)(s->halo + h.off_flag_e);
         p.done_w = (unsigned int *)(s->halo + h.off_done_w);
         p.done_e = (unsigned int *)(s->halo + h.off_done_e);
         p.error_word = (unsigned int *)(s->halo + h.off_error);
+        p.halo_timeout_ns = s->halo_timeout_ns;
         if (s->peer[LB_WEST]) {   // my westward populations land in the west neighbour's EAST ghost
             p.out_w = s->peer[LB_WEST] + h.off_ghost_e[wp];
             p.flag_w_remote = (unsigned int *)(s->peer[LB_WEST] + h.off_flag_e);
@@ -543,7 +498,7 @@ static void fill_params(lb_sim *s, StepParams &p, int src_idx, int write_moments
             p.out_e = s->peer[LB_EAST] + h.off_ghost_w[wp];
             p.flag_e_remote = (unsigned int *)(s->peer[LB_EAST] + h.off_flag_w);
         }
-        p.step_id = state_index + 1;
+        p.step_id = epoch + 1;
         p.edge_first = 1;
     }
 }
@@ -581,11 +536,12 @@ static int ensure_tmaps(lb_sim *sim)
     return LB_OK;
 }
 
-static int launch_step(lb_sim *sim, int src_idx, int write_moments, uint32_t state_index)
+// one lattice update: reads buffer src_idx, writes the other one
+static int launch_step(lb_sim *sim, int src_idx, int write_moments)
 {
     StepParams p;
-    fill_params(sim, p, src_idx, write_moments, state_index);
-    const Variant &var = g_variants[sim->variant];
+    fill_params(sim, p, src_idx, write_moments);
+    const LbVariant &var = g_variants[sim->variant];
     if (var.launch_tma) {
         int rc = ensure_tmaps(sim);
         if (rc) return rc;
@@ -594,127 +550,87 @@ static int launch_step(lb_sim *sim, int src_idx, int write_moments, uint32_t sta
     } else var.launch(p, sim->stream);
     CU(cudaGetLastError());
     sim->launches++;
+    if (uses_halo(sim)) sim->halo_epoch++;
     return LB_OK;
 }
 
-// ---- temporal blocking (lb_tb2.cuh, lb_tb2v.cuh): two steps per launch ---------------------------------
-#define LB_TB2_AUTO_F32 "rows6.w8"
-#define LB_TB2_AUTO_F64 "rows6.w8"
-struct Tb2Shape {
-    const char *name;
-    int bx, by, nt;            // bx == 0: the row-per-warp version (lb_tb2v.cuh), tile width = 32*V
-    void (*launch[2][2])(const Tb2Params &, dim3, size_t, cudaStream_t);    // [dtype][math], lb_tb2.cuh
-    void (*launch_v[2][2])(const StepParams &, dim3, size_t, cudaStream_t); // [dtype][math], lb_tb2v.cuh
-};
-
-template <typename T, int MATH, int BX, int BY, int NT, int MINB>
-static void launch_tb2(const Tb2Params &p, dim3 grid, size_t smem, cudaStream_t st)
-{
-    static bool configured[64] = {};                  // one opt-in per instantiation and device (dynamic smem > 48 KB)
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (!configured[dev & 63]) {
-        cudaFuncSetAttribute(fused_two_step_kernel<T, MATH, BX, BY, NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured[dev & 63] = true;
-    }
-    fused_two_step_kernel<T, MATH, BX, BY, NT, MINB><<<grid, NT, smem, st>>>(p);
-}
-template <typename T, int V, int MATH, int BY, int NW, int MINB>
-static void launch_tb2v(const StepParams &p, dim3 grid, size_t smem, cudaStream_t st)
-{
-    static bool configured[64] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (!configured[dev & 63]) {
-        cudaFuncSetAttribute(fused_two_step_v2_kernel<T, V, MATH, BY, NW, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured[dev & 63] = true;
-    }
-    fused_two_step_v2_kernel<T, V, MATH, BY, NW, MINB><<<grid, 32 * NW, smem, st>>>(p);
-}
-#define TB2(BX, BY, NT, MINB)                                                                          \
-    {#BX "x" #BY ".t" #NT, BX, BY, NT,                                                                     \
-     {{launch_tb2<float, MATH_STRICT, BX, BY, NT, MINB>, launch_tb2<float, MATH_FAST, BX, BY, NT, MINB>},  \
-      {launch_tb2<double, MATH_STRICT, BX, BY, NT, MINB>, launch_tb2<double, MATH_FAST, BX, BY, NT, MINB>}}, \
-     {{nullptr, nullptr}, {nullptr, nullptr}}}
-#define TB2V(BY, NW, MINB)                                                                             \
-    {"rows" #BY ".w" #NW, 0, BY, 32 * NW, {{nullptr, nullptr}, {nullptr, nullptr}},                         \
-     {{launch_tb2v<float, 4, MATH_STRICT, BY, NW, MINB>, launch_tb2v<float, 4, MATH_FAST, BY, NW, MINB>},  \
-      {launch_tb2v<double, 2, MATH_STRICT, BY, NW, MINB>, launch_tb2v<double, 2, MATH_FAST, BY, NW, MINB>}}}
-static const Tb2Shape g_tb2_shapes[] = {
-    {"off", 0, 0, 0, {{nullptr, nullptr}, {nullptr, nullptr}}, {{nullptr, nullptr}, {nullptr, nullptr}}},
-    TB2(128, 16, 256, 2),
-    TB2(64, 32, 256, 2),
-    TB2(128, 8, 256, 4),
-    TB2(256, 8, 256, 2),
-    TB2(128, 32, 512, 1),
-    TB2(64, 16, 256, 3),
-    TB2(64, 8, 128, 6),
-    TB2V(6, 8, 3),
-    TB2V(14, 8, 2),
-    TB2V(22, 8, 1),
-    TB2V(30, 8, 1),
-    TB2V(6, 4, 6),
-    TB2V(14, 4, 4),
-};
-static const int g_ntb2 = (int)(sizeof(g_tb2_shapes) / sizeof(g_tb2_shapes[0]));
-
-static inline bool tb2_is_rows(int shape) { return shape > 0 && g_tb2_shapes[shape].bx == 0; }
+// ---- two lattice updates per launch (lb_march.cuh; with -DLB_EXPERIMENTS also lb_tb2.cuh, lb_tb2v.cuh) -------
+static inline int tb_kind(int shape) { return (shape > 0 && shape < g_ntb) ? g_tb_shapes[shape].kind : LB_TB_OFF; }
 
 static size_t tb2_smem_bytes(const lb_sim *sim, int shape)
 {
-    const Tb2Shape &t = g_tb2_shapes[shape];
-    if (tb2_is_rows(shape)) {
+    const LbTbShape &t = g_tb_shapes[shape];
+    if (t.kind == LB_TB_ROWS) {
         const int off = 16 / sim->elem, span = sim->elem == 4 ? 128 : 64;
         return (size_t)9 * (span + 2 * off) * (t.by + 2) * sim->elem;
     }
-    return (size_t)9 * (t.bx + 2) * (t.by + 2) * sim->elem;
+    if (t.kind == LB_TB_CELLS) return (size_t)9 * (t.bx + 2) * (t.by + 2) * sim->elem;
+    return 0;
 }
 
-static bool tb2_servable(const lb_sim *sim)
+// why `shape` cannot serve this handle (nullptr: it can)
+static const char *tb_refusal(const lb_sim *sim, int shape)
 {
-    return sim->cfg.scheme == LB_SCHEME_OPENCL && sim->cfg.model == LB_MODEL_D2Q9 && !uses_halo(sim) &&
-           sim->cfg.global_nx == sim->cfg.nx;
+    const int kind = tb_kind(shape);
+    if (kind == LB_TB_OFF) return nullptr;
+    if (sim->cfg.scheme != LB_SCHEME_OPENCL || sim->cfg.model != LB_MODEL_D2Q9)
+        return "two-update kernels serve LB_SCHEME_OPENCL / LB_MODEL_D2Q9 lattices";
+    if (g_variants[sim->variant].launch_tma) return "two-update kernels do not combine with a TMA-staged one-update variant";
+    const int span = sim->elem == 4 ? 128 : 64;
+    if (kind == LB_TB_MARCH) {
+        if (sim->cfg.west_edge == LB_EDGE_WRAP && sim->cfg.nx % span)
+            return "the marching kernel needs nx to be a multiple of the strip width (128 fp32 / 64 fp64 cells) on a single-slab periodic box";
+        return nullptr;
+    }
+    // the round-1 shared-memory tiles: single slab only
+    if (uses_halo(sim) || sim->cfg.global_nx != sim->cfg.nx) return "the shared-memory tiles serve single-slab lattices";
+    if (sim->cfg.ny > 65535 * g_tb_shapes[shape].by) return "lattice too tall for this tile";
+    if (tb2_smem_bytes(sim, shape) > 227 * 1024) return "tile does not fit shared memory for this dtype";
+    if (kind == LB_TB_ROWS && sim->cfg.bc == LB_BC_PERIODIC && sim->cfg.nx % span)
+        return "the row-per-warp tiles need nx to be a multiple of the tile width on a periodic box";
+    return nullptr;
 }
 
 static int tb2_find(const char *name)
 {
-    for (int k = 1; k < g_ntb2; ++k)
-        if (!strcmp(g_tb2_shapes[k].name, name)) return k;
+    for (int k = 1; k < g_ntb; ++k)
+        if (!strcmp(g_tb_shapes[k].name, name)) return k;
     return 0;
 }
 
-// The tile used when the caller did not choose (tb2_shape == -1): the measured best on B200
-// (profiles/README.md section 7) for lattices large enough to be HBM-bound; small lattices keep the
-// graph-batched one-step kernel.  0 = one-step kernel.
+// The shape used when the caller did not choose (tb2_shape == -1): the marching kernel on lattices large
+// enough to be HBM-bound; small lattices keep the graph-batched one-update kernel.  The decision uses only
+// what every slab of a decomposed lattice knows (global width, height), so all slabs decide alike.
 static int tb2_auto_shape(const lb_sim *sim)
 {
-    if (!tb2_servable(sim) || g_variants[sim->variant].launch_tma) return 0;
-    if ((long long)sim->cfg.nx * sim->cfg.ny < (1ll << 22) || sim->cfg.ny < 64) return 0;
-    const int span = sim->elem == 4 ? 128 : 64;
-    if (sim->cfg.bc == LB_BC_PERIODIC && sim->cfg.nx % span) return 0;
-    const int k = tb2_find(sim->elem == 4 ? LB_TB2_AUTO_F32 : LB_TB2_AUTO_F64);
-    if (k > 0 && sim->cfg.ny > 65535 * g_tb2_shapes[k].by) return 0;      // grid.y limit: one-step kernel (3-D grid)
-    return k;
+    if ((long long)sim->cfg.global_nx * sim->cfg.ny < (1ll << 22) || sim->cfg.ny < 64) return 0;
+    const int k = tb2_find(sim->elem == 4 ? g_tb_auto_f32 : g_tb_auto_f64);
+    return (k > 0 && !tb_refusal(sim, k)) ? k : 0;
 }
 
 static int tb2_effective_shape(const lb_sim *sim)
 {
-    if (sim->tb2_shape >= 0) return tb2_servable(sim) ? sim->tb2_shape : 0;
+    if (sim->tb2_shape >= 0) return tb_refusal(sim, sim->tb2_shape) ? 0 : sim->tb2_shape;
     return tb2_auto_shape(sim);
 }
 
-// two moment-free steps: reads buffer src_idx, writes the other one
-static int launch_two_steps(lb_sim *sim, int src_idx, int shape)
+// two steps: reads buffer src_idx, writes the other one.  The marching kernel can store the moments of the
+// second step; the round-1 tiles cannot (write_moments must be 0 for them).
+static int launch_two_steps(lb_sim *sim, int src_idx, int shape, int write_moments)
 {
-    const Tb2Shape &t = g_tb2_shapes[shape];
-    const size_t smem = tb2_smem_bytes(sim, shape);
+    const LbTbShape &t = g_tb_shapes[shape];
     const int di = sim->cfg.dtype == LB_F64, mi = sim->cfg.math == LB_MATH_FAST;
-    if (tb2_is_rows(shape)) {
+    if (t.kind == LB_TB_MARCH) {
         StepParams p;
-        fill_params(sim, p, src_idx, 0, sim->state_index);
+        fill_params(sim, p, src_idx, write_moments);
+        p.seg_rows = t.seg_rows;
+        t.launch_march[di][mi](p, sim->stream);
+    } else if (t.kind == LB_TB_ROWS) {
+        StepParams p;
+        fill_params(sim, p, src_idx, 0);
         const int span = sim->elem == 4 ? 128 : 64;
         const dim3 grid(sim->pitch / span, (sim->cfg.ny + t.by - 1) / t.by);
-        t.launch_v[di][mi](p, grid, smem, sim->stream);
+        t.launch_rows[di][mi](p, grid, tb2_smem_bytes(sim, shape), sim->stream);
     } else {
         Tb2Params p{};
         p.src = sim->buf[src_idx]; p.dst = sim->buf[src_idx ^ 1];
@@ -724,10 +640,11 @@ static int launch_two_steps(lb_sim *sim, int src_idx, int shape)
         p.mask = sim->mask; p.mask_pitch = sim->mask_pitch;
         p.cf = consts_of<float>(sim); p.cd = consts_of<double>(sim);
         const dim3 grid((sim->cfg.nx + t.bx - 1) / t.bx, (sim->cfg.ny + t.by - 1) / t.by);
-        t.launch[di][mi](p, grid, smem, sim->stream);
+        t.launch_cells[di][mi](p, grid, tb2_smem_bytes(sim, shape), sim->stream);
     }
     CU(cudaGetLastError());
     sim->launches++;
+    if (uses_halo(sim)) sim->halo_epoch++;
     return LB_OK;
 }
 
@@ -737,23 +654,23 @@ static int launch_two_steps(lb_sim *sim, int src_idx, int shape)
 extern "C" {
 
 int lb_temporal_blocking(const lb_sim *sim) { return sim ? tb2_effective_shape(sim) : 0; }
-int lb_tb2_shape_count(void) { return g_ntb2; }
-const char *lb_tb2_shape_name(int shape) { return (shape >= 0 && shape < g_ntb2) ? g_tb2_shapes[shape].name : nullptr; }
+int lb_tb2_shape_count(void) { return g_ntb; }
+const char *lb_tb2_shape_name(int shape) { return (shape >= 0 && shape < g_ntb) ? g_tb_shapes[shape].name : nullptr; }
 
 int lb_set_temporal_blocking(lb_sim *sim, int shape)
 {
     if (!sim) return LB_ERR_INVALID;
     if (shape == -1) { sim->tb2_shape = -1; return LB_OK; }
-    if (shape < 0 || shape >= g_ntb2) return fail(sim, LB_ERR_INVALID, "lb_set_temporal_blocking: unknown tile shape");
-    if (shape > 0) {
-        if (sim->cfg.scheme != LB_SCHEME_OPENCL || sim->cfg.model != LB_MODEL_D2Q9 || uses_halo(sim) || sim->cfg.global_nx != sim->cfg.nx)
-            return fail(sim, LB_ERR_INVALID, "lb_set_temporal_blocking: serves single-slab LB_SCHEME_OPENCL / LB_MODEL_D2Q9 lattices");
-        if (sim->cfg.ny > 65535 * g_tb2_shapes[shape].by) return fail(sim, LB_ERR_INVALID, "lb_set_temporal_blocking: lattice too tall for this tile");
-        if (tb2_smem_bytes(sim, shape) > 227 * 1024) return fail(sim, LB_ERR_INVALID, "lb_set_temporal_blocking: tile does not fit shared memory for this dtype");
-        if (tb2_is_rows(shape) && sim->cfg.bc == LB_BC_PERIODIC && sim->cfg.nx % (sim->elem == 4 ? 128 : 64))
-            return fail(sim, LB_ERR_INVALID, "lb_set_temporal_blocking: the row-per-warp tiles need nx to be a multiple of the tile width on a periodic box");
-    }
+    if (shape < 0 || shape >= g_ntb) return fail(sim, LB_ERR_INVALID, "lb_set_temporal_blocking: unknown shape");
+    if (const char *why = tb_refusal(sim, shape)) return fail(sim, LB_ERR_INVALID, std::string("lb_set_temporal_blocking: ") + why);
     sim->tb2_shape = shape;
+    return LB_OK;
+}
+
+int lb_set_halo_timeout(lb_sim *sim, double seconds)
+{
+    if (!sim || !(seconds > 0.0)) return fail(sim, LB_ERR_INVALID, "lb_set_halo_timeout: seconds must be positive");
+    sim->halo_timeout_ns = seconds > 1.8e10 ? ~0ull : (unsigned long long)(seconds * 1e9);
     return LB_OK;
 }
 
@@ -939,7 +856,11 @@ int lb_set_variant(lb_sim *sim, int variant)
 
 int64_t lb_launch_count(const lb_sim *sim) { return sim ? sim->launches : 0; }
 
-int lb_set_mask(lb_sim *sim, const void *host_mask, int elem_bytes)
+}  // extern "C"
+
+// host arrays may be wider than the slab (lb_multi_*: a slab's columns inside the global array): `host_row`
+// is the host row length in elements, the pointer already points at the slab's first column
+static int set_mask_impl(lb_sim *sim, const void *host_mask, int elem_bytes, size_t host_row)
 {
     if (!sim) return LB_ERR_INVALID;
     CU(cudaSetDevice(sim->cfg.device));
@@ -952,18 +873,13 @@ int lb_set_mask(lb_sim *sim, const void *host_mask, int elem_bytes)
         return LB_OK;
     }
     if (elem_bytes != 1 && elem_bytes != 4) return fail(sim, LB_ERR_INVALID, "lb_set_mask: elem_bytes must be 1 or 4");
-    std::vector<uint8_t> packed((size_t)nx * ny);
-    if (elem_bytes == 1) {
-        const uint8_t *m = (const uint8_t *)host_mask;
-        for (size_t i = 0; i < packed.size(); ++i) packed[i] = (m[i] == 1) ? 1 : 0;
-    } else {
-        const int32_t *m = (const int32_t *)host_mask;
-        for (size_t i = 0; i < packed.size(); ++i) packed[i] = (m[i] == 1) ? 1 : 0;
-    }
     if (sim->cfg.bc == LB_BC_VELOCITY_YPERIODIC && is_cython(sim))      // lb_cython.cuh folds the row exchange into the pull
-        for (int x = 0; x < nx; ++x)
-            if (packed[x] || packed[(size_t)(ny - 1) * nx + x])
-                return fail(sim, LB_ERR_INVALID, "lb_set_mask: with LB_BC_VELOCITY_YPERIODIC the exchanged rows y=0 and y=ny-1 must be free of solid nodes");
+        for (int row : {0, ny - 1})
+            for (int x = 0; x < nx; ++x) {
+                const size_t i = (size_t)row * host_row + x;
+                const bool solid = elem_bytes == 1 ? ((const uint8_t *)host_mask)[i] == 1 : ((const int32_t *)host_mask)[i] == 1;
+                if (solid) return fail(sim, LB_ERR_INVALID, "lb_set_mask: with LB_BC_VELOCITY_YPERIODIC the exchanged rows y=0 and y=ny-1 must be free of solid nodes");
+            }
     if (!sim->mask) {
         sim->mask_pitch = sim->pitch;
         sim->nspans = sim->pitch / 32;
@@ -971,12 +887,36 @@ int lb_set_mask(lb_sim *sim, const void *host_mask, int elem_bytes)
         CU(cudaMalloc((void **)&sim->span_solid, (size_t)sim->nspans * ny));
     }
     CU(cudaMemsetAsync(sim->mask, 0, (size_t)sim->mask_pitch * ny, sim->stream));
-    CU(cudaMemcpy2DAsync(sim->mask, sim->mask_pitch, packed.data(), nx, nx, ny, cudaMemcpyHostToDevice, sim->stream));
-    k_span_solid<<<dim3((sim->nspans + 63) / 64, ny), 64, 0, sim->stream>>>(nx, ny, sim->mask, sim->mask_pitch,
-                                                                            sim->span_solid, sim->nspans);
-    CU(cudaGetLastError());
-    CU(cudaStreamSynchronize(sim->stream));   // `packed` is about to go out of scope
+    // staged through a bounded device buffer (<= 64 MB), normalised to {0,1} on the device
+    const size_t row_bytes = (size_t)nx * elem_bytes;
+    int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)ny, ((size_t)64 << 20) / row_bytes));
+    void *stage = nullptr;
+    CU(cudaMalloc(&stage, row_bytes * chunk));
+    cudaError_t e = cudaSuccess;
+    for (int y0 = 0; y0 < ny && e == cudaSuccess; y0 += chunk) {
+        const int rows = std::min(chunk, ny - y0);
+        e = cudaMemcpy2DAsync(stage, row_bytes, (const char *)host_mask + (size_t)y0 * host_row * elem_bytes, host_row * elem_bytes,
+                              row_bytes, rows, cudaMemcpyHostToDevice, sim->stream);
+        if (e != cudaSuccess) break;
+        uint8_t *dst = sim->mask + (size_t)y0 * sim->mask_pitch;
+        if (elem_bytes == 1) k_mask_pack<uint8_t><<<rows_grid((nx + 127) / 128, rows), 128, 0, sim->stream>>>(nx, rows, (const uint8_t *)stage, nx, dst, sim->mask_pitch);
+        else k_mask_pack<int32_t><<<rows_grid((nx + 127) / 128, rows), 128, 0, sim->stream>>>(nx, rows, (const int32_t *)stage, nx, dst, sim->mask_pitch);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess)
+        k_span_solid<<<rows_grid((sim->nspans + 63) / 64, ny), 64, 0, sim->stream>>>(nx, ny, sim->mask, sim->mask_pitch, sim->span_solid, sim->nspans);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(sim->stream);   // the host array may go away after the call
+    cudaFree(stage);
+    CU(e);
     return LB_OK;
+}
+
+extern "C" {
+
+int lb_set_mask(lb_sim *sim, const void *host_mask, int elem_bytes)
+{
+    return set_mask_impl(sim, host_mask, elem_bytes, sim ? (size_t)sim->cfg.nx : 0);
 }
 
 int lb_set_mask_disk(lb_sim *sim, double cx, double cy, double r)
@@ -993,21 +933,25 @@ int lb_set_mask_disk(lb_sim *sim, double cx, double cy, double r)
     }
     CU(cudaMemsetAsync(sim->mask, 0, (size_t)sim->mask_pitch * ny, sim->stream));
     k_mask_disk<<<grid2d(sim), 128, 0, sim->stream>>>(nx, ny, sim->cfg.x_offset, cx, cy, r * r, sim->mask, sim->mask_pitch);
-    k_span_solid<<<dim3((sim->nspans + 63) / 64, ny), 64, 0, sim->stream>>>(nx, ny, sim->mask, sim->mask_pitch,
+    k_span_solid<<<rows_grid((sim->nspans + 63) / 64, ny), 64, 0, sim->stream>>>(nx, ny, sim->mask, sim->mask_pitch,
                                                                             sim->span_solid, sim->nspans);
     CU(cudaGetLastError());
     return LB_OK;
 }
 
-int lb_upload_f(lb_sim *sim, const void *host_f)
+}  // extern "C"
+
+static int upload_f_impl(lb_sim *sim, const void *host_f, size_t host_row)
 {
     if (!sim || !host_f) return fail(sim, LB_ERR_INVALID, "lb_upload_f: null argument");
     CU(cudaSetDevice(sim->cfg.device));
     const size_t w = (size_t)sim->cfg.nx * sim->elem, dp = (size_t)sim->pitch * sim->elem;
     // planes are contiguous (plane = ny*pitch), so one 2-D copy of 9*ny rows does all nine
-    CU(cudaMemcpy2DAsync(sim->buf[sim->cur], dp, host_f, w, w, (size_t)9 * sim->cfg.ny, cudaMemcpyHostToDevice, sim->stream));
-    // the reference seeds f_streamed with the same data (opencl_dim.py:324-327)
-    CU(cudaMemcpyAsync(sim->buf_base[sim->cur ^ 1], sim->buf_base[sim->cur], sim->buf_bytes, cudaMemcpyDeviceToDevice, sim->stream));
+    CU(cudaMemcpy2DAsync(sim->buf[sim->cur], dp, host_f, host_row * sim->elem, w, (size_t)9 * sim->cfg.ny, cudaMemcpyHostToDevice, sim->stream));
+    // The reference seeds f_streamed with the same data (opencl_dim.py:324-327).  Only `move` as a single stage
+    // can see that seed (destinations without an upstream node keep it); the fused step overwrites or closes
+    // every such slot, so the copy is deferred until lb_stage_move asks for it.
+    sim->seed_pending = true;
     if (is_oldcl(sim)) {
         const int n = sim->cfg.nx > sim->cfg.ny ? sim->cfg.nx : sim->cfg.ny;
         oc_capture_frozen_kernel<<<(n + 127) / 128, 128, 0, sim->stream>>>(sim->cfg.nx, sim->cfg.ny, sim->pitch, sim->plane,
@@ -1019,7 +963,7 @@ int lb_upload_f(lb_sim *sim, const void *host_f)
     return LB_OK;
 }
 
-int lb_upload_moments(lb_sim *sim, const void *host_rho, const void *host_u, const void *host_v)
+static int upload_moments_impl(lb_sim *sim, const void *host_rho, const void *host_u, const void *host_v, size_t host_row)
 {
     if (!sim) return LB_ERR_INVALID;
     CU(cudaSetDevice(sim->cfg.device));
@@ -1028,10 +972,19 @@ int lb_upload_moments(lb_sim *sim, const void *host_rho, const void *host_u, con
     for (int i = 0; i < 3; ++i) {
         const int eb = i == 0 ? sim->elem : sim->uv_elem;      // u, v are float64 for the cython schemes
         const size_t w = (size_t)sim->cfg.nx * eb, dp = (size_t)sim->pitch * eb;
-        if (hs[i]) CU(cudaMemcpy2DAsync(ds[i], dp, hs[i], w, w, sim->cfg.ny, cudaMemcpyHostToDevice, sim->stream));
+        if (hs[i]) CU(cudaMemcpy2DAsync(ds[i], dp, hs[i], host_row * eb, w, sim->cfg.ny, cudaMemcpyHostToDevice, sim->stream));
     }
     CU(cudaStreamSynchronize(sim->stream));
     return LB_OK;
+}
+
+extern "C" {
+
+int lb_upload_f(lb_sim *sim, const void *host_f) { return upload_f_impl(sim, host_f, sim ? (size_t)sim->cfg.nx : 0); }
+
+int lb_upload_moments(lb_sim *sim, const void *host_rho, const void *host_u, const void *host_v)
+{
+    return upload_moments_impl(sim, host_rho, host_u, host_v, sim ? (size_t)sim->cfg.nx : 0);
 }
 
 static int ensure_feq(lb_sim *sim)
@@ -1142,7 +1095,7 @@ static int ensure_graph(lb_sim *sim)
     CU(cudaStreamBeginCapture(sim->stream, cudaStreamCaptureModeThreadLocal));
     int idx = sim->cur, rc = LB_OK;
     const int64_t l0 = sim->launches;
-    for (int i = 0; i < GRAPH_LEN && rc == LB_OK; ++i) { rc = launch_step(sim, idx, 0, 0); idx ^= 1; }
+    for (int i = 0; i < GRAPH_LEN && rc == LB_OK; ++i) { rc = launch_step(sim, idx, 0); idx ^= 1; }
     sim->launches = l0;                  // captured, not executed
     cudaError_t ce = cudaStreamEndCapture(sim->stream, &g);
     if (rc != LB_OK) { if (g) cudaGraphDestroy(g); return rc; }
@@ -1155,7 +1108,11 @@ static int ensure_graph(lb_sim *sim)
     return LB_OK;
 }
 
-int lb_step(lb_sim *sim, int n_steps)
+}  // extern "C"
+
+// n_steps lattice updates.  `final`: the run ends here, so its last launch stores rho, u, v; lb_multi_step
+// enqueues long runs in chunks and passes false for all but the last one.
+static int step_impl(lb_sim *sim, int n_steps, bool final)
 {
     if (!sim) return LB_ERR_INVALID;
     if (n_steps < 0) return fail(sim, LB_ERR_INVALID, "lb_step: negative step count");
@@ -1167,17 +1124,35 @@ int lb_step(lb_sim *sim, int n_steps)
             if (e == LB_EDGE_HALO && !sim->peer[side]) return fail(sim, LB_ERR_STATE, "lb_step: halo edge not connected");
         }
     }
+    sim->seed_pending = false;              // every launch below rewrites the other ping-pong buffer completely
     if (is_oldcl(sim)) return oldcl_steps(sim, n_steps);
     if (sim->cfg.scheme != LB_SCHEME_OPENCL) return cython_steps(sim, n_steps);
+    const int tb = tb2_effective_shape(sim);
+    if (tb_kind(tb) == LB_TB_MARCH) {
+        // every step of the run inside two-update launches: an odd run starts with one single step, and the
+        // launch that ends the run also stores rho, u, v (the moments of the run's last step)
+        int remaining = n_steps;
+        if (remaining & 1) {
+            int rc = launch_step(sim, sim->cur, final && remaining == 1);
+            if (rc) return rc;
+            sim->cur ^= 1; sim->state_index++; --remaining;
+        }
+        for (; remaining > 0; remaining -= 2) {
+            int rc = launch_two_steps(sim, sim->cur, tb, final && remaining == 2);
+            if (rc) return rc;
+            sim->cur ^= 1; sim->state_index += 2;
+        }
+        return LB_OK;
+    }
     int remaining = n_steps - 1;            // all but the last step skip the moment stores
-    if (const int tb2 = tb2_effective_shape(sim)) {   // temporal blocking: moment-free steps two at a time
+    if (tb) {                               // round-1 tiles (-DLB_EXPERIMENTS): moment-free steps two at a time
         for (; remaining >= 2; remaining -= 2) {
-            int rc = launch_two_steps(sim, sim->cur, tb2);
+            int rc = launch_two_steps(sim, sim->cur, tb, 0);
             if (rc) return rc;
             sim->cur ^= 1; sim->state_index += 2;
         }
     }
-    const bool graphs_ok = !uses_halo(sim); // halo launches carry a per-step flag value
+    const bool graphs_ok = !uses_halo(sim); // halo launches carry a per-launch flag value
     while (graphs_ok && remaining >= GRAPH_LEN) {
         int rc = ensure_graph(sim);
         if (rc) return rc;
@@ -1187,62 +1162,19 @@ int lb_step(lb_sim *sim, int n_steps)
         remaining -= GRAPH_LEN;
     }
     for (; remaining > 0; --remaining) {
-        int rc = launch_step(sim, sim->cur, 0, sim->state_index);
+        int rc = launch_step(sim, sim->cur, 0);
         if (rc) return rc;
         sim->cur ^= 1; sim->state_index++;
     }
-    int rc = launch_step(sim, sim->cur, 1, sim->state_index);
+    int rc = launch_step(sim, sim->cur, final ? 1 : 0);
     if (rc) return rc;
     sim->cur ^= 1; sim->state_index++;
     return LB_OK;
 }
 
-// ---- L2-level temporal blocking (experimental) ---------------------------------
-// `depth` consecutive steps travel down the lattice together: step s works on row band b - s, each band
-// shifted up by s rows, so stream order alone satisfies "row y of step s+1 needs rows y-1..y+1 of step s" and
-// "step s+1 may overwrite a row of the buffer step s reads only after step s is done with it".  What step s
-// wrote is read by step s+1 a band later, while it is still in L2, and the intermediate time levels are
-// overwritten in L2 (the ping-pong buffers alias them) before they are ever written back.
-int lb_step_banded(lb_sim *sim, int n_steps, int band_rows, int depth)
-{
-    if (!sim) return LB_ERR_INVALID;
-    if (n_steps < 0 || band_rows < 1 || depth < 1) return fail(sim, LB_ERR_INVALID, "lb_step_banded: bad argument");
-    if (sim->cfg.scheme != LB_SCHEME_OPENCL || uses_halo(sim) || sim->cfg.bc == LB_BC_PERIODIC || g_variants[sim->variant].launch_tma)
-        return fail(sim, LB_ERR_INVALID, "lb_step_banded: serves single-slab, non-periodic LB_SCHEME_OPENCL lattices (register-shuffle kernel)");
-    if (n_steps == 0) return LB_OK;
-    CU(cudaSetDevice(sim->cfg.device));
-    const int ny = sim->cfg.ny;
-    int remaining = n_steps - 1;                       // the last step stores the moments: whole-lattice launch
-    const Variant &var = g_variants[sim->variant];
-    while (remaining > 0) {
-        const int k = remaining < depth ? remaining : depth;
-        const int nb = (ny + k + band_rows - 1) / band_rows;          // bands of the most shifted step reach row ny
-        for (int b = 0; b < nb + k - 1; ++b) {
-            for (int s = 0; s < k; ++s) {
-                const int band = b - s;
-                if (band < 0 || band >= nb) continue;
-                int y0 = band * band_rows - s, y1 = y0 + band_rows;
-                if (y0 < 0) y0 = 0;
-                if (y1 > ny) y1 = ny;
-                if (band == nb - 1) y1 = ny;
-                if (y0 >= y1) continue;
-                StepParams p;
-                fill_params(sim, p, sim->cur ^ (s & 1), 0, sim->state_index + s);
-                p.y_begin = y0; p.y_end = y1;
-                var.launch(p, sim->stream);
-                sim->launches++;
-            }
-        }
-        CU(cudaGetLastError());
-        sim->cur ^= (k & 1);
-        sim->state_index += k;
-        remaining -= k;
-    }
-    int rc = launch_step(sim, sim->cur, 1, sim->state_index);
-    if (rc) return rc;
-    sim->cur ^= 1; sim->state_index++;
-    return LB_OK;
-}
+extern "C" {
+
+int lb_step(lb_sim *sim, int n_steps) { return step_impl(sim, n_steps, true); }
 
 int lb_sync(lb_sim *sim)
 {
@@ -1257,12 +1189,15 @@ int lb_sync(lb_sim *sim)
     return LB_OK;
 }
 
-int lb_download(lb_sim *sim, int field, void *host_out)
+}  // extern "C"
+
+static int download_impl(lb_sim *sim, int field, void *host_out, size_t host_row, bool sync)
 {
     if (!sim || !host_out) return fail(sim, LB_ERR_INVALID, "lb_download: null argument");
     CU(cudaSetDevice(sim->cfg.device));
-    size_t w = (size_t)sim->cfg.nx * sim->elem, dp = (size_t)sim->pitch * sim->elem;
-    if (field == LB_FIELD_U || field == LB_FIELD_V) { w = (size_t)sim->cfg.nx * sim->uv_elem; dp = (size_t)sim->pitch * sim->uv_elem; }
+    int eb = sim->elem;
+    if (field == LB_FIELD_U || field == LB_FIELD_V) eb = sim->uv_elem;
+    const size_t w = (size_t)sim->cfg.nx * eb, dp = (size_t)sim->pitch * eb;
     const void *src = nullptr;
     size_t rows = sim->cfg.ny;
     switch (field) {
@@ -1273,9 +1208,13 @@ int lb_download(lb_sim *sim, int field, void *host_out)
     case LB_FIELD_V: src = sim->v; break;
     default: return fail(sim, LB_ERR_INVALID, "lb_download: unknown field");
     }
-    CU(cudaMemcpy2DAsync(host_out, w, src, dp, w, rows, cudaMemcpyDeviceToHost, sim->stream));
-    return lb_sync(sim);
+    CU(cudaMemcpy2DAsync(host_out, host_row * eb, src, dp, w, rows, cudaMemcpyDeviceToHost, sim->stream));
+    return sync ? lb_sync(sim) : LB_OK;
 }
+
+extern "C" {
+
+int lb_download(lb_sim *sim, int field, void *host_out) { return download_impl(sim, field, host_out, sim ? (size_t)sim->cfg.nx : 0, true); }
 
 int lb_download_strided(lb_sim *sim, int field, int stride_x, int stride_y, void *host_out)
 {
@@ -1288,7 +1227,7 @@ int lb_download_strided(lb_sim *sim, int field, int stride_x, int stride_y, void
     const int ox = (sim->cfg.nx + stride_x - 1) / stride_x, oy = (sim->cfg.ny + stride_y - 1) / stride_y;
     void *tmp = nullptr;
     CU(cudaMallocAsync(&tmp, (size_t)ox * oy * eb, sim->stream));
-    const dim3 grid((ox + 127) / 128, oy);
+    const dim3 grid = rows_grid((ox + 127) / 128, oy);
     if (eb == 4) k_subsample<float><<<grid, 128, 0, sim->stream>>>(sim->cfg.nx, sim->cfg.ny, sim->pitch, stride_x, stride_y, ox, (const float *)src, (float *)tmp);
     else k_subsample<double><<<grid, 128, 0, sim->stream>>>(sim->cfg.nx, sim->cfg.ny, sim->pitch, stride_x, stride_y, ox, (const double *)src, (double *)tmp);
     CU(cudaGetLastError());
@@ -1327,6 +1266,10 @@ int lb_stage_move(lb_sim *sim)
     if (!sim) return LB_ERR_INVALID;
     if (uses_halo(sim)) return fail(sim, LB_ERR_STATE, "single stages are not available on halo-connected slabs");
     CU(cudaSetDevice(sim->cfg.device));
+    if (sim->seed_pending) {       // opencl_dim.py:324-327: f_streamed starts as a copy of f
+        CU(cudaMemcpyAsync(sim->buf_base[sim->cur ^ 1], sim->buf_base[sim->cur], sim->buf_bytes, cudaMemcpyDeviceToDevice, sim->stream));
+        sim->seed_pending = false;
+    }
     if (is_cython(sim) || is_oldcl(sim)) {
         const float *src = (const float *)sim->buf[sim->cur];
         float *dst = (float *)sim->buf[sim->cur ^ 1];
@@ -1544,22 +1487,312 @@ int lb_halo_prime(lb_sim *sim)
     if (!uses_halo(sim)) return LB_OK;
     CU(cudaSetDevice(sim->cfg.device));
     const HaloLayout &h = sim->hl;
-    const int par = sim->state_index & 1;
-    char *ow = (sim->cfg.west_edge == LB_EDGE_HALO && sim->peer[LB_WEST]) ? sim->peer[LB_WEST] + h.off_ghost_e[par] : nullptr;
-    char *oe = (sim->cfg.east_edge == LB_EDGE_HALO && sim->peer[LB_EAST]) ? sim->peer[LB_EAST] + h.off_ghost_w[par] : nullptr;
-    unsigned int *fw = ow ? (unsigned int *)(sim->peer[LB_WEST] + h.off_flag_e) : nullptr;
-    unsigned int *fe = oe ? (unsigned int *)(sim->peer[LB_EAST] + h.off_flag_w) : nullptr;
-    if ((sim->cfg.west_edge == LB_EDGE_HALO && !ow) || (sim->cfg.east_edge == LB_EDGE_HALO && !oe))
-        return fail(sim, LB_ERR_STATE, "lb_halo_prime: halo edge not connected");
+    const int par = sim->halo_epoch & 1;
+    const bool w = sim->cfg.west_edge == LB_EDGE_HALO, e = sim->cfg.east_edge == LB_EDGE_HALO;
+    if ((w && !sim->peer[LB_WEST]) || (e && !sim->peer[LB_EAST])) return fail(sim, LB_ERR_STATE, "lb_halo_prime: halo edge not connected");
+    // my westward columns land in the west neighbour's EAST ghost / mask column, and vice versa
+    char *ow = w ? sim->peer[LB_WEST] + h.off_ghost_e[par] : nullptr;
+    char *oe = e ? sim->peer[LB_EAST] + h.off_ghost_w[par] : nullptr;
+    uint8_t *mw = w ? (uint8_t *)(sim->peer[LB_WEST] + h.off_mask_e) : nullptr;
+    uint8_t *me = e ? (uint8_t *)(sim->peer[LB_EAST] + h.off_mask_w) : nullptr;
+    unsigned int *fw = w ? (unsigned int *)(sim->peer[LB_WEST] + h.off_flag_e) : nullptr;
+    unsigned int *fe = e ? (unsigned int *)(sim->peer[LB_EAST] + h.off_flag_w) : nullptr;
+    unsigned int *err = (unsigned int *)(sim->halo + h.off_error);
+    // a handle that timed out may have left its edge-tile counters half way
+    CU(cudaMemsetAsync(sim->halo + h.off_done_w, 0, 4, sim->stream));
+    CU(cudaMemsetAsync(sim->halo + h.off_done_e, 0, 4, sim->stream));
     if (sim->cfg.dtype == LB_F32)
         k_halo_prime<float><<<1, 1024, 0, sim->stream>>>(sim->cfg.nx, sim->cfg.ny, sim->pitch, sim->plane, (const float *)sim->buf[sim->cur],
-                                                          (float *)ow, (float *)oe, fw, fe, sim->state_index + 1);
+                                                          sim->mask, sim->mask_pitch, (float *)ow, (float *)oe, mw, me, fw, fe, err, sim->halo_epoch + 1);
     else
         k_halo_prime<double><<<1, 1024, 0, sim->stream>>>(sim->cfg.nx, sim->cfg.ny, sim->pitch, sim->plane, (const double *)sim->buf[sim->cur],
-                                                           (double *)ow, (double *)oe, fw, fe, sim->state_index + 1);
+                                                           sim->mask, sim->mask_pitch, (double *)ow, (double *)oe, mw, me, fw, fe, err, sim->halo_epoch + 1);
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(sim->stream));
+    // the neighbours' mask columns arrive in MY arena by THEIR prime; always consult them (all zeros = no solids)
+    sim->peer_has_mask[LB_WEST] = w;
+    sim->peer_has_mask[LB_EAST] = e;
     return LB_OK;
+}
+
+}  // extern "C"
+
+// =====================================================================================
+// lb_multi: one lattice on several slabs / devices behind one handle (SURVEY.md section 8b:
+// the handle owns streams, peer mappings and the step loop; the reference binds one queue to devices[0],
+// opencl_dim.py:229-240)
+// =====================================================================================
+struct lb_multi {
+    lb_config cfg;                       // the whole lattice
+    std::vector<lb_sim *> slabs;
+    std::vector<int> x0, w, device;
+    std::vector<cudaStream_t> shared_streams;   // one per device that carries more than one slab
+    bool concurrent = false;             // one slab per device: slabs run asynchronously, synchronised by the in-kernel flags
+    bool primed = false;
+    std::string err;
+};
+
+static thread_local std::string g_multi_create_error;
+
+static int mfail(lb_multi *m, int code, const std::string &msg)
+{
+    if (m) m->err = msg; else g_multi_create_error = msg;
+    return code;
+}
+// a failed slab call: copy its message up
+static int mslab(lb_multi *m, size_t k, int rc)
+{
+    if (rc != LB_OK) m->err = "slab " + std::to_string(k) + ": " + m->slabs[k]->err;
+    return rc;
+}
+#define MS(k, call) do { int rc__ = mslab(m, (k), (call)); if (rc__ != LB_OK) return rc__; } while (0)
+
+static int multi_prime(lb_multi *m)
+{
+    if (m->slabs.size() > 1) {
+        for (size_t k = 0; k < m->slabs.size(); ++k) MS(k, lb_sync(m->slabs[k]));          // every state final ...
+        for (size_t k = 0; k < m->slabs.size(); ++k) MS(k, lb_halo_prime(m->slabs[k]));    // ... before any ghost is written
+    }
+    m->primed = true;
+    return LB_OK;
+}
+
+extern "C" {
+
+const char *lb_multi_last_error(const lb_multi *m) { return m ? m->err.c_str() : g_multi_create_error.c_str(); }
+int lb_multi_slab_count(const lb_multi *m) { return m ? (int)m->slabs.size() : 0; }
+
+int lb_multi_slab(lb_multi *m, int k, lb_sim **slab, int *x_offset, int *nx)
+{
+    if (!m || k < 0 || k >= (int)m->slabs.size()) return mfail(m, LB_ERR_INVALID, "lb_multi_slab: bad index");
+    if (slab) *slab = m->slabs[k];
+    if (x_offset) *x_offset = m->x0[k];
+    if (nx) *nx = m->w[k];
+    return LB_OK;
+}
+
+int lb_multi_destroy(lb_multi *m)
+{
+    if (!m) return LB_OK;
+    // a neighbour's last launch may still be storing into a slab's arena: drain everything first
+    for (lb_sim *s : m->slabs) if (s) { cudaSetDevice(s->cfg.device); cudaStreamSynchronize(s->stream); }
+    for (size_t k = m->slabs.size(); k-- > 0;) lb_destroy(m->slabs[k]);
+    for (size_t d = 0; d < m->shared_streams.size(); ++d) if (m->shared_streams[d]) cudaStreamDestroy(m->shared_streams[d]);
+    cudaGetLastError();
+    delete m;
+    return LB_OK;
+}
+
+int lb_multi_create(const lb_config *cfg, int n_slabs, const int *device_ids, lb_multi **out)
+{
+    if (!cfg || !out || n_slabs < 1 || !device_ids) return mfail(nullptr, LB_ERR_INVALID, "lb_multi_create: bad argument");
+    *out = nullptr;
+    if (cfg->struct_size != (int32_t)sizeof(lb_config)) return mfail(nullptr, LB_ERR_INVALID, "lb_multi_create: lb_config size mismatch (ABI)");
+    if (cfg->global_nx != cfg->nx || cfg->x_offset != 0) return mfail(nullptr, LB_ERR_INVALID, "lb_multi_create: cfg describes the WHOLE lattice (global_nx = nx, x_offset = 0)");
+    if (n_slabs > 1 && cfg->scheme != LB_SCHEME_OPENCL) return mfail(nullptr, LB_ERR_INVALID, "lb_multi_create: only LB_SCHEME_OPENCL lattices decompose into slabs");
+    if (cfg->nx / n_slabs < 2) return mfail(nullptr, LB_ERR_INVALID, "lb_multi_create: each slab needs at least 2 columns");
+    lb_multi *m = new lb_multi();
+    m->cfg = *cfg;
+    // remainder columns go to the first slabs: widths differ by at most one
+    const int base = cfg->nx / n_slabs, rem = cfg->nx % n_slabs;
+    int ndev = 0;
+    cudaGetDeviceCount(&ndev);
+    cudaGetLastError();
+    std::vector<int> per_device(ndev > 0 ? ndev : 1, 0);
+    for (int k = 0; k < n_slabs; ++k)
+        if (device_ids[k] >= 0 && device_ids[k] < ndev) per_device[device_ids[k]]++;
+    m->shared_streams.assign(per_device.size(), nullptr);
+    bool distinct = n_slabs > 1;
+    for (int c : per_device) if (c > 1) distinct = false;
+    m->concurrent = distinct;
+    int x = 0;
+    for (int k = 0; k < n_slabs; ++k) {
+        lb_config c = *cfg;
+        c.device = device_ids[k];
+        c.nx = base + (k < rem ? 1 : 0);
+        c.x_offset = x;
+        c.global_nx = cfg->nx;
+        if (n_slabs > 1) {
+            const bool periodic = cfg->bc == LB_BC_PERIODIC;
+            c.west_edge = (periodic || k > 0) ? LB_EDGE_HALO : LB_EDGE_BOUNDARY;
+            c.east_edge = (periodic || k < n_slabs - 1) ? LB_EDGE_HALO : LB_EDGE_BOUNDARY;
+        }
+        // slabs that share a device share a stream and advance in lock-step, one launch at a time
+        c.stream = nullptr;
+        if (c.device >= 0 && c.device < ndev && per_device[c.device] > 1) {
+            if (!m->shared_streams[c.device]) {
+                if (cudaSetDevice(c.device) != cudaSuccess || cudaStreamCreateWithFlags(&m->shared_streams[c.device], cudaStreamNonBlocking) != cudaSuccess) {
+                    cudaGetLastError();
+                    lb_multi_destroy(m);
+                    return mfail(nullptr, LB_ERR_CUDA, "lb_multi_create: cannot create a stream");
+                }
+            }
+            c.stream = m->shared_streams[c.device];
+        }
+        lb_sim *s = nullptr;
+        const int rc = lb_create(&c, &s);
+        if (rc != LB_OK) {
+            const std::string why = "lb_multi_create: slab " + std::to_string(k) + ": " + g_create_error;
+            lb_multi_destroy(m);
+            return mfail(nullptr, rc, why);
+        }
+        m->slabs.push_back(s); m->x0.push_back(x); m->w.push_back(c.nx); m->device.push_back(c.device);
+        x += c.nx;
+    }
+    for (int k = 0; k < n_slabs && n_slabs > 1; ++k) {
+        lb_sim *s = m->slabs[k];
+        int rc = LB_OK;
+        if (s->cfg.west_edge == LB_EDGE_HALO) rc = lb_halo_connect_local(s, LB_WEST, m->slabs[(k + n_slabs - 1) % n_slabs]);
+        if (rc == LB_OK && s->cfg.east_edge == LB_EDGE_HALO) rc = lb_halo_connect_local(s, LB_EAST, m->slabs[(k + 1) % n_slabs]);
+        if (rc != LB_OK) {
+            const std::string why = "lb_multi_create: connecting slab " + std::to_string(k) + ": " + s->err;
+            lb_multi_destroy(m);
+            return mfail(nullptr, rc, why);
+        }
+    }
+    *out = m;
+    return LB_OK;
+}
+
+/* global host arrays in, global host arrays out: every slab copies its own columns (strided 2-D copies) */
+int lb_multi_set_mask(lb_multi *m, const void *host_mask, int elem_bytes)
+{
+    if (!m) return LB_ERR_INVALID;
+    for (size_t k = 0; k < m->slabs.size(); ++k)
+        MS(k, set_mask_impl(m->slabs[k], host_mask ? (const char *)host_mask + (size_t)m->x0[k] * elem_bytes : nullptr, elem_bytes, (size_t)m->cfg.nx));
+    m->primed = false;                   // the neighbours hold a copy of each slab's boundary mask column
+    return LB_OK;
+}
+
+int lb_multi_set_mask_disk(lb_multi *m, double cx, double cy, double r)
+{
+    if (!m) return LB_ERR_INVALID;
+    for (size_t k = 0; k < m->slabs.size(); ++k) MS(k, lb_set_mask_disk(m->slabs[k], cx, cy, r));
+    m->primed = false;
+    return LB_OK;
+}
+
+int lb_multi_upload_f(lb_multi *m, const void *host_f)
+{
+    if (!m || !host_f) return mfail(m, LB_ERR_INVALID, "lb_multi_upload_f: null argument");
+    for (size_t k = 0; k < m->slabs.size(); ++k)
+        MS(k, upload_f_impl(m->slabs[k], (const char *)host_f + (size_t)m->x0[k] * m->slabs[k]->elem, (size_t)m->cfg.nx));
+    return multi_prime(m);
+}
+
+int lb_multi_upload_moments(lb_multi *m, const void *host_rho, const void *host_u, const void *host_v)
+{
+    if (!m) return LB_ERR_INVALID;
+    for (size_t k = 0; k < m->slabs.size(); ++k) {
+        lb_sim *s = m->slabs[k];
+        auto at = [&](const void *p, int eb) { return p ? (const void *)((const char *)p + (size_t)m->x0[k] * eb) : nullptr; };
+        MS(k, upload_moments_impl(s, at(host_rho, s->elem), at(host_u, s->uv_elem), at(host_v, s->uv_elem), (size_t)m->cfg.nx));
+    }
+    return LB_OK;
+}
+
+int lb_multi_init_synthetic(lb_multi *m, int kind, double u0, double amplitude, uint64_t seed)
+{
+    if (!m) return LB_ERR_INVALID;
+    for (size_t k = 0; k < m->slabs.size(); ++k) MS(k, lb_init_synthetic(m->slabs[k], kind, u0, amplitude, seed));
+    return multi_prime(m);
+}
+
+int lb_multi_set_temporal_blocking(lb_multi *m, int shape)
+{
+    if (!m) return LB_ERR_INVALID;
+    for (size_t k = 0; k < m->slabs.size(); ++k) MS(k, lb_set_temporal_blocking(m->slabs[k], shape));
+    return LB_OK;
+}
+
+int lb_multi_temporal_blocking(const lb_multi *m) { return (m && !m->slabs.empty()) ? tb2_effective_shape(m->slabs[0]) : 0; }
+
+int lb_multi_prime(lb_multi *m) { return m ? multi_prime(m) : LB_ERR_INVALID; }
+
+/* the hot path: Pipe_Flow.run (opencl_dim.py:372-387) on every slab; no host synchronisation inside */
+int lb_multi_step(lb_multi *m, int n_steps)
+{
+    if (!m) return LB_ERR_INVALID;
+    if (n_steps < 0) return mfail(m, LB_ERR_INVALID, "lb_multi_step: negative step count");
+    if (n_steps == 0) return LB_OK;
+    const size_t n = m->slabs.size();
+    if (n == 1) { MS(0, step_impl(m->slabs[0], n_steps, true)); return LB_OK; }
+    if (!m->primed) { int rc = multi_prime(m); if (rc) return rc; }
+    if (m->concurrent) {
+        // one slab per device: enqueue bounded chunks round-robin; the kernels of neighbouring devices
+        // synchronise among themselves through the peer-memory flags.  Chunks are even, so every slab issues
+        // the same sequence of single-update / two-update launches.
+        const int CHUNK = 32;
+        int done = 0;
+        while (done < n_steps) {
+            int chunk = std::min(CHUNK, n_steps - done);
+            if (done == 0 && (n_steps & 1) && chunk > 1 && !(chunk & 1)) chunk -= 1;   // the odd step goes first
+            const bool last = done + chunk == n_steps;
+            for (size_t k = 0; k < n; ++k) MS(k, step_impl(m->slabs[k], chunk, last));
+            done += chunk;
+        }
+        return LB_OK;
+    }
+    // slabs sharing a device share its stream: advance in lock-step, ONE LAUNCH per slab at a time -- a slab's
+    // launch waits in-kernel for what its neighbour's previous launch published, and on one stream that
+    // launch must already be enqueued ahead of it
+    const bool two = tb_kind(tb2_effective_shape(m->slabs[0])) == LB_TB_MARCH;
+    int remaining = n_steps;
+    if (!two || (remaining & 1)) {
+        const int singles = two ? 1 : remaining;
+        for (int i = 0; i < singles; ++i, --remaining)
+            for (size_t k = 0; k < n; ++k) MS(k, step_impl(m->slabs[k], 1, remaining == 1));
+    }
+    for (; remaining > 0; remaining -= 2)
+        for (size_t k = 0; k < n; ++k) MS(k, step_impl(m->slabs[k], 2, remaining == 2));
+    return LB_OK;
+}
+
+int lb_multi_sync(lb_multi *m)
+{
+    if (!m) return LB_ERR_INVALID;
+    int first = LB_OK;
+    for (size_t k = 0; k < m->slabs.size(); ++k) {
+        const int rc = mslab(m, k, lb_sync(m->slabs[k]));
+        if (rc != LB_OK && first == LB_OK) first = rc;
+    }
+    return first;
+}
+
+int lb_multi_download(lb_multi *m, int field, void *host_out)
+{
+    if (!m || !host_out) return mfail(m, LB_ERR_INVALID, "lb_multi_download: null argument");
+    for (size_t k = 0; k < m->slabs.size(); ++k) {       // all copies in flight together, one sync each afterwards
+        lb_sim *s = m->slabs[k];
+        const int eb = (field == LB_FIELD_U || field == LB_FIELD_V) ? s->uv_elem : s->elem;
+        MS(k, download_impl(s, field, (char *)host_out + (size_t)m->x0[k] * eb, (size_t)m->cfg.nx, false));
+    }
+    return lb_multi_sync(m);
+}
+
+int lb_multi_total_mass(lb_multi *m, double *out)
+{
+    if (!m || !out) return LB_ERR_INVALID;
+    long double acc = 0;
+    for (size_t k = 0; k < m->slabs.size(); ++k) { double v = 0; MS(k, lb_total_mass(m->slabs[k], &v)); acc += v; }
+    *out = (double)acc;
+    return LB_OK;
+}
+
+int lb_multi_checksum(lb_multi *m, uint64_t *out)
+{
+    if (!m || !out) return LB_ERR_INVALID;
+    uint64_t acc = 0;
+    for (size_t k = 0; k < m->slabs.size(); ++k) { uint64_t v = 0; MS(k, lb_checksum(m->slabs[k], &v)); acc += v; }
+    *out = acc;
+    return LB_OK;
+}
+
+int64_t lb_multi_launch_count(const lb_multi *m)
+{
+    int64_t n = 0;
+    if (m) for (const lb_sim *s : m->slabs) n += s->launches;
+    return n;
 }
 
 }  // extern "C"

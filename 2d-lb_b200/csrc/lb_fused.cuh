@@ -39,22 +39,32 @@ struct StepParams {
     void *rho, *u, *v;        // [ny][pitch]
     Consts<float> cf;         // per-launch constants, precomputed on the host in both types
     Consts<double> cd;
-    // x-slab halo (EDGE_HALO): ghost columns are [3][ny+2] (slot, y+1)
-    const void *ghost_w;      // populations 1,5,8 of the west neighbour's last column (read)
-    const void *ghost_e;      // populations 3,6,7 of the east neighbour's first column (read)
-    void *out_w;              // west neighbour's east ghost column (write 3,6,7 of my column 0)
-    void *out_e;              // east neighbour's west ghost column (write 1,5,8 of my column nx-1)
+    Consts<F2> c2;            // cf with both lanes of every packed register set (lb_f32x2.cuh)
+    // x-slab halo (EDGE_HALO): ghost columns are [GHOST_SLOTS][ny+2] (slot, y+1), all values post-collision:
+    //   slots 0-2  the three populations entering my slab from the neighbour's boundary column
+    //              (1,5,8 of the west neighbour's last column / 3,6,7 of the east neighbour's first column)
+    //   slots 3-5  populations 0,2,4 of that same column                      } what a two-update launch needs on
+    //   slots 6-8  the same three entering populations, one column further in } top, to advance the neighbour's
+    //                                                                           boundary column by one level itself
+    const void *ghost_w;      // filled by the west neighbour (read)
+    const void *ghost_e;      // filled by the east neighbour (read)
+    void *out_w;              // west neighbour's east ghost column (written from my columns 0, 1)
+    void *out_e;              // east neighbour's west ghost column (written from my columns nx-1, nx-2)
+    const uint8_t *gmask_w, *gmask_e;   // [ny] obstacle mask of the neighbours' boundary columns (nullptr: none)
     unsigned int *flag_w_local, *flag_e_local;     // polled: neighbour's data for this step is in
     unsigned int *flag_w_remote, *flag_e_remote;   // published: my data for the next step is out
     unsigned int *done_w, *done_e;                 // edge-tile completion counters (local)
     unsigned int *error_word;                      // set on hand-shake timeout
+    unsigned long long halo_timeout_ns;            // bound of one flag wait (lb_set_halo_timeout)
     unsigned int step_id;                          // flag value that must be visible before reading ghosts
     int tiles_x, tiles_y;
     int edge_first;           // 1-D grid with the two edge tile columns first (halo overlap); else 2-D/3-D grid
     int edge_rows;            // rows per warp in an edge tile (tall tiles: few participants in the hand-shake)
     int edge_tiles_y;         // edge tiles per side
     int y_begin, y_end;       // rows this launch updates (whole lattice: 0, ny); band launches of lb_step_banded
+    int seg_rows;             // marching kernel (lb_march.cuh): rows per segment
 };
+enum : int { GHOST_SLOTS = 9 };
 
 template <typename T> __device__ __forceinline__ const Consts<T> &consts_in(const StepParams &p);
 template <> __device__ __forceinline__ const Consts<float> &consts_in<float>(const StepParams &p) { return p.cf; }
@@ -145,17 +155,28 @@ __device__ __forceinline__ unsigned long long globaltimer_ns()
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
-// Wait (bounded: 2 s) until *flag >= want.  One thread polls, the CTA follows through a barrier.
-__device__ __forceinline__ void wait_flag(const unsigned int *flag, unsigned int want, unsigned int *error_word)
+// Wait (bounded by `timeout_ns`) until *flag >= want.  One thread polls, the CTA follows through a barrier.
+// Returns false -- for every thread of the CTA -- when the wait timed out now or an earlier wait of this
+// handle did: the caller then skips its tile, so that nothing computed from stale ghost columns is stored,
+// published to a neighbour or released by a flag.  The fault stays local; lb_sync reports LB_ERR_HALO, and
+// the neighbours, which never see this slab's flag, time out in turn.  lb_halo_prime clears the error.
+__device__ __forceinline__ bool wait_flag(const unsigned int *flag, unsigned int want, unsigned int *error_word,
+                                          unsigned long long timeout_ns)
 {
+    __shared__ unsigned int wait_failed;
     if (threadIdx.x == 0) {
+        unsigned int failed = *reinterpret_cast<volatile unsigned int *>(error_word);
         const unsigned long long t0 = globaltimer_ns();
-        while ((int)(ld_acquire_sys(flag) - want) < 0) {
-            if (globaltimer_ns() - t0 > 2000000000ull) { atomicExch(error_word, 1u); break; }
+        while (!failed && (int)(ld_acquire_sys(flag) - want) < 0) {
+            if (globaltimer_ns() - t0 > timeout_ns) { atomicExch(error_word, 1u); failed = 1u; break; }
             __nanosleep(64);
         }
+        wait_failed = failed;
     }
     __syncthreads();
+    const bool ok = wait_failed == 0u;
+    __syncthreads();                                   // the shared word may be reused by the CTA's second wait
+    return ok;
 }
 
 // ---- everything after the nine shifted populations of a thread's V nodes are in registers:
@@ -166,7 +187,7 @@ __device__ __forceinline__ void wait_flag(const unsigned int *flag, unsigned int
 //      came from a shared-memory tile whose rim already holds the wrapped / ghost values, so the slab-edge
 //      fix-up from `src` is skipped (phase 2).
 enum : int { ROW_FULL = 0, ROW_TO_REGISTERS = 1, ROW_FROM_TILE = 2 };
-template <typename T, int V, int MATH, int STP, int MODEL, int ROLE = ROW_FULL>
+template <typename T, int V, int MATH, int STP, int MODEL, int ROLE = ROW_FULL, bool PACKED = false>
 __device__ __forceinline__ void finish_row(const StepParams &p, const Consts<T> &c, Pack<T, V> (&q)[9],
                                            const T *__restrict__ src, T *__restrict__ dst,
                                            int x0, int span0, int y, int ym, int yp)
@@ -305,6 +326,20 @@ __device__ __forceinline__ void finish_row(const StepParams &p, const Consts<T> 
 #pragma unroll
             for (int j = 0; j < 9; ++j) q[j].v[e] = g[j];
         }
+    } else if constexpr (PACKED && sizeof(T) == 4 && V % 2 == 0 && MODEL == MODEL_D2Q9) {
+        // two nodes per instruction: FADD2 / FMUL2 / FFMA2, each lane rounded like the scalar code above
+#pragma unroll
+        for (int e = 0; e < V; e += 2) {
+            F2 g[9], r2, u2, v2;
+#pragma unroll
+            for (int j = 0; j < 9; ++j) g[j] = F2((float)q[j].v[e], (float)q[j].v[e + 1]);
+            collide_node<F2, MATH, MODEL>(p.c2, g, r2, u2, v2, false);
+#pragma unroll
+            for (int j = 0; j < 9; ++j) { q[j].v[e] = (T)g[j].lo(); q[j].v[e + 1] = (T)g[j].hi(); }
+            mrho.v[e] = (T)r2.lo(); mrho.v[e + 1] = (T)r2.hi();
+            mu.v[e] = (T)u2.lo(); mu.v[e + 1] = (T)u2.hi();
+            mv.v[e] = (T)v2.lo(); mv.v[e + 1] = (T)v2.hi();
+        }
     } else {
 #pragma unroll
         for (int e = 0; e < V; ++e) {
@@ -344,23 +379,29 @@ __device__ __forceinline__ void finish_row(const StepParams &p, const Consts<T> 
         }
     }
 
-    // --- publish my boundary columns into the neighbours' ghost columns ---
-    if (!(has_west || has_east)) return;
-    if (has_west && p.west == EDGE_HALO) {
-        T *ow = static_cast<T *>(p.out_w);
-        ow[0 * (ny + 2) + (y + 1)] = q[3].v[0];
-        ow[1 * (ny + 2) + (y + 1)] = q[6].v[0];
-        ow[2 * (ny + 2) + (y + 1)] = q[7].v[0];
-    }
-    if (has_east && p.east == EDGE_HALO) {
-        T *oe = static_cast<T *>(p.out_e);
+    // --- publish my two outermost columns into the neighbours' ghost columns (layout: StepParams) ---
+    const int gs = ny + 2;                            // ghost slot stride
+    if (p.west == EDGE_HALO && x0 <= 1) {
+        T *ow = static_cast<T *>(p.out_w) + (y + 1);
 #pragma unroll
-        for (int e = 0; e < V; ++e)
-            if (e == el_east) {
-                oe[0 * (ny + 2) + (y + 1)] = q[1].v[e];
-                oe[1 * (ny + 2) + (y + 1)] = q[5].v[e];
-                oe[2 * (ny + 2) + (y + 1)] = q[8].v[e];
+        for (int e = 0; e < V; ++e) {
+            if (x0 + e == 0) {
+                ow[0 * gs] = q[3].v[e]; ow[1 * gs] = q[6].v[e]; ow[2 * gs] = q[7].v[e];
+                ow[3 * gs] = q[0].v[e]; ow[4 * gs] = q[2].v[e]; ow[5 * gs] = q[4].v[e];
             }
+            if (x0 + e == 1) { ow[6 * gs] = q[3].v[e]; ow[7 * gs] = q[6].v[e]; ow[8 * gs] = q[7].v[e]; }
+        }
+    }
+    if (p.east == EDGE_HALO && x0 + V > nx - 2 && x0 < nx) {
+        T *oe = static_cast<T *>(p.out_e) + (y + 1);
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+            if (x0 + e == nx - 1) {
+                oe[0 * gs] = q[1].v[e]; oe[1 * gs] = q[5].v[e]; oe[2 * gs] = q[8].v[e];
+                oe[3 * gs] = q[0].v[e]; oe[4 * gs] = q[2].v[e]; oe[5 * gs] = q[4].v[e];
+            }
+            if (x0 + e == nx - 2) { oe[6 * gs] = q[1].v[e]; oe[7 * gs] = q[5].v[e]; oe[8 * gs] = q[8].v[e]; }
+        }
     }
 }
 
@@ -397,8 +438,8 @@ __global__ void __launch_bounds__(32 * WX * WY, MINB) fused_step_kernel(const St
     }
     const bool halo_w = (p.west == EDGE_HALO) && (bx == 0);
     const bool halo_e = (p.east == EDGE_HALO) && (bx == p.tiles_x - 1);
-    if (halo_w) wait_flag(p.flag_w_local, p.step_id, p.error_word);
-    if (halo_e) wait_flag(p.flag_e_local, p.step_id, p.error_word);
+    if (halo_w && !wait_flag(p.flag_w_local, p.step_id, p.error_word, p.halo_timeout_ns)) return;
+    if (halo_e && !wait_flag(p.flag_e_local, p.step_id, p.error_word, p.halo_timeout_ns)) return;
 
     const int span0 = (bx * WX + wx) * SPAN;          // first cell of this warp's span
     const int x0 = span0 + lane * V;                  // first cell of this thread

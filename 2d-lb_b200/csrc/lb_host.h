@@ -1,0 +1,40 @@
+// Host-side tables of compiled kernel instantiations, shared between the translation units of the library:
+//   lb_k_step.cu   the one-update kernel's tile variants (lb_fused.cuh, lb_tma.cuh)
+//   lb_k_march.cu  the two-update kernels (lb_march.cuh; with -DLB_EXPERIMENTS also the round-1 shared-memory
+//                  tiles of lb_tb2.cuh / lb_tb2v.cuh)
+//   lb_d2q9.cu     the C ABI, which picks from these tables
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "lb_fused.cuh"
+#include "lb_tb2.cuh"
+
+struct LbVariant {
+    const char *name;
+    int dtype, math, model, V, WX, WY, R;
+    void (*launch)(const lb::StepParams &, cudaStream_t);
+    bool is_default;
+    void (*launch_tma)(const CUtensorMap &, const CUtensorMap &, const lb::StepParams &, cudaStream_t);   // non-null: TMA-staged kernel
+    int tma_ty;                                                                                       // its box height
+};
+extern const LbVariant g_variants[];
+extern const int g_nvariants;
+
+// two updates per launch
+enum LbTbKind { LB_TB_OFF = 0, LB_TB_MARCH = 1, LB_TB_ROWS = 2, LB_TB_CELLS = 3 };
+struct LbTbShape {
+    const char *name;
+    int kind;
+    int seg_rows;              // LB_TB_MARCH: rows per segment
+    int nw;                    // LB_TB_MARCH: warps (= strips) per CTA
+    int bx, by, nt;            // LB_TB_ROWS / LB_TB_CELLS: tile geometry (round-1 kernels, -DLB_EXPERIMENTS)
+    // [dtype][math]; LB_TB_MARCH and LB_TB_ROWS take StepParams, LB_TB_CELLS takes Tb2Params
+    void (*launch_march[2][2])(const lb::StepParams &, cudaStream_t);
+    void (*launch_rows[2][2])(const lb::StepParams &, dim3, size_t, cudaStream_t);
+    void (*launch_cells[2][2])(const lb::Tb2Params &, dim3, size_t, cudaStream_t);
+};
+extern const LbTbShape g_tb_shapes[];
+extern const int g_ntb;
+extern const char *const g_tb_auto_f32;   // names of the shapes lb_step picks on its own
+extern const char *const g_tb_auto_f64;

@@ -1,0 +1,88 @@
+// Instantiations of the two-update kernels.  Default build: the marching kernel (lb_march.cuh).
+// -DLB_EXPERIMENTS adds the round-1 shared-memory tiles (lb_tb2v.cuh row-per-warp, lb_tb2.cuh cell-per-thread),
+// kept for A/B measurements (profiles/README.md section 7).
+#include "lb_host.h"
+#include "lb_march.cuh"
+#ifdef LB_EXPERIMENTS
+#include "lb_tb2v.cuh"
+#endif
+
+using namespace lb;
+
+template <typename T, int V, int MATH, int NW, int MINB, bool PACKED>
+static void launch_march(const StepParams &p_in, cudaStream_t st)
+{
+    StepParams p = p_in;
+    constexpr int SPAN = 32 * V;
+    const int nstrips = p.pitch / SPAN;                // the pitch is a multiple of SPAN
+    p.tiles_x = (nstrips + NW - 1) / NW;
+    p.tiles_y = (p.ny + p.seg_rows - 1) / p.seg_rows;  // segments
+    p.edge_tiles_y = p.tiles_y;                        // one edge CTA per segment and side
+    const unsigned grid = (unsigned)p.tiles_x * (unsigned)p.tiles_y;
+    fused_march_kernel<T, V, MATH, NW, MINB, PACKED><<<grid, 32 * NW, 0, st>>>(p);
+}
+
+// name: march.w<warps per CTA>b<CTAs per SM>[.scalar].s<rows per segment>
+#define MARCH(NW, MINB, PACKED, PN, S)                                                                         \
+    {"march.w" #NW "b" #MINB PN ".s" #S, LB_TB_MARCH, S, NW, 0, 0, 0,                                           \
+     {{launch_march<float, 4, MATH_STRICT, NW, MINB, PACKED>, launch_march<float, 4, MATH_FAST, NW, MINB, PACKED>},   \
+      {launch_march<double, 2, MATH_STRICT, NW, MINB, false>, launch_march<double, 2, MATH_FAST, NW, MINB, false>}}, \
+     {{nullptr, nullptr}, {nullptr, nullptr}}, {{nullptr, nullptr}, {nullptr, nullptr}}}
+#define MARCH_S(NW, MINB, PACKED, PN) MARCH(NW, MINB, PACKED, PN, 32), MARCH(NW, MINB, PACKED, PN, 64), MARCH(NW, MINB, PACKED, PN, 128), MARCH(NW, MINB, PACKED, PN, 256)
+
+#ifdef LB_EXPERIMENTS
+template <typename T, int MATH, int BX, int BY, int NT, int MINB>
+static void launch_tb2(const Tb2Params &p, dim3 grid, size_t smem, cudaStream_t st)
+{
+    static bool configured[64] = {};                  // one opt-in per instantiation and device (dynamic smem > 48 KB)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!configured[dev & 63]) {
+        cudaFuncSetAttribute(fused_two_step_kernel<T, MATH, BX, BY, NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured[dev & 63] = true;
+    }
+    fused_two_step_kernel<T, MATH, BX, BY, NT, MINB><<<grid, NT, smem, st>>>(p);
+}
+template <typename T, int V, int MATH, int BY, int NW, int MINB>
+static void launch_tb2v(const StepParams &p, dim3 grid, size_t smem, cudaStream_t st)
+{
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!configured[dev & 63]) {
+        cudaFuncSetAttribute(fused_two_step_v2_kernel<T, V, MATH, BY, NW, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured[dev & 63] = true;
+    }
+    fused_two_step_v2_kernel<T, V, MATH, BY, NW, MINB><<<grid, 32 * NW, smem, st>>>(p);
+}
+#define TB2(BX, BY, NT, MINB)                                                                          \
+    {#BX "x" #BY ".t" #NT, LB_TB_CELLS, 0, 0, BX, BY, NT, {{nullptr, nullptr}, {nullptr, nullptr}},         \
+     {{nullptr, nullptr}, {nullptr, nullptr}},                                                          \
+     {{launch_tb2<float, MATH_STRICT, BX, BY, NT, MINB>, launch_tb2<float, MATH_FAST, BX, BY, NT, MINB>},  \
+      {launch_tb2<double, MATH_STRICT, BX, BY, NT, MINB>, launch_tb2<double, MATH_FAST, BX, BY, NT, MINB>}}}
+#define TB2V(BY, NW, MINB)                                                                             \
+    {"rows" #BY ".w" #NW, LB_TB_ROWS, 0, 0, 0, BY, 32 * NW, {{nullptr, nullptr}, {nullptr, nullptr}},       \
+     {{launch_tb2v<float, 4, MATH_STRICT, BY, NW, MINB>, launch_tb2v<float, 4, MATH_FAST, BY, NW, MINB>},  \
+      {launch_tb2v<double, 2, MATH_STRICT, BY, NW, MINB>, launch_tb2v<double, 2, MATH_FAST, BY, NW, MINB>}}, \
+     {{nullptr, nullptr}, {nullptr, nullptr}}}
+#endif
+
+const LbTbShape g_tb_shapes[] = {
+    {"off", LB_TB_OFF, 0, 0, 0, 0, 0, {{nullptr, nullptr}, {nullptr, nullptr}}, {{nullptr, nullptr}, {nullptr, nullptr}}, {{nullptr, nullptr}, {nullptr, nullptr}}},
+    MARCH_S(4, 4, true, ""),
+    MARCH_S(4, 3, true, ""),
+    MARCH_S(4, 5, true, ""),
+    MARCH_S(8, 2, true, ""),
+    MARCH_S(2, 8, true, ""),
+    MARCH_S(4, 4, false, ".scalar"),
+#ifdef LB_EXPERIMENTS
+    TB2(128, 16, 256, 2),
+    TB2(128, 8, 256, 4),
+    TB2V(6, 8, 3),
+    TB2V(14, 8, 2),
+    TB2V(6, 4, 6),
+#endif
+};
+const int g_ntb = (int)(sizeof(g_tb_shapes) / sizeof(g_tb_shapes[0]));
+const char *const g_tb_auto_f32 = "march.w4b4.s64";
+const char *const g_tb_auto_f64 = "march.w4b4.s64";

@@ -89,7 +89,7 @@ __device__ __forceinline__ void oc_velocity_bc(const OcParams &p, int x, int y, 
 // start of a run: closure + bounce-back of rows 1..ny-2, in place (rows 0 and ny-1: oc_rows_kernel)
 __global__ void oc_prestream_kernel(OcParams p, float *f)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = lb_grid_row();
     if (x >= p.nx || y < 1 || y >= p.ny - 1) return;
     const bool solid = p.mask && p.mask[(long long)y * p.mask_pitch + x] == 1;
     if (!solid && x != 0 && x != p.nx - 1) return;
@@ -128,7 +128,7 @@ __global__ void oc_rows_kernel(int nx, int ny, int pitch, long long plane, float
 __global__ void oc_stage_move_kernel(int nx, int ny, int pitch, long long plane, const float *src, float *dst,
                                      const float *frozen)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = lb_grid_row();
     if (x >= nx || y >= ny) return;
     const int lx = nx - 1, ly = ny - 1;
     const long long i = (long long)y * pitch + x;
@@ -152,7 +152,7 @@ __global__ void oc_stage_move_kernel(int nx, int ny, int pitch, long long plane,
 // update_hydro_PeriodicBC_VelocityInlet (D2Q9.cl:323-374) [+ set_zero_velocity_in_obstacle with a mask]
 __global__ void oc_stage_hydro_kernel(OcParams p, const float *f)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = lb_grid_row();
     if (x >= p.nx || y >= p.ny) return;
     const int lx = p.nx - 1, ly = p.ny - 1;
     const long long i = (long long)y * p.pitch + x;

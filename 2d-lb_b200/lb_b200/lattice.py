@@ -30,6 +30,35 @@ def _ptr(a):
     return ct.c_void_p(a.ctypes.data)
 
 
+def make_config(nx, ny, omega, inlet_rho=1.0, outlet_rho=1.0, bc="pipe", dtype=np.float32, math="strict", device=0,
+                zero_obstacle_velocity=False, global_nx=None, x_offset=0, west_edge=None, east_edge=None, stream=None,
+                scheme="opencl", model="d2q9", u_west=0.0, u_east=0.0):
+    """The lb_config of include/lb_d2q9.h for one slab (or, for lb_multi_create, for the whole lattice)."""
+    dtype = np.dtype(dtype)
+    if dtype not in (np.dtype(np.float32), np.dtype(np.float64)):
+        raise ValueError("dtype must be float32 or float64")
+    default_edge = "wrap" if bc == "periodic" else "boundary"
+    cfg = N.LBConfig()
+    cfg.struct_size = ct.sizeof(N.LBConfig)
+    cfg.device = int(device)
+    cfg.nx, cfg.ny = int(nx), int(ny)
+    cfg.dtype = N.F32 if dtype == np.float32 else N.F64
+    cfg.bc = _BC[bc]
+    cfg.math = _MATH[math]
+    cfg.zero_obstacle_velocity = int(bool(zero_obstacle_velocity))
+    cfg.global_nx = int(global_nx if global_nx is not None else nx)
+    cfg.x_offset = int(x_offset)
+    cfg.west_edge = _EDGE[west_edge or default_edge]
+    cfg.east_edge = _EDGE[east_edge or default_edge]
+    cfg.scheme = _SCHEME[scheme]
+    cfg.model = {"d2q9": N.MODEL_D2Q9, "d2q9i": N.MODEL_D2Q9I}[model]
+    cfg.omega, cfg.inlet_rho, cfg.outlet_rho = float(omega), float(inlet_rho), float(outlet_rho)
+    cfg.cs2, cfg.cs22, cfg.two_cs4 = float(cs2), float(cs22), float(two_cs4)
+    cfg.u_west, cfg.u_east = float(u_west), float(u_east)
+    cfg.stream = ct.c_void_p(stream) if stream else None
+    return cfg
+
+
 class Lattice:
     """D2Q9 BGK lattice on one CUDA device.
 
@@ -59,29 +88,12 @@ class Lattice:
         self.scheme = scheme
         self.nx, self.ny = int(nx), int(ny)
         self.dtype = np.dtype(dtype)
-        if self.dtype not in (np.dtype(np.float32), np.dtype(np.float64)):
-            raise ValueError("dtype must be float32 or float64")
         self.bc, self.math = bc, math
-        default_edge = "wrap" if bc == "periodic" else "boundary"
-        cfg = N.LBConfig()
-        cfg.struct_size = ct.sizeof(N.LBConfig)
-        cfg.device = int(device)
-        cfg.nx, cfg.ny = self.nx, self.ny
-        cfg.dtype = N.F32 if self.dtype == np.float32 else N.F64
-        cfg.bc = _BC[bc]
-        cfg.math = _MATH[math]
-        cfg.zero_obstacle_velocity = int(bool(zero_obstacle_velocity))
-        cfg.global_nx = int(global_nx if global_nx is not None else nx)
-        cfg.x_offset = int(x_offset)
-        cfg.west_edge = _EDGE[west_edge or default_edge]
-        cfg.east_edge = _EDGE[east_edge or default_edge]
-        cfg.scheme = _SCHEME[scheme]
-        cfg.model = {"d2q9": N.MODEL_D2Q9, "d2q9i": N.MODEL_D2Q9I}[model]
+        cfg = make_config(nx, ny, omega, inlet_rho, outlet_rho, bc=bc, dtype=dtype, math=math, device=device,
+                          zero_obstacle_velocity=zero_obstacle_velocity, global_nx=global_nx, x_offset=x_offset,
+                          west_edge=west_edge, east_edge=east_edge, stream=stream, scheme=scheme, model=model,
+                          u_west=u_west, u_east=u_east)
         self.model = model
-        cfg.omega, cfg.inlet_rho, cfg.outlet_rho = float(omega), float(inlet_rho), float(outlet_rho)
-        cfg.cs2, cfg.cs22, cfg.two_cs4 = float(cs2), float(cs22), float(two_cs4)
-        cfg.u_west, cfg.u_east = float(u_west), float(u_east)
-        cfg.stream = ct.c_void_p(stream) if stream else None
         self.cfg = cfg
         self.omega, self.inlet_rho, self.outlet_rho = cfg.omega, cfg.inlet_rho, cfg.outlet_rho
         self.device = cfg.device
@@ -128,7 +140,7 @@ class Lattice:
         m = np.asarray(mask)
         if m.shape != (self.ny, self.nx):
             raise ValueError(f"mask must have shape (ny, nx) = {(self.ny, self.nx)}, got {m.shape}")
-        m = np.ascontiguousarray(m, dtype=np.uint8)
+        m = np.ascontiguousarray(m == 1, dtype=np.uint8)     # solid <=> exactly 1 (D2Q9.cl:410), whatever the dtype
         self._call("lb_set_mask", _ptr(m), 1)
 
     def upload_f(self, f):
@@ -227,17 +239,10 @@ class Lattice:
         self._call("lb_total_mass", ct.byref(out))
         return out.value
 
-    def run_banded(self, n, band_rows, depth, sync=True):
-        """run(n) with the steps issued `depth` at a time as skewed row-band launches (L2-level temporal
-        blocking, experimental).  Same bits as run(n)."""
-        self._call("lb_step_banded", int(n), int(band_rows), int(depth))
-        if sync:
-            self.sync()
-
     def set_temporal_blocking(self, shape):
-        """Two lattice updates per pass through HBM (csrc/lb_tb2*.cuh): `shape` is 'auto' / -1 (default:
-        the measured-best tile on large lattices), 'off' / 0, a tile index or a tile name such as
-        'rows14.w8'.  Bit-identical results; single-slab 'opencl' scheme only."""
+        """Two lattice updates per pass through HBM (csrc/lb_march.cuh): `shape` is 'auto' / -1 (default:
+        the measured-best shape on large lattices), 'off' / 0, a shape index or a name such as
+        'march.w4b4.s64'.  Bit-identical results; 'opencl' scheme, single slabs and halo-connected slabs."""
         if isinstance(shape, str):
             if shape == "auto":
                 shape = -1
@@ -301,6 +306,9 @@ class Lattice:
     def halo_prime(self):
         self._call("lb_halo_prime")
 
+    def set_halo_timeout(self, seconds):
+        self._call("lb_set_halo_timeout", float(seconds))
+
 
 def split_slabs(global_nx, parts):
     """Column ranges [(x_offset, nx), ...] of an x-slab decomposition into `parts` slabs.
@@ -328,57 +336,78 @@ def slab_edges(rank, parts, bc):
     return ("boundary" if rank == 0 else "halo"), ("boundary" if rank == parts - 1 else "halo")
 
 
-class LocalSlabs:
-    """`parts` x-slabs of one lattice living in ONE process, with the same interface as `Lattice`
-    (device-layout global arrays in, global arrays out).
+class _BorrowedSlab(Lattice):
+    """One slab of an lb_multi handle, seen through the single-slab interface (tuning / diagnostics).  The
+    multi handle owns it: closing this view frees nothing."""
 
-    * several slabs on ONE device ("virtual ranks"): they share a stream and advance in lock-step,
-      one step at a time, so the flag hand-shake of the fused kernel is always already satisfied
-      when a kernel starts.  Used to prove that the decomposition is arithmetic-neutral.
-    * one slab per DEVICE (`devices=[0, 1, ...]`): every slab has its own stream; steps are enqueued
-      asynchronously in bounded chunks, round-robin over the slabs, and the kernels synchronise
-      among themselves through the peer-memory flags -- the single-process multi-GPU path behind
-      `Pipe_Flow(..., devices=[...])`.
+    def __init__(self, handle, cfg_like, nx, ny, dtype, scheme):
+        self._h = handle
+        self.nx, self.ny, self.dtype, self.scheme = nx, ny, np.dtype(dtype), scheme
+        self.cfg = cfg_like
+        self._stream_owner = None
+
+    def close(self):
+        self._h = None
+
+
+class LocalSlabs:
+    """`parts` x-slabs of one lattice in ONE process, with the same interface as `Lattice` (device-layout
+    GLOBAL arrays in, global arrays out).  A thin caller of the C library's multi-device handle (lb_multi_*,
+    include/lb_d2q9.h), which owns the slabs, their streams and peer mappings, keeps the ghost columns primed
+    and runs the step loop:
+
+    * one slab per DEVICE (`devices=[0, 1, ...]`): the slabs advance asynchronously and synchronise among
+      themselves through the peer-memory flags -- the single-process multi-GPU path behind
+      `Pipe_Flow(..., devices=[...])`;
+    * several slabs on ONE device ("virtual ranks"): they share a stream and advance in lock-step, one launch
+      at a time.  Used to prove that the decomposition is arithmetic-neutral.
     """
 
-    CHUNK = 32      # steps enqueued per slab before moving to the next one (bounds launch-queue depth)
-
     def __init__(self, global_nx, ny, parts=None, devices=None, **kw):
+        self._m = None
         if parts is None:
             parts = len(devices)
         self.global_nx, self.ny, self.parts = int(global_nx), int(ny), int(parts)
         self.nx = self.global_nx
         self.bc = kw.get("bc", "pipe")
         self.scheme = kw.get("scheme", "opencl")
-        self.ranges = split_slabs(global_nx, parts)
         devices = list(devices) if devices else [kw.pop("device", 0)] * parts
         kw.pop("device", None)
         if len(devices) != parts:
             raise ValueError("one device per slab")
         self.devices = devices
-        self.concurrent = len(set(devices)) == parts and parts > 1
+        self.ranges = split_slabs(global_nx, parts)
+        cfg = make_config(global_nx, ny, **kw)
+        self.cfg = cfg
+        self.dtype = np.dtype(kw.get("dtype", np.float32))
+        self.uv_dtype = np.dtype(np.float64) if self.scheme in ("cython", "cython_old") else self.dtype
+        h = ct.c_void_p()
+        N.check_multi(N.lib().lb_multi_create(ct.byref(cfg), self.parts, (ct.c_int * self.parts)(*devices), ct.byref(h)))
+        self._m = h
         self.slabs = []
-        streams = {}          # one stream per device, shared by the slabs that live there
-        for r, (x0, w) in enumerate(self.ranges):
-            we, ee = slab_edges(r, parts, self.bc)
-            lender = streams.get(devices[r])
-            s = Lattice(w, ny, global_nx=global_nx, x_offset=x0, west_edge=we, east_edge=ee,
-                        device=devices[r], stream=lender.stream_ptr if lender else None, **kw)
-            s._stream_owner = lender       # the lender (which owns the stream) must outlive the borrower
-            streams.setdefault(devices[r], s)
-            self.slabs.append(s)
-        self.dtype = self.slabs[0].dtype
-        if parts > 1:
-            for r, s in enumerate(self.slabs):
-                if s.cfg.west_edge == N.EDGE_HALO:
-                    s.halo_connect_local("west", self.slabs[(r - 1) % parts])
-                if s.cfg.east_edge == N.EDGE_HALO:
-                    s.halo_connect_local("east", self.slabs[(r + 1) % parts])
-        self._primed = False
+        for k in range(self.parts):
+            sh, x0, w = ct.c_void_p(), ct.c_int(), ct.c_int()
+            self._call("lb_multi_slab", k, ct.byref(sh), ct.byref(x0), ct.byref(w))
+            assert (x0.value, w.value) == self.ranges[k]
+            self.slabs.append(_BorrowedSlab(sh, cfg, w.value, self.ny, self.dtype, self.scheme))
+
+    def _call(self, fn, *args):
+        if self._m is None:
+            raise N.LBError(-3, "lattice is closed")
+        N.check_multi(getattr(N.lib(), fn)(self._m, *args), self._m)
 
     def close(self):
-        for s in reversed(self.slabs):     # borrowers of a shared stream first, its owner last
-            s.close()
+        if self._m is not None:
+            N.lib().lb_multi_destroy(self._m)      # drains every slab before freeing any arena
+            self._m = None
+            for s in self.slabs:
+                s.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def __enter__(self):
         return self
@@ -386,55 +415,60 @@ class LocalSlabs:
     def __exit__(self, *exc):
         self.close()
 
-    def _each(self, a):
-        for s, (x0, w) in zip(self.slabs, self.ranges):
-            yield s, (None if a is None else np.ascontiguousarray(a[..., x0:x0 + w]))
+    def field_dtype(self, field):
+        return self.uv_dtype if field in ("u", "v") else self.dtype
 
     # -- uploads (global device-layout arrays) -------------------------------------------------------
     def set_mask(self, mask):
-        for s, part in self._each(None if mask is None else np.asarray(mask)):
-            s.set_mask(part)
+        if mask is None:
+            self._call("lb_multi_set_mask", None, 1)
+            return
+        m = np.asarray(mask)
+        if m.shape != (self.ny, self.nx):
+            raise ValueError(f"mask must have shape (ny, nx) = {(self.ny, self.nx)}, got {m.shape}")
+        m = np.ascontiguousarray(m == 1, dtype=np.uint8)
+        self._call("lb_multi_set_mask", _ptr(m), 1)
 
     def upload_f(self, f):
-        for s, part in self._each(np.asarray(f)):
-            s.upload_f(part)
-        self.prime()
+        a = np.ascontiguousarray(f, dtype=self.dtype)
+        if a.shape != (9, self.ny, self.nx):
+            raise ValueError(f"f must have shape (9, ny, nx) = {(9, self.ny, self.nx)}, got {a.shape}")
+        self._call("lb_multi_upload_f", _ptr(a))
 
     def upload_moments(self, rho=None, u=None, v=None):
-        parts = [list(self._each(None if a is None else np.asarray(a))) for a in (rho, u, v)]
-        for k, s in enumerate(self.slabs):
-            s.upload_moments(parts[0][k][1], parts[1][k][1], parts[2][k][1])
+        arrs = []
+        for k, a in enumerate((rho, u, v)):
+            arrs.append(None if a is None else np.ascontiguousarray(a, dtype=self.dtype if k == 0 else self.uv_dtype))
+            if arrs[-1] is not None and arrs[-1].shape != (self.ny, self.nx):
+                raise ValueError("moment fields must have shape (ny, nx)")
+        self._call("lb_multi_upload_moments", *[(_ptr(a) if a is not None else None) for a in arrs])
 
     def prime(self):
-        """Publish every slab's boundary columns to its neighbours (after any change of f)."""
-        for s in self.slabs:
-            s.sync()
-        for s in self.slabs:
-            s.halo_prime()
-        self._primed = True
+        """Publish every slab's boundary columns to its neighbours (only needed after changing a slab's state
+        through `slabs[k]`; uploads and initialisers do it themselves)."""
+        self._call("lb_multi_prime")
 
     # -- hot path ---------------------------------------------------------------------------------
     def run(self, n, sync=True):
-        n = int(n)
-        if self.parts > 1 and not self._primed:
-            self.prime()
-        if self.concurrent:
-            done = 0
-            while done < n:
-                chunk = min(self.CHUNK, n - done)
-                for s in self.slabs:
-                    s.run(chunk, sync=False)
-                done += chunk
-        else:
-            for _ in range(n):
-                for s in self.slabs:
-                    s.run(1, sync=False)
+        self._call("lb_multi_step", int(n))
         if sync:
             self.sync()
 
     def sync(self):
-        for s in self.slabs:
-            s.sync()
+        self._call("lb_multi_sync")
+
+    def set_temporal_blocking(self, shape):
+        if isinstance(shape, str):
+            if shape == "auto":
+                shape = -1
+            else:
+                names = [N.lib().lb_tb2_shape_name(k).decode() for k in range(N.lib().lb_tb2_shape_count())]
+                shape = names.index(shape)
+        self._call("lb_multi_set_temporal_blocking", int(shape))
+
+    @property
+    def temporal_blocking(self):
+        return N.lib().lb_tb2_shape_name(N.lib().lb_multi_temporal_blocking(self._m)).decode()
 
     # -- stages that need no halo -----------------------------------------------------------------
     def update_feq(self):
@@ -452,30 +486,35 @@ class LocalSlabs:
 
     # -- readback ------------------------------------------------------------------------------------
     def download(self, field, out=None):
-        whole = np.concatenate([s.download(field) for s in self.slabs], axis=-1)
+        shape = (9, self.ny, self.nx) if field in ("f", "feq") else (self.ny, self.nx)
+        dt = self.field_dtype(field)
         if out is None:
-            return whole
-        out[...] = whole
+            out = np.empty(shape, dtype=dt)
+        elif out.shape != shape or out.dtype != dt or not out.flags.c_contiguous:
+            raise ValueError("out must be a C-contiguous array of the field's shape and dtype")
+        self._call("lb_multi_download", _FIELD[field], _ptr(out))
         return out
 
     def fields(self):
         return {k: self.download(k) for k in ("f", "feq", "rho", "u", "v")}
 
     def total_mass(self):
-        return sum(s.total_mass() for s in self.slabs)
+        out = ct.c_double()
+        self._call("lb_multi_total_mass", ct.byref(out))
+        return out.value
 
     def checksum(self):
-        return sum(s.checksum() for s in self.slabs) & 0xFFFFFFFFFFFFFFFF
+        out = ct.c_uint64()
+        self._call("lb_multi_checksum", ct.byref(out))
+        return out.value
 
     @property
     def launch_count(self):
-        return sum(s.launch_count for s in self.slabs)
+        return int(N.lib().lb_multi_launch_count(self._m))
 
-    def init_synthetic(self, *a, **k):
-        for s in self.slabs:
-            s.init_synthetic(*a, **k)
-        self.prime()
+    def init_synthetic(self, kind="pipe_ramp", u0=0.0, amplitude=0.0, seed=0):
+        k = {"pipe_ramp": N.SYNTH_PIPE_RAMP, "shear_layers": N.SYNTH_SHEAR_LAYERS}[kind]
+        self._call("lb_multi_init_synthetic", k, float(u0), float(amplitude), ct.c_uint64(int(seed)))
 
-    def set_mask_disk(self, *a):
-        for s in self.slabs:
-            s.set_mask_disk(*a)
+    def set_mask_disk(self, cx, cy, r):
+        self._call("lb_multi_set_mask_disk", float(cx), float(cy), float(r))

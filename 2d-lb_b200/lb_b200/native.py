@@ -18,7 +18,7 @@ WEST, EAST = 0, 1
 EDGE_BOUNDARY, EDGE_WRAP, EDGE_HALO = 0, 1, 2
 SYNTH_PIPE_RAMP, SYNTH_SHEAR_LAYERS = 0, 1
 IPC_HANDLE_BYTES = 64
-ABI_VERSION = 4
+ABI_VERSION = 5
 SCHEME_OPENCL, SCHEME_CYTHON, SCHEME_CYTHON_OLD, SCHEME_OPENCL_OLD = 0, 1, 2, 3
 MODEL_D2Q9, MODEL_D2Q9I = 0, 1
 
@@ -28,9 +28,14 @@ SYMBOLS = [
     "lb_set_mask", "lb_upload_f", "lb_upload_moments", "lb_step", "lb_sync", "lb_download", "lb_download_strided",
     "lb_stage_move", "lb_stage_move_bcs", "lb_stage_update_hydro", "lb_stage_update_feq",
     "lb_stage_collide", "lb_stage_zero_velocity", "lb_init_synthetic", "lb_set_mask_disk",
-    "lb_total_mass", "lb_checksum", "lb_selftest_rcp", "lb_selftest_copy", "lb_set_temporal_blocking", "lb_temporal_blocking", "lb_step_banded", "lb_tb2_shape_count", "lb_tb2_shape_name", "lb_launch_count", "lb_set_variant", "lb_variant_count", "lb_variant_name",
+    "lb_total_mass", "lb_checksum", "lb_selftest_rcp", "lb_selftest_copy", "lb_set_temporal_blocking", "lb_temporal_blocking", "lb_tb2_shape_count", "lb_tb2_shape_name", "lb_launch_count", "lb_set_variant", "lb_variant_count", "lb_variant_name",
     "lb_device_ptr", "lb_stream", "lb_halo_ipc_handle", "lb_halo_connect_ipc", "lb_halo_connect_local",
-    "lb_halo_prime",
+    "lb_halo_prime", "lb_set_halo_timeout",
+    "lb_multi_create", "lb_multi_destroy", "lb_multi_last_error", "lb_multi_slab_count", "lb_multi_slab",
+    "lb_multi_set_mask", "lb_multi_set_mask_disk", "lb_multi_upload_f", "lb_multi_upload_moments",
+    "lb_multi_init_synthetic", "lb_multi_set_temporal_blocking", "lb_multi_temporal_blocking", "lb_multi_prime",
+    "lb_multi_step", "lb_multi_sync", "lb_multi_download", "lb_multi_total_mass", "lb_multi_checksum",
+    "lb_multi_launch_count",
 ]
 
 
@@ -90,7 +95,6 @@ def _declare(lib):
         "lb_selftest_copy": (i, [vp, i, ct.POINTER(ct.c_double)]),
         "lb_set_temporal_blocking": (i, [vp, i]),
         "lb_temporal_blocking": (i, [vp]),
-        "lb_step_banded": (i, [vp, i, i, i]),
         "lb_tb2_shape_count": (i, []),
         "lb_tb2_shape_name": (ct.c_char_p, [i]),
         "lb_launch_count": (ct.c_int64, [vp]),
@@ -103,6 +107,26 @@ def _declare(lib):
         "lb_halo_connect_ipc": (i, [vp, i, vp, i]),
         "lb_halo_connect_local": (i, [vp, i, vp]),
         "lb_halo_prime": (i, [vp]),
+        "lb_set_halo_timeout": (i, [vp, d]),
+        "lb_multi_create": (i, [ct.POINTER(LBConfig), i, ct.POINTER(ct.c_int), ct.POINTER(vp)]),
+        "lb_multi_destroy": (i, [vp]),
+        "lb_multi_last_error": (ct.c_char_p, [vp]),
+        "lb_multi_slab_count": (i, [vp]),
+        "lb_multi_slab": (i, [vp, i, ct.POINTER(vp), ct.POINTER(ct.c_int), ct.POINTER(ct.c_int)]),
+        "lb_multi_set_mask": (i, [vp, vp, i]),
+        "lb_multi_set_mask_disk": (i, [vp, d, d, d]),
+        "lb_multi_upload_f": (i, [vp, vp]),
+        "lb_multi_upload_moments": (i, [vp, vp, vp, vp]),
+        "lb_multi_init_synthetic": (i, [vp, i, d, d, ct.c_uint64]),
+        "lb_multi_set_temporal_blocking": (i, [vp, i]),
+        "lb_multi_temporal_blocking": (i, [vp]),
+        "lb_multi_prime": (i, [vp]),
+        "lb_multi_step": (i, [vp, i]),
+        "lb_multi_sync": (i, [vp]),
+        "lb_multi_download": (i, [vp, i, vp]),
+        "lb_multi_total_mass": (i, [vp, ct.POINTER(d)]),
+        "lb_multi_checksum": (i, [vp, ct.POINTER(ct.c_uint64)]),
+        "lb_multi_launch_count": (ct.c_int64, [vp]),
     }
     assert sorted(sig) == sorted(SYMBOLS)
     for name, (res, args) in sig.items():
@@ -130,6 +154,12 @@ def lib():
 def check(status, handle=None):
     if status != 0:
         msg = lib().lb_last_error(handle)
+        raise LBError(status, msg.decode() if msg else "unknown error")
+
+
+def check_multi(status, handle=None):
+    if status != 0:
+        msg = lib().lb_multi_last_error(handle)
         raise LBError(status, msg.decode() if msg else "unknown error")
 
 

@@ -43,6 +43,7 @@ class SlabLattice:
                                    device=self.device, zero_obstacle_velocity=zero_obstacle_velocity,
                                    global_nx=global_nx, x_offset=self.x_offset, west_edge=self.west_edge,
                                    east_edge=self.east_edge, stream=stream)
+        self._primed = False
         self._connect()
 
     # -- rendezvous ---------------------------------------------------------------------
@@ -67,6 +68,7 @@ class SlabLattice:
 
     def prime(self):
         """Publish the current boundary columns to the neighbours (after any upload/initialiser)."""
+        self._primed = True
         if self.world == 1:
             return
         self.lat.sync()
@@ -81,6 +83,11 @@ class SlabLattice:
 
     def set_mask(self, global_mask):
         self.lat.set_mask(self.local(np.asarray(global_mask)))
+        self._primed = False         # the neighbours hold a copy of this slab's boundary mask column
+
+    def set_mask_disk(self, cx, cy, r):
+        self.lat.set_mask_disk(cx, cy, r)
+        self._primed = False
 
     def upload_f(self, global_f):
         self.lat.upload_f(self.local(np.asarray(global_f)))
@@ -88,6 +95,8 @@ class SlabLattice:
 
     # -- hot path ---------------------------------------------------------------------------
     def run(self, n, sync=True):
+        if not self._primed:
+            self.prime()             # collective, like every call that precedes it on all ranks
         self.lat.run(n, sync=sync)
 
     def sync(self):
@@ -105,8 +114,24 @@ class SlabLattice:
         self.dist.all_gather_object(parts, self.lat.total_mass())
         return float(sum(parts))
 
+    def checksum(self):
+        """Exact checksum of the whole lattice: the per-slab 64-bit sums, added modulo 2^64."""
+        parts = [None] * self.world
+        self.dist.all_gather_object(parts, self.lat.checksum())
+        return sum(parts) & 0xFFFFFFFFFFFFFFFF
+
     def close(self):
-        self.lat.close()
+        """Collective: every rank drains its stream, then all ranks meet, then the arenas go away -- a
+        neighbour's last launch stores into this rank's arena until that neighbour has synchronised."""
+        if self.lat is None:
+            return
+        try:
+            self.lat.sync()
+        finally:
+            if self.world > 1:
+                self.dist.barrier()
+            self.lat.close()
+            self.lat = None
 
 
 __all__ = ["SlabLattice", "N"]

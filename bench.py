@@ -188,6 +188,7 @@ class ClockSampler:
 # reference CPU path (oracle/_ref = the unmodified compiled reference; test infrastructure, used
 # here only as the timed CPU arm)
 # ---------------------------------------------------------------------------------------------
+CPU_BASELINE_STEPS = 600
 CPU_SAMPLE = "reference cython_dim.Pipe_Flow_Cylinder 751x251 (the cylinder-wake workload at N=25), fp32 storage"
 
 
@@ -382,8 +383,8 @@ def main():
     lat = slab.lat
     if args.variant:
         lat.set_variant(args.variant)
-    if world == 1 and args.tb2 != "auto":
-        lat.set_temporal_blocking(args.tb2)
+    if args.tb2 != "auto":
+        lat.set_temporal_blocking(args.tb2)           # same choice on every rank (the slabs exchange per LAUNCH)
     if wl["mask"] == "disk":
         lat.set_mask_disk(gnx / 4.0, gny / 2.0, gny / 10.0)
     elif wl["mask"] == "cs205":
@@ -429,6 +430,7 @@ def main():
     launches = lat.launch_count - launches0
     lat.sync()
     mass = slab.total_mass() if world > 1 else lat.total_mass()
+    checksum = slab.checksum() if world > 1 else lat.checksum()
     value = cells_global * args.steps / (ms * 1e-3) / 1e6
     launch_ms = ms / args.steps
     achieved = cells_local * bytes_per_lu / (launch_ms * 1e-3) / 1e9
@@ -480,32 +482,40 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            v, wall, kind, cells = time_reference_cpu(600, 2, 1)
+            v, wall, kind, cells = time_reference_cpu(CPU_BASELINE_STEPS, 2, 1)
             cpu = {"value": v, "unit": "MLUPS", "cores": 1, "kind": kind,
-                   "sample": f"{CPU_SAMPLE}, 300 steps, 1 thread ({wall:.1f} s) of {os.cpu_count()} host cores available"}
+                   "sample": f"{CPU_SAMPLE}, {CPU_BASELINE_STEPS} steps, 1 thread ({wall:.1f} s) of {os.cpu_count()} host cores available"}
         except Exception as exc:
             cpu = {"value": None, "unit": "MLUPS", "cores": 0, "kind": "unavailable", "sample": repr(exc)}
 
     if rank == 0:
-        traffic = None
-        tb2 = lat.temporal_blocking if world == 1 else "off"
-        kernel = ("fused_step_kernel (one lattice update per launch)" if tb2 == "off" else
-                  f"fused_two_step_v2_kernel tile {tb2} (two lattice updates per launch, intermediate level in shared "
-                  "memory) + fused_step_kernel for the last step of the run")
+        tb2 = lat.temporal_blocking
+        two = tb2 != "off"
+        updates_per_launch = 2 if two else 1
+        kernel = ("fused_step_kernel (one lattice update per launch)" if not two else
+                  f"fused_march_kernel shape {tb2} (two lattice updates per launch, the intermediate time level in "
+                  "registers; an odd run starts with one fused_step_kernel launch)")
+        # measured DRAM traffic of ONE launch of the dominant kernel (ncu --set full, dram__bytes_read.sum +
+        # dram__bytes_write.sum), recorded per lattice node in profiles/traffic.json with the capture's own grid
+        traffic, traffic_note = None, None
         try:
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
-                t = json.load(fh).get(wl["dtype"] + ("" if tb2 == "off" else "_tb2"))
-                if t:
-                    traffic = t["dram_bytes_per_lattice_update"] * cells_local
+                t = json.load(fh).get(wl["dtype"] + ("_march" if two else ""))
+            if t:
+                traffic = t["dram_bytes_per_node_per_launch"] * cells_local
+                same = list(t.get("grid", [])) == [slab.nx, gny]
+                traffic_note = ("ncu capture of this kernel on this grid: " if same else
+                                f"ncu capture of this kernel on {t.get('grid')}, scaled by node count: ") + t["source"]
         except Exception:
             pass
+        launch_dur_ms = launch_ms * updates_per_launch
         line = {
             "metric": "D2Q9 MLUPS", "value": value, "unit": "MLUPS", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": launch_ms, "higher_is_better": True, "scaling": wl["scaling"],
             "vs_baseline": None, "dtype": wl["dtype"], "data": "synthetic",
             "config": {"workload": f"{args.workload}: {wl['desc']}", "global_grid": [gnx, gny],
                        "per_gpu_grid": [slab.nx, gny], "bc": wl["bc"], "omega": wl["omega"], "math": args.math,
-                       "decomposition": f"x-slabs x{world}, peer-memory halos (3 populations per face per step)",
+                       "decomposition": f"x-slabs x{world}, peer-memory halos over NVLink (9 values per face row per launch)",
                        "kernel": kernel,
                        "l2": f"inputs larger than L2: {2 * 9 * cells_local * elem / 1e9:.1f} GB ping-pong working set per GPU vs 126 MB",
                        "published_reference_mlups_other_hw": PUBLISHED_REFERENCE_MLUPS},
@@ -513,14 +523,25 @@ def main():
             "e2e": e2e,
             "gpu_launches": int(launches) * world,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0,
-                         "bytes_per_lattice_update": bytes_per_lu, "per": "GPU, " + kernel.split(" ")[0],
-                         "note": None if tb2 == "off" else "achieved counts the ALGORITHMIC 9 loads + 9 stores per update; with "
-                                 "temporal blocking the kernel moves fewer bytes than that (see traffic), so frac can exceed 1",
+                         "traffic": traffic, "traffic_source": traffic_note,
+                         "dram_GBs_on_measured_traffic": (traffic / (launch_dur_ms * 1e-3) / 1e9) if traffic else None,
+                         "frac_on_measured_traffic": (traffic / (launch_dur_ms * 1e-3) / 1e9 / peak) if traffic else None,
+                         "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0,
+                         "bytes_per_lattice_update": bytes_per_lu, "updates_per_launch": updates_per_launch,
+                         "launch_ms": launch_dur_ms, "algorithmic_bytes_per_launch": cells_local * bytes_per_lu * updates_per_launch,
+                         "per": "GPU, " + kernel.split(" ")[0],
+                         "note": None if not two else "achieved = ALGORITHMIC bytes (9 loads + 9 stores per update, two updates "
+                                 "per launch) / launch duration; the kernel keeps the intermediate level on chip and moves about "
+                                 "half of that through HBM (traffic), so frac can exceed 1 -- frac_on_measured_traffic is the "
+                                 "share of the measured HBM peak the kernel's real DRAM traffic amounts to",
                          "pattern_copy_ceiling": ceiling,
                          "frac_of_pattern_copy_ceiling": (achieved / ceiling["GB/s"]) if ceiling and ceiling.get("GB/s") else None},
             "cpu_baseline": cpu,
-            "checks": {"total_mass": mass, "mass_finite": bool(np.isfinite(mass))},
+            "checks": {"total_mass": mass, "mass_finite": bool(np.isfinite(mass)),
+                       "checksum": f"{checksum:016x}",
+                       "checksum_of": f"populations after {args.warmup} + {args.steps} steps from the seeded device-side initial "
+                                      "state: 64-bit wrap-around sum of all bit patterns, summed over ranks -- equal values at "
+                                      "every N (and with --tb2 off) mean bit-identical results"},
         }
         emit(line)
     slab.close()

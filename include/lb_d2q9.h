@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define LB_ABI_VERSION 4
+#define LB_ABI_VERSION 5
 
 typedef struct lb_sim lb_sim; /* opaque */
 
@@ -201,26 +201,23 @@ int lb_init_synthetic(lb_sim *sim, int kind, double u0, double amplitude, uint64
 /* solid disk in GLOBAL coordinates (centre cx,cy, radius r): mask = (gx-cx)^2+(y-cy)^2 < r^2 */
 int lb_set_mask_disk(lb_sim *sim, double cx, double cy, double r);
 
-/* -- temporal blocking: TWO lattice updates per pass through HBM (csrc/lb_tb2.cuh, lb_tb2v.cuh).  lb_step
- *    runs the moment-free steps of a run two at a time -- the intermediate time level stays in shared
- *    memory -- and the one-step kernel only for an odd step and for the last one.  Results are
- *    bit-identical to the one-step path in both math modes.
- *    shape -1 = automatic (default): the measured-best tile for lattices of at least 2^22 nodes, the
- *    one-step kernel below that; 0 = off; 1 .. lb_tb2_shape_count()-1 = a tile geometry by index
- *    (lb_tb2_shape_name: "BXxBY.tNT" cell-per-thread tiles, "rowsBY.wNW" row-per-warp tiles).  Serves
- *    single-slab LB_SCHEME_OPENCL / LB_MODEL_D2Q9 lattices (pipe; periodic boxes whose width is a
- *    multiple of the 128-/64-cell tile for the row-per-warp tiles); halo-connected slabs always run the
- *    one-step kernel.  lb_temporal_blocking returns the tile index lb_step will use (0 = one-step kernel). */
+/* -- two lattice updates per pass through HBM (csrc/lb_march.cuh).  lb_step runs a run's steps two at a
+ *    time in one launch -- the intermediate time level lives in registers, so only 36 B (fp32) / 72 B (fp64)
+ *    per lattice update cross the HBM interface -- preceded by one single-update launch when n_steps is
+ *    odd; the launch that ends the run also stores rho, u, v.  Results are bit-identical to the one-update
+ *    kernel in both math modes, on single slabs and on halo-connected slabs (which then exchange two columns
+ *    every second step instead of one column every step).
+ *    shape -1 = automatic (default): the measured-best shape when the WHOLE lattice (global_nx x ny) has at
+ *    least 2^22 nodes and ny >= 64, the graph-batched one-update kernel below that; 0 = off;
+ *    1 .. lb_tb2_shape_count()-1 = a compiled shape by index (lb_tb2_shape_name:
+ *    "march.w<warps per CTA>b<CTAs per SM>[.scalar].s<rows per segment>").  Serves LB_SCHEME_OPENCL /
+ *    LB_MODEL_D2Q9 lattices; a single-slab periodic box needs nx to be a multiple of the strip width (128 fp32 /
+ *    64 fp64 cells).  All slabs of one lattice must use the same setting.  lb_temporal_blocking returns the
+ *    shape lb_step will use (0 = one-update kernel). */
 int lb_set_temporal_blocking(lb_sim *sim, int shape);
 int lb_temporal_blocking(const lb_sim *sim);
 int lb_tb2_shape_count(void);
 const char *lb_tb2_shape_name(int shape);
-
-/* -- L2-level temporal blocking, EXPERIMENTAL: the same result as lb_step(n_steps), with
- *    the moment-free steps issued `depth` at a time as row-band launches of `band_rows` rows in a skewed
- *    order, so that each step reads what the previous one wrote while it is still in the 126 MB L2.
- *    Single-slab, non-periodic LB_SCHEME_OPENCL lattices. */
-int lb_step_banded(lb_sim *sim, int n_steps, int band_rows, int depth);
 
 /* -- diagnostics */
 /* Device self-test of the branch-free reciprocal used by STRICT fp32 math: compares it with IEEE
@@ -255,20 +252,63 @@ int lb_device_ptr(lb_sim *sim, int field, void **ptr, int64_t *pitch_elems);
 void *lb_stream(lb_sim *sim);
 
 /* -- x-slab halo exchange over NVLink peer memory (new design; the reference is single-device).
- *    Each slab owns a halo arena: two ghost columns x two parities x the 3 incoming
- *    populations, plus step flags.  A slab's boundary threads store their outgoing
- *    populations (1,5,8 eastward; 3,6,7 westward) straight into the NEIGHBOUR's arena
- *    inside the fused kernel and then publish a step flag there; the neighbour's
- *    boundary tiles poll their local flag before reading the ghost column. */
+ *    Each slab owns a halo arena: two ghost columns x two parities x nine values per row
+ *    (the 3 populations entering the slab from the neighbour's boundary column, that
+ *    column's populations 0,2,4, and the 3 entering populations one column further in --
+ *    what a two-update launch needs to advance the neighbour's boundary column itself),
+ *    the neighbours' mask columns, and launch flags.  A slab's boundary threads store those
+ *    values straight into the NEIGHBOUR's arena inside the fused kernel and then publish a
+ *    flag there; the neighbour's boundary tiles poll their local flag before reading. */
 #define LB_IPC_HANDLE_BYTES 64
 int lb_halo_ipc_handle(lb_sim *sim, void *out_handle /* LB_IPC_HANDLE_BYTES */);
 /* connect `side` to a neighbour slab living in another process (CUDA IPC) ... */
 int lb_halo_connect_ipc(lb_sim *sim, int side, const void *peer_handle, int peer_device);
 /* ... or in this process (virtual ranks on one device / several devices of one process) */
 int lb_halo_connect_local(lb_sim *sim, int side, lb_sim *peer);
-/* push the current state's boundary columns to the neighbours (call on every slab after
- * uploads / initialisers and before the first lb_step; callers barrier in between) */
+/* push the current state's two outermost columns and the boundary column of the obstacle mask to the
+ * neighbours (call on every slab after uploads / mask changes / initialisers and before the first lb_step;
+ * callers barrier in between).  Also clears a previous LB_ERR_HALO condition of this handle. */
 int lb_halo_prime(lb_sim *sim);
+/* bound of the in-kernel wait for a neighbour's ghost columns (default 30 s; the wait is a hand-shake between
+ * GPUs that normally lasts microseconds).  When it expires the waiting tiles skip their work -- nothing derived
+ * from stale ghost data is stored or published -- and the next lb_sync returns LB_ERR_HALO; upload + prime
+ * recovers the handle. */
+int lb_set_halo_timeout(lb_sim *sim, double seconds);
+/* LIFETIME of connected slabs: a neighbour's last launch may still be storing into this handle's halo arena
+ * when this handle's own stream is idle.  Before lb_destroy, lb_sync EVERY slab of the lattice (and, across
+ * processes, barrier) -- lb_b200.slab.SlabLattice.close and LocalSlabs.close do. */
+
+/* -- one lattice on several slabs / devices behind ONE handle.  The reference binds one command queue to
+ *    devices[0] (opencl_dim.py:229-240); this is the multi-device form of the same calls.  `cfg` describes the
+ *    WHOLE lattice (global_nx = nx, x_offset = 0; edges are derived).  The lattice is cut into n_slabs x-slabs
+ *    (widths differ by at most one column, remainder to the first slabs); slab k lives on device_ids[k].  The
+ *    handle owns the per-slab lb_sim handles, their streams and peer mappings, keeps the ghost columns primed,
+ *    and runs the step loop: with one slab per device the slabs advance asynchronously (bounded chunks,
+ *    synchronised by the in-kernel NVLink flags); slabs that share a device share a stream and advance in
+ *    lock-step ("virtual ranks": the arithmetic-neutrality tests).  Host arrays are GLOBAL arrays in the
+ *    layout stated at the top of this file; every slab copies its own columns.  Results are bit-identical to
+ *    the single-slab lattice.  (One process per GPU -- torch.distributed ranks -- uses lb_create +
+ *    lb_halo_ipc_handle / lb_halo_connect_ipc instead: lb_b200.slab.SlabLattice.) */
+typedef struct lb_multi lb_multi;
+int lb_multi_create(const lb_config *cfg, int n_slabs, const int *device_ids, lb_multi **out);
+int lb_multi_destroy(lb_multi *m);     /* drains every slab before freeing any arena */
+const char *lb_multi_last_error(const lb_multi *m);   /* m == NULL: the last failed lb_multi_create */
+int lb_multi_slab_count(const lb_multi *m);
+int lb_multi_slab(lb_multi *m, int k, lb_sim **slab, int *x_offset, int *nx);   /* borrow slab k (tuning, diagnostics) */
+int lb_multi_set_mask(lb_multi *m, const void *host_mask, int elem_bytes);       /* lb_set_mask, global [ny][nx] */
+int lb_multi_set_mask_disk(lb_multi *m, double cx, double cy, double r);
+int lb_multi_upload_f(lb_multi *m, const void *host_f);                           /* lb_upload_f, global; primes the ghosts */
+int lb_multi_upload_moments(lb_multi *m, const void *host_rho, const void *host_u, const void *host_v);
+int lb_multi_init_synthetic(lb_multi *m, int kind, double u0, double amplitude, uint64_t seed);
+int lb_multi_set_temporal_blocking(lb_multi *m, int shape);                      /* the same shape on every slab */
+int lb_multi_temporal_blocking(const lb_multi *m);
+int lb_multi_prime(lb_multi *m);       /* republish ghost columns after changing slab state through lb_multi_slab */
+int lb_multi_step(lb_multi *m, int n_steps);                                      /* Pipe_Flow.run, opencl_dim.py:372-387 */
+int lb_multi_sync(lb_multi *m);
+int lb_multi_download(lb_multi *m, int field, void *host_out);                    /* lb_download, global */
+int lb_multi_total_mass(lb_multi *m, double *out);
+int lb_multi_checksum(lb_multi *m, uint64_t *out);
+int64_t lb_multi_launch_count(const lb_multi *m);
 
 #ifdef __cplusplus
 }

@@ -999,14 +999,15 @@ def test_copy_ceiling_diagnostic_leaves_the_state_untouched(gpu, orc, dtype):
 
 
 # ------------------------------------------------------------------------------------------------
-# temporal blocking: two lattice updates per pass through HBM (csrc/lb_tb2.cuh)
+# two lattice updates per pass through HBM (csrc/lb_march.cuh)
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 @pytest.mark.parametrize("math", ["strict", "fast"])
 def test_temporal_blocking_is_bit_identical(gpu, orc, dtype, math):
-    """Every tile shape, pipe (obstacles on every edge, velocity zeroing on and off) and periodic boxes,
-    widths that are not a multiple of anything, odd and even step counts, several run() calls: the same
-    bits as the one-step kernel -- and, in STRICT math, as the oracle."""
+    """Every compiled shape of the two-update kernel, pipe (obstacles on every edge, velocity zeroing on and
+    off) and periodic boxes, widths that are not a multiple of anything, odd and even step counts, several
+    run() calls: the same bits -- populations AND the moments stored by the run's last launch -- as the
+    one-update kernel, and, in STRICT math, as the oracle."""
     from lb_b200 import Lattice, native
     L = native.lib()
     shapes = [L.lb_tb2_shape_name(k).decode() for k in range(1, L.lb_tb2_shape_count())]
@@ -1017,7 +1018,7 @@ def test_temporal_blocking_is_bit_identical(gpu, orc, dtype, math):
         cases.append(("pipe", f0, m, False))
         if m is not None:
             cases.append(("pipe", f0, m, True))
-    for (nx, ny) in ((96, 40), (131, 67), (3, 3), (256, 37), (128, 5)):
+    for (nx, ny) in ((96, 40), (131, 67), (3, 3), (256, 37), (128, 5), (384, 70), (64, 2)):
         cases.append(("periodic", periodic_case(orc, nx, ny, dtype, amplitude=1e-3, seed=ny), None, False))
     f0, m = pipe_case(orc, 700, 41, dtype, mask="bulky", seed=11)
     cases.append(("pipe", f0, m, True))
@@ -1041,10 +1042,12 @@ def test_temporal_blocking_is_bit_identical(gpu, orc, dtype, math):
                 try:
                     sim.set_temporal_blocking(shape)
                 except native.LBError:
-                    # the largest tiles do not fit shared memory in double; the row-per-warp tiles need a
-                    # periodic box whose width is a multiple of the tile width
-                    assert dtype == np.float64 or (shape.startswith("rows") and bc == "periodic" and nx % 128)
+                    # a single-slab periodic box must be a whole number of strips wide (the round-1 tiles of
+                    # an LB_EXPERIMENTS build have their own limits: shared memory in double, tile width)
+                    span = 128 if dtype == np.float32 else 64
+                    assert (bc == "periodic" and nx % span) or not shape.startswith("march")
                     continue
+                assert sim.temporal_blocking == shape
                 done = 0
                 for n in (1, 2, 5, 8):
                     sim.run(n)
@@ -1069,20 +1072,100 @@ def test_temporal_blocking_refuses_what_it_does_not_serve(gpu):
         sim.set_temporal_blocking(0)
 
 
-@pytest.mark.parametrize("dtype", [np.float32, np.float64])
-def test_banded_schedule_is_bit_identical(gpu, orc, dtype):
-    """lb_step_banded (skewed row-band launches, L2-level temporal blocking): any band height and depth
-    gives the bits of lb_step."""
+def test_run_of_n_steps_takes_half_as_many_launches(gpu, orc):
+    """lb_step with the marching kernel: every step of a run inside two-update launches -- 20 steps are 10
+    launches, 21 steps one single-update launch + 10 -- and the moments come from the run's last launch."""
     from lb_b200 import Lattice
-    for (nx, ny, mask) in ((301, 77, "touching"), (130, 35, "none"), (700, 41, "bulky"), (64, 3, "none")):
-        f0, m = pipe_case(orc, nx, ny, dtype, mask=mask, seed=nx)
-        with Lattice(nx, ny, 1.4, 1.01, 1.0, mask=m, f0=f0, dtype=dtype, math="strict", zero_obstacle_velocity=True) as plain:
-            plain.run(13)
-            want = plain.fields()
-        for band_rows, depth in ((1, 1), (1, 5), (2, 3), (7, 2), (16, 4), (64, 12), (5, 20)):
-            with Lattice(nx, ny, 1.4, 1.01, 1.0, mask=m, f0=f0, dtype=dtype, math="strict", zero_obstacle_velocity=True) as sim:
-                sim.run_banded(6, band_rows, depth)
-                sim.run_banded(7, band_rows, depth)
-                got = sim.fields()
-                for k in ("f", "rho", "u", "v"):
-                    assert np.array_equal(got[k], want[k]), (nx, ny, band_rows, depth, k)
+    f0, m = pipe_case(orc, 300, 70, np.float32, mask="blocks", seed=2)
+    with Lattice(300, 70, 1.3, 1.01, 1.0, mask=m, f0=f0) as sim:
+        sim.set_temporal_blocking("march.w4b4.s32")
+        n0 = sim.launch_count
+        sim.run(20)
+        assert sim.launch_count - n0 == 10
+        sim.run(21)
+        assert sim.launch_count - n0 == 21
+        sim.set_temporal_blocking("off")
+        sim.run(3)
+        assert sim.launch_count - n0 == 24
+
+
+@pytest.mark.parametrize("bc", ["pipe", "periodic"])
+@pytest.mark.parametrize("parts", [2, 3, 5])
+@pytest.mark.parametrize("dtype,math", [(np.float32, "strict"), (np.float32, "fast"), (np.float64, "strict")])
+def test_two_update_kernel_on_halo_connected_slabs_is_bit_identical(gpu, orc, bc, parts, dtype, math):
+    """The marching kernel on x-slabs (virtual ranks on one GPU): two-column ghost exchange every second
+    step, rim nodes beyond a slab edge rebuilt from the neighbour's published columns and mask -- the single
+    slab's bits, for obstacles straddling the cuts, slabs narrower than a strip, odd and even runs."""
+    from lb_b200 import Lattice
+    from lb_b200.lattice import LocalSlabs
+    for (nx, ny, mask, zv) in ((203, 45, "touching", False), (700, 41, "bulky", True), (47, 70, "touching", False), (11, 9, "none", False)):
+        if nx // parts < 2:
+            continue
+        if bc == "pipe":
+            f0, m = pipe_case(orc, nx, ny, dtype, mask=mask if min(nx, ny) > 8 else "none", seed=7)
+        else:
+            f0, m = periodic_case(orc, nx, ny, dtype, amplitude=1e-3), None
+        kw = dict(bc=bc, dtype=dtype, math=math, zero_obstacle_velocity=zv)
+        with Lattice(nx, ny, 1.4, 1.01, 1.0, mask=m, f0=f0, **kw) as one:
+            want = {}
+            done = 0
+            for n in (2, 1, 6, 5):
+                one.run(n)
+                done += n
+                want[done] = one.fields()
+        for shape in ("march.w4b4.s32", "march.w2b8.s256"):
+            slabs = LocalSlabs(nx, ny, parts, omega=1.4, inlet_rho=1.01, outlet_rho=1.0, **kw)
+            try:
+                slabs.set_temporal_blocking(shape)
+                if m is not None:
+                    slabs.set_mask(m)
+                slabs.upload_f(f0)
+                done = 0
+                for n in (2, 1, 6, 5):
+                    slabs.run(n)
+                    done += n
+                    for k in ("f", "rho", "u", "v"):
+                        assert np.array_equal(slabs.download(k), want[done][k]), (nx, ny, shape, done, k)
+            finally:
+                slabs.close()
+
+
+def test_self_ring_halo_with_two_update_launches(gpu, orc):
+    """A periodic slab whose halo edges are connected to itself, marching kernel: equals in-kernel wrap."""
+    from lb_b200 import Lattice
+    f0 = periodic_case(orc, 150, 33, np.float32, amplitude=1e-3)
+    with Lattice(150, 33, 1.6, bc="periodic", f0=f0) as a:
+        a.run(13)
+        want = a.download("f")
+    with Lattice(150, 33, 1.6, bc="periodic", west_edge="halo", east_edge="halo") as b:
+        b.halo_connect_local("west", b)
+        b.halo_connect_local("east", b)
+        b.set_temporal_blocking("march.w4b4.s32")
+        b.upload_f(f0)
+        b.halo_prime()
+        b.run(1)
+        for _ in range(6):
+            b.run(2)
+        assert np.array_equal(b.download("f"), want)
+
+
+def test_halo_timeout_is_contained_and_recoverable(gpu, orc):
+    """A slab whose neighbour never publishes: the bounded in-kernel wait expires, lb_sync reports
+    LB_ERR_HALO, and upload + prime brings the handle back (no stuck error word)."""
+    from lb_b200 import Lattice, native
+    f0 = periodic_case(orc, 150, 33, np.float32, amplitude=1e-3)
+    with Lattice(150, 33, 1.6, bc="periodic", f0=f0) as a:
+        a.run(4)
+        want = a.download("f")
+    with Lattice(150, 33, 1.6, bc="periodic", west_edge="halo", east_edge="halo") as b:
+        b.halo_connect_local("west", b)
+        b.halo_connect_local("east", b)
+        b.set_halo_timeout(0.05)
+        b.upload_f(f0)               # no prime: the flags never arrive
+        with pytest.raises(native.LBError, match="halo"):
+            b.run(1)
+        b.upload_f(f0)
+        b.halo_prime()
+        for _ in range(4):
+            b.run(1)
+        assert np.array_equal(b.download("f"), want)
