@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -578,8 +579,11 @@ static const char *tb_refusal(const lb_sim *sim, int shape)
     if (g_variants[sim->variant].launch_tma) return "two-update kernels do not combine with a TMA-staged one-update variant";
     const int span = sim->elem == 4 ? 128 : 64;
     if (kind == LB_TB_MARCH) {
-        if (sim->cfg.west_edge == LB_EDGE_WRAP && sim->cfg.nx % span)
-            return "the marching kernel needs nx to be a multiple of the strip width (128 fp32 / 64 fp64 cells) on a single-slab periodic box";
+        const bool rim = !strncmp(g_tb_shapes[shape].name, "rim", 3);       // -DLB_EXPERIMENTS: lb_march_rim.cuh
+        const int need = rim ? span : (sim->elem == 4 ? 4 : 2);
+        if (sim->cfg.west_edge == LB_EDGE_WRAP && sim->cfg.nx % need)
+            return rim ? "the rim-gather marching kernel needs nx to be a multiple of the strip width (128 fp32 / 64 fp64 cells) on a single-slab periodic box"
+                       : "the marching kernel needs nx to be a multiple of the vector width (4 fp32 / 2 fp64 cells) on a single-slab periodic box";
         return nullptr;
     }
     // the round-1 shared-memory tiles: single slab only

@@ -62,7 +62,7 @@ struct StepParams {
     int edge_rows;            // rows per warp in an edge tile (tall tiles: few participants in the hand-shake)
     int edge_tiles_y;         // edge tiles per side
     int y_begin, y_end;       // rows this launch updates (whole lattice: 0, ny); band launches of lb_step_banded
-    int seg_rows;             // marching kernel (lb_march.cuh): rows per segment
+    int seg_rows;             // marching kernel (lb_march.cuh): rows per segment (within y_begin .. y_end)
 };
 enum : int { GHOST_SLOTS = 9 };
 
@@ -186,11 +186,16 @@ __device__ __forceinline__ bool wait_flag(const unsigned int *flag, unsigned int
 //      collision, the caller keeps q (phase 1 stores it to shared memory); ROW_FROM_TILE = the populations
 //      came from a shared-memory tile whose rim already holds the wrapped / ghost values, so the slab-edge
 //      fix-up from `src` is skipped (phase 2).
-enum : int { ROW_FULL = 0, ROW_TO_REGISTERS = 1, ROW_FROM_TILE = 2 };
-template <typename T, int V, int MATH, int STP, int MODEL, int ROLE = ROW_FULL, bool PACKED = false>
+//      The marching kernel (lb_march.cuh) brings its own slab-edge values and obstacle bits: ROW_REGS_NOFIX =
+//      ROW_TO_REGISTERS without the fix-up; CALLER_MASK = `solid_in` holds one bit per node of the thread (the
+//      per-32-cell flag array is indexed by aligned spans, which that kernel's overlapping strips are not);
+//      `store_ok` = false suppresses the stores and the halo publication of a lane that only computes overlap.
+enum : int { ROW_FULL = 0, ROW_TO_REGISTERS = 1, ROW_FROM_TILE = 2, ROW_REGS_NOFIX = 3 };
+template <typename T, int V, int MATH, int STP, int MODEL, int ROLE = ROW_FULL, bool PACKED = false, bool CALLER_MASK = false>
 __device__ __forceinline__ void finish_row(const StepParams &p, const Consts<T> &c, Pack<T, V> (&q)[9],
                                            const T *__restrict__ src, T *__restrict__ dst,
-                                           int x0, int span0, int y, int ym, int yp)
+                                           int x0, int span0, int y, int ym, int yp,
+                                           uint32_t solid_in = 0u, bool store_ok = true)
 {
     constexpr int SPAN = 32 * V;
     const long long plane = p.plane;
@@ -205,7 +210,7 @@ __device__ __forceinline__ void finish_row(const StepParams &p, const Consts<T> 
     //     fix-up (wrap, ghost column) and the boundary closure, behind ONE branch
     const bool row_is_wall = (!periodic) && (y == 0 || y == ny - 1);
     if (has_west || has_east || row_is_wall) {
-        if (ROLE != ROW_FROM_TILE && has_west && p.west != EDGE_BOUNDARY) {
+        if (ROLE != ROW_FROM_TILE && ROLE != ROW_REGS_NOFIX && has_west && p.west != EDGE_BOUNDARY) {
             T a1, a5, a8;
             if (p.west == EDGE_WRAP) {
                 a1 = src[1 * plane + (long long)y * pitch + (nx - 1)];
@@ -219,7 +224,7 @@ __device__ __forceinline__ void finish_row(const StepParams &p, const Consts<T> 
             }
             q[1].v[0] = a1; q[5].v[0] = a5; q[8].v[0] = a8;
         }
-        if (ROLE != ROW_FROM_TILE && has_east && p.east != EDGE_BOUNDARY) {
+        if (ROLE != ROW_FROM_TILE && ROLE != ROW_REGS_NOFIX && has_east && p.east != EDGE_BOUNDARY) {
             T a3, a6, a7;
             if (p.east == EDGE_WRAP) {
                 a3 = src[3 * plane + (long long)y * pitch];
@@ -256,7 +261,30 @@ __device__ __forceinline__ void finish_row(const StepParams &p, const Consts<T> 
     //     whole register packs -- a compile-time renaming, no mask bytes loaded, no per-node selects.
     uint32_t solid_bits = 0;
     bool all_solid = false;
-    if (p.mask != nullptr) {
+    if constexpr (CALLER_MASK) {
+        solid_bits = solid_in;
+        if (p.mask != nullptr && __any_sync(0xffffffffu, solid_bits != 0)) {
+            if (__all_sync(0xffffffffu, solid_bits == (1u << V) - 1u)) {     // D2Q9.cl:410-431 on every node of the warp
+                all_solid = true;
+                Pack<T, V> t;
+                t = q[1]; q[1] = q[3]; q[3] = t;
+                t = q[2]; q[2] = q[4]; q[4] = t;
+                t = q[5]; q[5] = q[7]; q[7] = t;
+                t = q[6]; q[6] = q[8]; q[8] = t;
+            } else {
+#pragma unroll
+                for (int e = 0; e < V; ++e) {
+                    if ((solid_bits >> e) & 1u) {
+                        T t;
+                        t = q[1].v[e]; q[1].v[e] = q[3].v[e]; q[3].v[e] = t;
+                        t = q[2].v[e]; q[2].v[e] = q[4].v[e]; q[4].v[e] = t;
+                        t = q[5].v[e]; q[5].v[e] = q[7].v[e]; q[7].v[e] = t;
+                        t = q[6].v[e]; q[6].v[e] = q[8].v[e]; q[8].v[e] = t;
+                    }
+                }
+            }
+        }
+    } else if (p.mask != nullptr) {
         const uint8_t *sf = p.span_solid + (long long)y * p.nspans + (span0 >> 5);
         uint32_t flags = 0, all = 0;
         if (SPAN == 128) { flags = *reinterpret_cast<const uint32_t *>(sf); all = 0x02020202u; }
@@ -352,7 +380,8 @@ __device__ __forceinline__ void finish_row(const StepParams &p, const Consts<T> 
         }
     }
 
-    if (ROLE == ROW_TO_REGISTERS) return;
+    if (ROLE == ROW_TO_REGISTERS || ROLE == ROW_REGS_NOFIX) return;
+    if (!store_ok) return;
 
     // --- stores: aligned vectors; the one thread straddling column nx-1 goes scalar ---
     if (x0 + V <= nx) {

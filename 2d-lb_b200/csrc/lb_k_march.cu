@@ -1,9 +1,11 @@
 // Instantiations of the two-update kernels.  Default build: the marching kernel (lb_march.cuh).
-// -DLB_EXPERIMENTS adds the round-1 shared-memory tiles (lb_tb2v.cuh row-per-warp, lb_tb2.cuh cell-per-thread),
-// kept for A/B measurements (profiles/README.md section 7).
+// -DLB_EXPERIMENTS adds its first version, which gathered the columns beside each strip with scalar loads
+// (lb_march_rim.cuh), and the round-1 shared-memory tiles (lb_tb2v.cuh row-per-warp, lb_tb2.cuh
+// cell-per-thread), kept for A/B measurements (profiles/README.md).
 #include "lb_host.h"
 #include "lb_march.cuh"
 #ifdef LB_EXPERIMENTS
+#include "lb_march_rim.cuh"
 #include "lb_tb2v.cuh"
 #endif
 
@@ -13,24 +15,43 @@ template <typename T, int V, int MATH, int NW, int MINB, bool PACKED>
 static void launch_march(const StepParams &p_in, cudaStream_t st)
 {
     StepParams p = p_in;
+    constexpr int OUT = 30 * V;
+    const int nstrips = (p.nx + OUT - 1) / OUT;
+    p.tiles_x = (nstrips + NW - 1) / NW;
+    p.tiles_y = (p.y_end - p.y_begin + p.seg_rows - 1) / p.seg_rows;  // segments
+    p.edge_tiles_y = p.tiles_y;                        // one edge CTA per segment and side
+    const unsigned grid = (unsigned)p.tiles_x * (unsigned)p.tiles_y;
+    fused_march_kernel<T, V, MATH, NW, MINB, PACKED><<<grid, 32 * NW, 0, st>>>(p);
+}
+// name: march.w<warps per CTA>b<CTAs per SM>[.scalar].s<rows per segment>
+#define MARCH(NW, MINB, PACKED, PN, S)                                                                           \
+    {"march.w" #NW "b" #MINB PN ".s" #S, LB_TB_MARCH, S, NW, 0, 0, 0,                                             \
+     {{launch_march<float, 4, MATH_STRICT, NW, MINB, PACKED>, launch_march<float, 4, MATH_FAST, NW, MINB, PACKED>},       \
+      {launch_march<double, 2, MATH_STRICT, NW, MINB, false>, launch_march<double, 2, MATH_FAST, NW, MINB, false>}},      \
+     {{nullptr, nullptr}, {nullptr, nullptr}}, {{nullptr, nullptr}, {nullptr, nullptr}}}
+#define MARCH_S(NW, MINB, PACKED, PN) MARCH(NW, MINB, PACKED, PN, 32), MARCH(NW, MINB, PACKED, PN, 64), MARCH(NW, MINB, PACKED, PN, 128), MARCH(NW, MINB, PACKED, PN, 256)
+
+#ifdef LB_EXPERIMENTS
+template <typename T, int V, int MATH, int NW, int MINB, bool PACKED>
+static void launch_rim(const StepParams &p_in, cudaStream_t st)
+{
+    StepParams p = p_in;
     constexpr int SPAN = 32 * V;
     const int nstrips = p.pitch / SPAN;                // the pitch is a multiple of SPAN
     p.tiles_x = (nstrips + NW - 1) / NW;
     p.tiles_y = (p.ny + p.seg_rows - 1) / p.seg_rows;  // segments
     p.edge_tiles_y = p.tiles_y;                        // one edge CTA per segment and side
     const unsigned grid = (unsigned)p.tiles_x * (unsigned)p.tiles_y;
-    fused_march_kernel<T, V, MATH, NW, MINB, PACKED><<<grid, 32 * NW, 0, st>>>(p);
+    fused_march_rim_kernel<T, V, MATH, NW, MINB, PACKED><<<grid, 32 * NW, 0, st>>>(p);
 }
 
-// name: march.w<warps per CTA>b<CTAs per SM>[.scalar].s<rows per segment>
-#define MARCH(NW, MINB, PACKED, PN, S)                                                                         \
-    {"march.w" #NW "b" #MINB PN ".s" #S, LB_TB_MARCH, S, NW, 0, 0, 0,                                           \
-     {{launch_march<float, 4, MATH_STRICT, NW, MINB, PACKED>, launch_march<float, 4, MATH_FAST, NW, MINB, PACKED>},   \
-      {launch_march<double, 2, MATH_STRICT, NW, MINB, false>, launch_march<double, 2, MATH_FAST, NW, MINB, false>}}, \
+#define RIM(NW, MINB, PACKED, PN, S)                                                                         \
+    {"rim.w" #NW "b" #MINB PN ".s" #S, LB_TB_MARCH, S, NW, 0, 0, 0,                                           \
+     {{launch_rim<float, 4, MATH_STRICT, NW, MINB, PACKED>, launch_rim<float, 4, MATH_FAST, NW, MINB, PACKED>},   \
+      {launch_rim<double, 2, MATH_STRICT, NW, MINB, false>, launch_rim<double, 2, MATH_FAST, NW, MINB, false>}}, \
      {{nullptr, nullptr}, {nullptr, nullptr}}, {{nullptr, nullptr}, {nullptr, nullptr}}}
-#define MARCH_S(NW, MINB, PACKED, PN) MARCH(NW, MINB, PACKED, PN, 32), MARCH(NW, MINB, PACKED, PN, 64), MARCH(NW, MINB, PACKED, PN, 128), MARCH(NW, MINB, PACKED, PN, 256)
+#define RIM_S(NW, MINB, PACKED, PN) RIM(NW, MINB, PACKED, PN, 32), RIM(NW, MINB, PACKED, PN, 64), RIM(NW, MINB, PACKED, PN, 128), RIM(NW, MINB, PACKED, PN, 256)
 
-#ifdef LB_EXPERIMENTS
 template <typename T, int MATH, int BX, int BY, int NT, int MINB>
 static void launch_tb2(const Tb2Params &p, dim3 grid, size_t smem, cudaStream_t st)
 {
@@ -70,12 +91,13 @@ static void launch_tb2v(const StepParams &p, dim3 grid, size_t smem, cudaStream_
 const LbTbShape g_tb_shapes[] = {
     {"off", LB_TB_OFF, 0, 0, 0, 0, 0, {{nullptr, nullptr}, {nullptr, nullptr}}, {{nullptr, nullptr}, {nullptr, nullptr}}, {{nullptr, nullptr}, {nullptr, nullptr}}},
     MARCH_S(4, 4, true, ""),
-    MARCH_S(4, 3, true, ""),
-    MARCH_S(4, 5, true, ""),
     MARCH_S(8, 2, true, ""),
-    MARCH_S(2, 8, true, ""),
     MARCH_S(4, 4, false, ".scalar"),
 #ifdef LB_EXPERIMENTS
+    MARCH_S(4, 3, true, ""),
+    MARCH_S(2, 8, true, ""),
+    RIM_S(4, 4, true, ""),
+    RIM_S(4, 4, false, ".scalar"),
     TB2(128, 16, 256, 2),
     TB2(128, 8, 256, 4),
     TB2V(6, 8, 3),

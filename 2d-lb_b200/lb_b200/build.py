@@ -15,7 +15,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(os.path.dirname(PKG), "csrc")
 LIB = os.path.join(CSRC, "liblb_d2q9.so")
 SOURCES = ["lb_d2q9.cu", "lb_k_step.cu", "lb_k_march.cu"]
-HEADERS = ["lb_device.cuh", "lb_f32x2.cuh", "lb_fused.cuh", "lb_march.cuh", "lb_host.h", "lb_cython.cuh", "lb_oldcl.cuh", "lb_tma.cuh",
+HEADERS = ["lb_device.cuh", "lb_f32x2.cuh", "lb_fused.cuh", "lb_march.cuh", "lb_march_rim.cuh", "lb_host.h", "lb_cython.cuh", "lb_oldcl.cuh", "lb_tma.cuh",
            "lb_tb2.cuh", "lb_tb2v.cuh", os.path.join("..", "..", "include", "lb_d2q9.h")]
 OBJ_DIR = os.path.join(os.path.dirname(os.path.dirname(PKG)), "build")
 
@@ -45,22 +45,26 @@ def is_stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build_library(force=False, verbose=False):
-    if not force and not is_stale():
+def build_library(force=False, verbose=False, extra_flags=(), out=None, tag=""):
+    """Build the library.  `extra_flags` / `out` / `tag` make a side build for A/B measurements (tools/):
+    extra nvcc flags, another output path, a suffix for the object files."""
+    out = out or LIB
+    if out == LIB and not force and not is_stale():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     os.makedirs(OBJ_DIR, exist_ok=True)
-    flags = NVCC_FLAGS + (["-DLB_EXPERIMENTS"] if _experiments() else []) + (["-Xptxas", "-v"] if verbose else [])
+    flags = (NVCC_FLAGS + (["-DLB_EXPERIMENTS"] if _experiments() else []) + (["-Xptxas", "-v"] if verbose else [])
+             + list(extra_flags))
 
     def compile_one(src):
-        obj = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
+        obj = os.path.join(OBJ_DIR, src.replace(".cu", tag + ".o"))
         subprocess.run([nvcc] + flags + ["-c", "-o", obj, src], cwd=CSRC, check=True)
         return obj
 
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as pool:
         objs = list(pool.map(compile_one, SOURCES))
-    subprocess.run([nvcc] + LINK_FLAGS + ["-o", LIB] + objs, cwd=CSRC, check=True)
-    return LIB
+    subprocess.run([nvcc] + LINK_FLAGS + ["-o", out] + objs, cwd=CSRC, check=True)
+    return out
 
 
 if __name__ == "__main__":

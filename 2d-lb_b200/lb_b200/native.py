@@ -7,7 +7,8 @@ import ctypes as ct
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_PKG), "csrc", "liblb_d2q9.so")
+# LB_D2Q9_LIB: another build of the same library (A/B measurements, tools/); the product path never sets it
+LIB_PATH = os.environ.get("LB_D2Q9_LIB") or os.path.join(os.path.dirname(_PKG), "csrc", "liblb_d2q9.so")
 
 # enums of lb_d2q9.h
 F32, F64 = 0, 1

@@ -211,8 +211,8 @@ int lb_set_mask_disk(lb_sim *sim, double cx, double cy, double r);
  *    least 2^22 nodes and ny >= 64, the graph-batched one-update kernel below that; 0 = off;
  *    1 .. lb_tb2_shape_count()-1 = a compiled shape by index (lb_tb2_shape_name:
  *    "march.w<warps per CTA>b<CTAs per SM>[.scalar].s<rows per segment>").  Serves LB_SCHEME_OPENCL /
- *    LB_MODEL_D2Q9 lattices; a single-slab periodic box needs nx to be a multiple of the strip width (128 fp32 /
- *    64 fp64 cells).  All slabs of one lattice must use the same setting.  lb_temporal_blocking returns the
+ *    LB_MODEL_D2Q9 lattices; a single-slab periodic box needs nx to be a multiple of the vector width (4 fp32 /
+ *    2 fp64 cells).  All slabs of one lattice must use the same setting.  lb_temporal_blocking returns the
  *    shape lb_step will use (0 = one-update kernel). */
 int lb_set_temporal_blocking(lb_sim *sim, int shape);
 int lb_temporal_blocking(const lb_sim *sim);

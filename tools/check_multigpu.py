@@ -5,8 +5,9 @@
         --master-port 29511 tools/check_multigpu.py
 
 For a pipe flow with obstacles and a periodic box (fp32 and fp64) the x-slab run over N GPUs with
-peer-memory halos must be BIT-IDENTICAL to the single-slab run of the same global lattice
-(rank 0 computes that one on its own GPU).  Exit code 0 = all identical.
+peer-memory halos -- one-update kernel and two-update marching kernel -- must be BIT-IDENTICAL to the
+single-slab one-update run of the same global lattice (rank 0 computes that one on its own GPU).
+Exit code 0 = all identical.
 """
 import os
 import sys
@@ -45,23 +46,26 @@ def main():
     ok = True
     for bc in ("pipe", "periodic"):
         for dtype in (np.float32, np.float64):
-            for math in ("strict", "fast"):
-                nx, ny, steps = 64 * world + 37, 301, 60
+            for math, tb in (("strict", "off"), ("strict", "march.w4b4.s64"), ("fast", "march.w4b4.s32"), ("fast", "off")):
+                nx, ny, steps = 64 * world + 37, 301, 61
                 f0, mask = make_case(bc, dtype, nx, ny, seed=11)
                 slab = SlabLattice(nx, ny, 1.5, 1.01, 1.0, bc=bc, dtype=dtype, math=math, device=local)
+                slab.lat.set_temporal_blocking(tb)
                 if mask is not None:
                     slab.set_mask(mask)
                 slab.upload_f(f0)
                 slab.run(steps)
+                slab.run(steps - 1)
                 got = {k: slab.gather(k) for k in ("f", "rho", "u")}
                 mass = slab.total_mass()
                 slab.close()
                 if rank == 0:
                     with Lattice(nx, ny, 1.5, 1.01, 1.0, mask=mask, f0=f0, bc=bc, dtype=dtype, math=math, device=local) as one:
-                        one.run(steps)
+                        one.set_temporal_blocking("off")
+                        one.run(2 * steps - 1)
                         same = all(np.array_equal(got[k], one.download(k)) for k in got)
                         m1 = one.total_mass()
-                    print(f"[check_multigpu] N={world} {bc:8s} {np.dtype(dtype).name} {math:6s}: "
+                    print(f"[check_multigpu] N={world} {bc:8s} {np.dtype(dtype).name} {math:6s} {tb:15s}: "
                           f"{'bit-identical' if same else 'MISMATCH'}  mass {mass:.10e} vs {m1:.10e}", flush=True)
                     ok = ok and same
                 dist.barrier()
@@ -72,16 +76,20 @@ def main():
         kw = dict(cylinder_center=[0.75, 0.5], cylinder_radius=0.1, diameter=1., rho=1., viscosity=1., pressure_grad=-10.,
                   pipe_length=3., N=20, time_prefactor=4., verbose=False)
         np.random.seed(3)
-        multi = lb.Pipe_Flow_Cylinder(devices=devs, **kw)
-        np.random.seed(3)
         single = lb.Pipe_Flow_Cylinder(device=local, **kw)
-        multi.run(150)
-        single.run(150)
-        fm, fs = multi.get_fields(), single.get_fields()
-        same = all(np.array_equal(fm[k], fs[k]) for k in ("f", "feq", "rho", "u", "v"))
-        print(f"[check_multigpu] single-process Pipe_Flow_Cylinder(devices={devs}) {multi.nx}x{multi.ny}: "
-              f"{'bit-identical' if same else 'MISMATCH'}", flush=True)
-        ok = ok and same
+        single.run(151)
+        fs = single.get_fields()
+        for tb in ("off", "march.w4b4.s32"):
+            np.random.seed(3)
+            multi = lb.Pipe_Flow_Cylinder(devices=devs, **kw)        # lb_multi_* underneath: one slab per device
+            multi.sim.set_temporal_blocking(tb)
+            multi.run(151)
+            fm = multi.get_fields()
+            same = all(np.array_equal(fm[k], fs[k]) for k in ("f", "feq", "rho", "u", "v"))
+            print(f"[check_multigpu] single-process Pipe_Flow_Cylinder(devices={devs}) {multi.nx}x{multi.ny} {tb}: "
+                  f"{'bit-identical' if same else 'MISMATCH'}", flush=True)
+            ok = ok and same
+            multi.sim.close()
     dist.barrier()
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)
