@@ -83,6 +83,8 @@ struct lb_sim {
     char *peer[2] = {nullptr, nullptr};   // neighbour arenas (mapped)
     bool peer_ipc[2] = {false, false};
     double *mass_scratch = nullptr;
+    cudaStream_t s_up = nullptr, s_down = nullptr;     // lb_run_streamed: copy streams
+    std::vector<cudaEvent_t> ev_pool;                   // lb_run_streamed: per-band events
     CUtensorMap tmap[2][3][2];    // [buffer][box height 2,4,8][plain | haloed box]: TMA descriptors of the ping-pong buffers
     bool tmap_ok = false;
     std::string err;
@@ -538,10 +540,11 @@ static int ensure_tmaps(lb_sim *sim)
 }
 
 // one lattice update: reads buffer src_idx, writes the other one
-static int launch_step(lb_sim *sim, int src_idx, int write_moments)
+static int launch_step(lb_sim *sim, int src_idx, int write_moments, int y_begin = 0, int y_end = -1)
 {
     StepParams p;
     fill_params(sim, p, src_idx, write_moments);
+    if (y_end >= 0) { p.y_begin = y_begin; p.y_end = y_end; }
     const LbVariant &var = g_variants[sim->variant];
     if (var.launch_tma) {
         int rc = ensure_tmaps(sim);
@@ -620,13 +623,14 @@ static int tb2_effective_shape(const lb_sim *sim)
 
 // two steps: reads buffer src_idx, writes the other one.  The marching kernel can store the moments of the
 // second step; the round-1 tiles cannot (write_moments must be 0 for them).
-static int launch_two_steps(lb_sim *sim, int src_idx, int shape, int write_moments)
+static int launch_two_steps(lb_sim *sim, int src_idx, int shape, int write_moments, int y_begin = 0, int y_end = -1)
 {
     const LbTbShape &t = g_tb_shapes[shape];
     const int di = sim->cfg.dtype == LB_F64, mi = sim->cfg.math == LB_MATH_FAST;
     if (t.kind == LB_TB_MARCH) {
         StepParams p;
         fill_params(sim, p, src_idx, write_moments);
+        if (y_end >= 0) { p.y_begin = y_begin; p.y_end = y_end; }
         p.seg_rows = t.seg_rows;
         t.launch_march[di][mi](p, sim->stream);
     } else if (t.kind == LB_TB_ROWS) {
@@ -835,6 +839,9 @@ int lb_destroy(lb_sim *sim)
     for (int i = 0; i < 2; ++i) cudaFree(sim->buf_base[i]);
     cudaFree(sim->rho); cudaFree(sim->u); cudaFree(sim->v); cudaFree(sim->feq);
     cudaFree(sim->mask); cudaFree(sim->span_solid); cudaFree(sim->halo); cudaFree(sim->mass_scratch); cudaFree(sim->frozen);
+    for (cudaEvent_t e : sim->ev_pool) cudaEventDestroy(e);
+    if (sim->s_up) cudaStreamDestroy(sim->s_up);
+    if (sim->s_down) cudaStreamDestroy(sim->s_down);
     if (sim->own_stream && sim->stream) cudaStreamDestroy(sim->stream);
     cudaGetLastError();
     delete sim;
@@ -944,6 +951,8 @@ int lb_set_mask_disk(lb_sim *sim, double cx, double cy, double r)
 }
 
 }  // extern "C"
+
+static int download_impl(lb_sim *sim, int field, void *host_out, size_t host_row, bool sync);
 
 static int upload_f_impl(lb_sim *sim, const void *host_f, size_t host_row)
 {
@@ -1179,6 +1188,97 @@ static int step_impl(lb_sim *sim, int n_steps, bool final)
 extern "C" {
 
 int lb_step(lb_sim *sim, int n_steps) { return step_impl(sim, n_steps, true); }
+
+// ---- end to end with host buffers: upload, n_steps, read-back -- pipelined by row bands -----------------------
+// The three stages of the reference's user code -- init_pop's upload (opencl_dim.py:324-327), run (:372-387),
+// get_fields' read-back (:390-407) -- touch every row once each, and row y of step s only needs rows y-1..y+1 of
+// step s-1.  So the lattice is uploaded in bands of rows; as soon as band b has arrived, every launch of the run
+// is issued for the rows whose dependency cone lies inside what has arrived (launch j, which brings the rows to
+// time level D_j, covers the rows up to D_j short of the band's end: a skewed wavefront), and the finished rows
+// of rho, u, v start their way back while later bands are still being uploaded.  H2D, compute and D2H overlap;
+// the call takes about as long as the upload alone.  Stream order alone guarantees correctness: a launch only
+// reads rows that earlier launches of the same stream (or the awaited upload) completed, and with non-decreasing
+// launch depths a launch never overwrites rows that a later-issued launch still reads.  Bit-identical to
+// lb_upload_f + lb_step + lb_download.
+int lb_run_streamed(lb_sim *sim, const void *host_f, int n_steps, void *host_rho, void *host_u, void *host_v)
+{
+    if (!sim || !host_f) return fail(sim, LB_ERR_INVALID, "lb_run_streamed: null argument");
+    if (n_steps < 1) return fail(sim, LB_ERR_INVALID, "lb_run_streamed: n_steps must be >= 1");
+    CU(cudaSetDevice(sim->cfg.device));
+    const int nx = sim->cfg.nx, ny = sim->cfg.ny;
+    const int tb = tb2_effective_shape(sim);
+    const bool can_stream = sim->cfg.scheme == LB_SCHEME_OPENCL && !uses_halo(sim) && sim->cfg.bc == LB_BC_PIPE &&
+                            tb_kind(tb) == LB_TB_MARCH && strncmp(g_tb_shapes[tb].name, "rim", 3) != 0 &&
+                            !g_variants[sim->variant].launch_tma && n_steps <= 256 && ny >= 1024;
+    void *outs[3] = {host_rho, host_u, host_v};
+    const int fields[3] = {LB_FIELD_RHO, LB_FIELD_U, LB_FIELD_V};
+    if (!can_stream) {                     // same result, stage after stage
+        int rc = upload_f_impl(sim, host_f, (size_t)nx);
+        if (rc == LB_OK) rc = step_impl(sim, n_steps, true);
+        for (int i = 0; i < 3 && rc == LB_OK; ++i)
+            if (outs[i]) rc = download_impl(sim, fields[i], outs[i], (size_t)nx, false);
+        return rc == LB_OK ? lb_sync(sim) : rc;
+    }
+    if (!sim->s_up) {
+        CU(cudaStreamCreateWithFlags(&sim->s_up, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&sim->s_down, cudaStreamNonBlocking));
+    }
+    // launch depths: an odd run starts with one single-update launch
+    std::vector<int> depth, reach;         // d_j and D_j = d_0 + ... + d_j
+    for (int left = n_steps; left > 0;) { const int d = (left & 1) ? 1 : 2; depth.push_back(d); left -= d; reach.push_back(n_steps - left); }
+    const int L = (int)depth.size();
+    int band = ((ny + 23) / 24 + 63) / 64 * 64;        // about 24 bands, whole segments
+    const int nb = (ny + band - 1) / band;
+    while ((int)sim->ev_pool.size() < 2 * nb + 1) {
+        cudaEvent_t e;
+        CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        sim->ev_pool.push_back(e);
+    }
+    const int A = sim->cur;                // level 0 is uploaded into the current buffer
+    const size_t w = (size_t)nx * sim->elem, dp = (size_t)sim->pitch * sim->elem;
+    // uploads start when everything already queued on the compute stream is done with the buffers
+    CU(cudaEventRecord(sim->ev_pool[2 * nb], sim->stream));
+    CU(cudaStreamWaitEvent(sim->s_up, sim->ev_pool[2 * nb], 0));
+    std::vector<int> done_to(L, 0);        // rows [0, done_to[j]) of launch j have been issued
+    for (int b = 0; b < nb; ++b) {
+        const int r0 = b * band, r1 = std::min(ny, r0 + band);
+        for (int j = 0; j < 9; ++j)
+            CU(cudaMemcpy2DAsync((char *)sim->buf[A] + ((size_t)j * sim->plane + (size_t)r0 * sim->pitch) * sim->elem, dp,
+                                 (const char *)host_f + ((size_t)j * ny + r0) * w, w, w, (size_t)(r1 - r0), cudaMemcpyHostToDevice, sim->s_up));
+        CU(cudaEventRecord(sim->ev_pool[b], sim->s_up));
+        CU(cudaStreamWaitEvent(sim->stream, sim->ev_pool[b], 0));
+        int lo_last = 0, hi_last = 0;
+        for (int j = 0; j < L; ++j) {
+            const int lo = done_to[j];
+            const int hi = (b == nb - 1) ? ny : std::max(0, r1 - reach[j]);
+            if (j == L - 1) { lo_last = lo; hi_last = std::max(lo, hi); }
+            if (hi <= lo) continue;
+            const int src_idx = A ^ (j & 1);
+            const int rc = depth[j] == 1 ? launch_step(sim, src_idx, j == L - 1, lo, hi) : launch_two_steps(sim, src_idx, tb, j == L - 1, lo, hi);
+            if (rc) return rc;
+            done_to[j] = hi;
+        }
+        if (hi_last > lo_last) {           // the rows of this band's last launch are final: send their moments home
+            CU(cudaEventRecord(sim->ev_pool[nb + b], sim->stream));
+            CU(cudaStreamWaitEvent(sim->s_down, sim->ev_pool[nb + b], 0));
+            void *dev[3] = {sim->rho, sim->u, sim->v};
+            for (int i = 0; i < 3; ++i) {
+                if (!outs[i]) continue;
+                const int eb = i == 0 ? sim->elem : sim->uv_elem;
+                CU(cudaMemcpy2DAsync((char *)outs[i] + (size_t)lo_last * nx * eb, (size_t)nx * eb,
+                                     (const char *)dev[i] + (size_t)lo_last * sim->pitch * eb, (size_t)sim->pitch * eb,
+                                     (size_t)nx * eb, (size_t)(hi_last - lo_last), cudaMemcpyDeviceToHost, sim->s_down));
+            }
+        }
+    }
+    sim->cur = A ^ (L & 1);
+    sim->state_index += (uint32_t)n_steps;
+    sim->seed_pending = false;
+    sim->prestream_done = false;
+    CU(cudaStreamSynchronize(sim->s_up));
+    CU(cudaStreamSynchronize(sim->s_down));
+    return lb_sync(sim);
+}
 
 int lb_sync(lb_sim *sim)
 {

@@ -180,6 +180,20 @@ class Lattice:
     def sync(self):
         self._call("lb_sync")
 
+    def run_streamed(self, f, n, rho=None, u=None, v=None):
+        """upload_f(f) + run(n) + download of rho, u, v into the given arrays (None = not wanted), pipelined
+        by row bands so that the host-to-device copy, the n steps and the device-to-host copies overlap
+        (lb_run_streamed).  Pass page-locked arrays; same bits as the three separate calls."""
+        a = np.ascontiguousarray(f, dtype=self.dtype)
+        if a.shape != (9, self.ny, self.nx):
+            raise ValueError(f"f must have shape (9, ny, nx) = {(9, self.ny, self.nx)}, got {a.shape}")
+        outs = []
+        for name, o in (("rho", rho), ("u", u), ("v", v)):
+            if o is not None and (o.shape != (self.ny, self.nx) or o.dtype != self.field_dtype(name) or not o.flags.c_contiguous):
+                raise ValueError(f"{name} must be a C-contiguous (ny, nx) array of dtype {self.field_dtype(name)}")
+            outs.append(_ptr(o) if o is not None else None)
+        self._call("lb_run_streamed", _ptr(a), int(n), *outs)
+
     # -- readback ---------------------------------------------------------------------
     def download(self, field, out=None):
         """Device layout array of `field` in {'f','feq','rho','u','v'}."""

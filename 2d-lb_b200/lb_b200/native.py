@@ -26,7 +26,7 @@ MODEL_D2Q9, MODEL_D2Q9I = 0, 1
 # every symbol include/lb_d2q9.h declares (tests/test_abi.py checks the library exports them all)
 SYMBOLS = [
     "lb_abi_version", "lb_device_count", "lb_create", "lb_destroy", "lb_last_error",
-    "lb_set_mask", "lb_upload_f", "lb_upload_moments", "lb_step", "lb_sync", "lb_download", "lb_download_strided",
+    "lb_set_mask", "lb_upload_f", "lb_upload_moments", "lb_step", "lb_run_streamed", "lb_sync", "lb_download", "lb_download_strided",
     "lb_stage_move", "lb_stage_move_bcs", "lb_stage_update_hydro", "lb_stage_update_feq",
     "lb_stage_collide", "lb_stage_zero_velocity", "lb_init_synthetic", "lb_set_mask_disk",
     "lb_total_mass", "lb_checksum", "lb_selftest_rcp", "lb_selftest_copy", "lb_set_temporal_blocking", "lb_temporal_blocking", "lb_tb2_shape_count", "lb_tb2_shape_name", "lb_launch_count", "lb_set_variant", "lb_variant_count", "lb_variant_name",
@@ -79,6 +79,7 @@ def _declare(lib):
         "lb_upload_f": (i, [vp, vp]),
         "lb_upload_moments": (i, [vp, vp, vp, vp]),
         "lb_step": (i, [vp, i]),
+        "lb_run_streamed": (i, [vp, vp, i, vp, vp, vp]),
         "lb_sync": (i, [vp]),
         "lb_download": (i, [vp, i, vp]),
         "lb_download_strided": (i, [vp, i, i, i, vp]),

@@ -463,8 +463,12 @@ def main():
         lat.download("f", out=f_np)          # the step's input, resident in pinned host memory (untimed)
 
         def e2e_call():
+            if world == 1:
+                # one C-ABI call: upload, K steps, read-back, pipelined by row bands (lb_run_streamed)
+                lat.run_streamed(f_np, args.steps, rho=m_np[0], u=m_np[1], v=m_np[2])
+                return
             lat.upload_f(f_np)               # H2D of all nine populations (blocking)
-            slab.prime()                     # N > 1: republish the fresh state's boundary columns
+            slab.prime()                     # republish the fresh state's boundary columns
             lat.run(args.steps, sync=False)
             for name, out in zip(("rho", "u", "v"), m_np):
                 lat.download(name, out=out)  # D2H of density and velocity (blocking)
@@ -475,7 +479,8 @@ def main():
         e2e = {"value": cells_global * args.steps / (ms_e2e * 1e-3) / 1e6, "unit": "MLUPS",
                "h2d_bytes_per_step": n_f * elem * world / args.steps, "d2h_bytes_per_step": 3 * n_m * elem * world / args.steps,
                "ms_per_call": ms_e2e, "steps_per_call": args.steps, "rho_finite": ok,
-               "call": "lb_upload_f(pinned host f) + lb_step(K) + lb_download(rho,u,v) per call"}
+               "call": ("lb_run_streamed(pinned host f, K, pinned rho, u, v): upload, K steps and read-back pipelined by row bands"
+                        if world == 1 else "lb_upload_f(pinned host f) + lb_halo_prime + lb_step(K) + lb_download(rho,u,v) per call")}
         del host_f, host_m
 
     # ---- CPU baseline (rank 0, N == 1 only) -------------------------------------------------------

@@ -161,6 +161,16 @@ int lb_upload_moments(lb_sim *sim, const void *host_rho, const void *host_u, con
 int lb_step(lb_sim *sim, int n_steps);
 int lb_sync(lb_sim *sim);
 
+/* -- the reference's whole user sequence in one call: init_pop's upload of f (opencl_dim.py:324-327),
+ *    run(n_steps) (:372-387) and get_fields' read-back of rho, u, v (:400-407; any output may be NULL), with the
+ *    three stages PIPELINED by row bands: a band is updated through all n_steps as soon as it has arrived (a
+ *    skewed wavefront of row-range launches) and its moments travel back while later bands are still being
+ *    uploaded, so H2D, compute and D2H overlap and the call lasts about as long as the upload alone.  Host
+ *    buffers should be page-locked (cudaHostAlloc / torch pin_memory) for the copies to overlap.  Blocking.
+ *    Bit-identical to lb_upload_f + lb_step + lb_download, to which it falls back where it cannot pipeline
+ *    (halo-connected slabs, periodic boxes, the other schemes, n_steps > 256, ny < 1024). */
+int lb_run_streamed(lb_sim *sim, const void *host_f, int n_steps, void *host_rho, void *host_u, void *host_v);
+
 /* -- readback: cl.enqueue_copy(queue, host, dev, is_blocking=True), opencl_dim.py:394-407.
  *    Blocking.  host_out has the layout stated at the top of this file. */
 int lb_download(lb_sim *sim, int field, void *host_out);
