@@ -190,8 +190,14 @@ __device__ __forceinline__ bool wait_flag(const unsigned int *flag, unsigned int
 //      ROW_TO_REGISTERS without the fix-up; CALLER_MASK = `solid_in` holds one bit per node of the thread (the
 //      per-32-cell flag array is indexed by aligned spans, which that kernel's overlapping strips are not);
 //      `store_ok` = false suppresses the stores and the halo publication of a lane that only computes overlap.
+//      ZOV = 0 compiles the zeroing of obstacle velocities out for handles that do not ask for it (ZOV = -1:
+//      decided at run time by the flag): the marching kernel's loop body is two of these back to back, and ncu
+//      showed 10 % of its stall cycles to be instruction fetches.  (Turning the boundary closure into a call as
+//      well made the kernel 11 % slower -- the call's register conventions reach into the hot path --
+//      profiles/r2_march_regs_vs_smem_window_bc_inline_vs_call.txt.)
 enum : int { ROW_FULL = 0, ROW_TO_REGISTERS = 1, ROW_FROM_TILE = 2, ROW_REGS_NOFIX = 3 };
-template <typename T, int V, int MATH, int STP, int MODEL, int ROLE = ROW_FULL, bool PACKED = false, bool CALLER_MASK = false>
+
+template <typename T, int V, int MATH, int STP, int MODEL, int ROLE = ROW_FULL, bool PACKED = false, bool CALLER_MASK = false, int ZOV = -1>
 __device__ __forceinline__ void finish_row(const StepParams &p, const Consts<T> &c, Pack<T, V> (&q)[9],
                                            const T *__restrict__ src, T *__restrict__ dst,
                                            int x0, int span0, int y, int ym, int yp,
@@ -334,7 +340,8 @@ __device__ __forceinline__ void finish_row(const StepParams &p, const Consts<T> 
     //     the loop: no velocity to zero (the common one, flag-free); every node solid with zeroed
     //     velocity (the equilibrium folds to w*rho at compile time); mixed warps with a per-node flag.
     Pack<T, V> mrho, mu, mv;
-    if (p.zero_obstacle_velocity && all_solid) {
+    const bool zov = ZOV < 0 ? (p.zero_obstacle_velocity != 0) : (ZOV != 0);
+    if (zov && all_solid) {
 #pragma unroll
         for (int e = 0; e < V; ++e) {
             T g[9];
@@ -344,7 +351,7 @@ __device__ __forceinline__ void finish_row(const StepParams &p, const Consts<T> 
 #pragma unroll
             for (int j = 0; j < 9; ++j) q[j].v[e] = g[j];
         }
-    } else if (p.zero_obstacle_velocity && __any_sync(0xffffffffu, solid_bits != 0)) {
+    } else if (zov && __any_sync(0xffffffffu, solid_bits != 0)) {
 #pragma unroll
         for (int e = 0; e < V; ++e) {
             T g[9];

@@ -11,7 +11,7 @@
 
 using namespace lb;
 
-template <typename T, int V, int MATH, int NW, int MINB, bool PACKED>
+template <typename T, int V, int MATH, int NW, int MINB, bool PACKED, bool PF = false, bool SH = false>
 static void launch_march(const StepParams &p_in, cudaStream_t st)
 {
     StepParams p = p_in;
@@ -21,13 +21,30 @@ static void launch_march(const StepParams &p_in, cudaStream_t st)
     p.tiles_y = (p.y_end - p.y_begin + p.seg_rows - 1) / p.seg_rows;  // segments
     p.edge_tiles_y = p.tiles_y;                        // one edge CTA per segment and side
     const unsigned grid = (unsigned)p.tiles_x * (unsigned)p.tiles_y;
-    fused_march_kernel<T, V, MATH, NW, MINB, PACKED><<<grid, 32 * NW, 0, st>>>(p);
+    // handles that do not zero obstacle velocities run the instantiation without that code
+    if (p.zero_obstacle_velocity) fused_march_kernel<T, V, MATH, NW, MINB, PACKED, PF, -1, SH><<<grid, 32 * NW, 0, st>>>(p);
+    else fused_march_kernel<T, V, MATH, NW, MINB, PACKED, PF, 0, SH><<<grid, 32 * NW, 0, st>>>(p);
 }
-// name: march.w<warps per CTA>b<CTAs per SM>[.scalar].s<rows per segment>
+// name: march.w<warps per CTA>b<CTAs per SM>[.sh | .scalar | .pf].s<rows per segment>
+//   .sh      the kept rows of the intermediate level in shared memory (thread-private slots): the shipped form
+//   (none)   ... in registers
+//   .scalar  registers, scalar fp32 collision instead of the packed one (A/B)
+//   .pf      registers, software-prefetched loads (LB_EXPERIMENTS; measured slower)
 #define MARCH(NW, MINB, PACKED, PN, S)                                                                           \
     {"march.w" #NW "b" #MINB PN ".s" #S, LB_TB_MARCH, S, NW, 0, 0, 0,                                             \
      {{launch_march<float, 4, MATH_STRICT, NW, MINB, PACKED>, launch_march<float, 4, MATH_FAST, NW, MINB, PACKED>},       \
       {launch_march<double, 2, MATH_STRICT, NW, MINB, false>, launch_march<double, 2, MATH_FAST, NW, MINB, false>}},      \
+     {{nullptr, nullptr}, {nullptr, nullptr}}, {{nullptr, nullptr}, {nullptr, nullptr}}}
+#define MARCHPF(NW, MINB, S)                                                                                     \
+    {"march.w" #NW "b" #MINB ".pf.s" #S, LB_TB_MARCH, S, NW, 0, 0, 0,                                            \
+     {{launch_march<float, 4, MATH_STRICT, NW, MINB, true, true>, launch_march<float, 4, MATH_FAST, NW, MINB, true, true>},   \
+      {launch_march<double, 2, MATH_STRICT, NW, MINB, false, true>, launch_march<double, 2, MATH_FAST, NW, MINB, false, true>}}, \
+     {{nullptr, nullptr}, {nullptr, nullptr}}, {{nullptr, nullptr}, {nullptr, nullptr}}}
+#define MARCHSH_S(NW, MINB) MARCHSH(NW, MINB, 32), MARCHSH(NW, MINB, 64), MARCHSH(NW, MINB, 128), MARCHSH(NW, MINB, 256)
+#define MARCHSH(NW, MINB, S)                                                                                     \
+    {"march.w" #NW "b" #MINB ".sh.s" #S, LB_TB_MARCH, S, NW, 0, 0, 0,                                            \
+     {{launch_march<float, 4, MATH_STRICT, NW, MINB, true, false, true>, launch_march<float, 4, MATH_FAST, NW, MINB, true, false, true>},   \
+      {launch_march<double, 2, MATH_STRICT, NW, MINB, false, false, true>, launch_march<double, 2, MATH_FAST, NW, MINB, false, false, true>}}, \
      {{nullptr, nullptr}, {nullptr, nullptr}}, {{nullptr, nullptr}, {nullptr, nullptr}}}
 #define MARCH_S(NW, MINB, PACKED, PN) MARCH(NW, MINB, PACKED, PN, 32), MARCH(NW, MINB, PACKED, PN, 64), MARCH(NW, MINB, PACKED, PN, 128), MARCH(NW, MINB, PACKED, PN, 256)
 
@@ -90,10 +107,13 @@ static void launch_tb2v(const StepParams &p, dim3 grid, size_t smem, cudaStream_
 
 const LbTbShape g_tb_shapes[] = {
     {"off", LB_TB_OFF, 0, 0, 0, 0, 0, {{nullptr, nullptr}, {nullptr, nullptr}}, {{nullptr, nullptr}, {nullptr, nullptr}}, {{nullptr, nullptr}, {nullptr, nullptr}}},
+    MARCHSH_S(4, 5),
     MARCH_S(4, 4, true, ""),
-    MARCH_S(8, 2, true, ""),
-    MARCH_S(4, 4, false, ".scalar"),
+    MARCH(4, 4, false, ".scalar", 64),
 #ifdef LB_EXPERIMENTS
+    MARCHSH_S(4, 4), MARCHSH_S(4, 6), MARCHSH_S(8, 3), MARCHSH_S(2, 10),
+    MARCH_S(8, 2, true, ""),
+    MARCHPF(4, 3, 64),
     MARCH_S(4, 3, true, ""),
     MARCH_S(2, 8, true, ""),
     RIM_S(4, 4, true, ""),
@@ -106,5 +126,5 @@ const LbTbShape g_tb_shapes[] = {
 #endif
 };
 const int g_ntb = (int)(sizeof(g_tb_shapes) / sizeof(g_tb_shapes[0]));
-const char *const g_tb_auto_f32 = "march.w4b4.s64";
-const char *const g_tb_auto_f64 = "march.w4b4.s64";
+const char *const g_tb_auto_f32 = "march.w4b5.sh.s64";
+const char *const g_tb_auto_f64 = "march.w4b5.sh.s64";

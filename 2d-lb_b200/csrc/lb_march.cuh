@@ -93,10 +93,36 @@ __device__ __forceinline__ uint32_t lap_solid_bits(const StepParams &p, int x0, 
 
 // grid: 1-D.  CTA = NW warps = NW adjacent strips of one segment of rows.  Halo launches order the two edge CTA
 // columns first (they wait for / publish the ghost columns), like fused_step_kernel.
-template <typename T, int V, int MATH, int NW, int MINB, bool PACKED>
+// nine aligned vector loads of one row: plane j at the row its population streams from
+template <typename T, int V>
+__device__ __forceinline__ void lap_load_row(Pack<T, V> (&q)[9], const T *__restrict__ src, long long plane, int pitch, int xl,
+                                             int gy, int ym, int yp)
+{
+    const T *pc = src + (long long)gy * pitch + xl;
+    const T *pm = src + (long long)ym * pitch + xl + 2 * plane;
+    const T *pp = src + (long long)yp * pitch + xl + 4 * plane;
+    q[0] = load_pack<T, V, 1>(pc);
+    q[1] = load_pack<T, V, 1>(pc + plane);
+    q[3] = load_pack<T, V, 1>(pc + 3 * plane);
+    q[2] = load_pack<T, V, 1>(pm);
+    q[5] = load_pack<T, V, 1>(pm + 3 * plane);
+    q[6] = load_pack<T, V, 1>(pm + 4 * plane);
+    q[4] = load_pack<T, V, 1>(pp);
+    q[7] = load_pack<T, V, 1>(pp + 3 * plane);
+    q[8] = load_pack<T, V, 1>(pp + 4 * plane);
+}
+
+// PF: software pipelining -- the loads of row y+1 are issued before row y is worked on (36 more registers in
+// flight; the warp never waits for DRAM with nothing to do).
+// SH: the kept rows of the intermediate level live in shared memory instead of registers -- nine 16-byte slots per
+// thread, private to it (no other thread reads them: no synchronisation, no bank conflicts) -- which brings the
+// kernel under 100 registers and 20 instead of 16 warps onto an SM.
+template <typename T, int V, int MATH, int NW, int MINB, bool PACKED, bool PF = false, int ZOV = -1, bool SH = false>
 __global__ void __launch_bounds__(32 * NW, MINB) fused_march_kernel(const StepParams p)
 {
     constexpr int OUT = 30 * V;
+    using VT = typename VecOf<T, V>::type;
+    __shared__ VT win_s[SH ? NW * 9 * 32 : 1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
     int bx, seg;
@@ -147,30 +173,42 @@ __global__ void __launch_bounds__(32 * NW, MINB) fused_march_kernel(const StepPa
         for (int e = 0; e < V; ++e) {
             h0.v[e] = h1.v[e] = h3.v[e] = a2.v[e] = a5.v[e] = a6.v[e] = b2.v[e] = b5.v[e] = b6.v[e] = (T)0;
         }
+        // SH: slot k of this thread; 0-2 = populations 0,1,3 of the previous row, 3-5 / 6-8 = populations 2,5,6 of
+        // the rows of even / odd index
+        VT *win = win_s + (SH ? warp * 9 * 32 + lane : 0);
+        if (SH) {
+#pragma unroll
+            for (int k = 0; k < 9; ++k) win[k * 32] = repack(h0);
+        }
         uint32_t solid_prev = 0u;                      // obstacle bits of the row phase 2 works on
+        // rows wrap on a periodic box; outside a pipe there is nothing to load
+        auto row_of = [&](int y, int &gy, int &ym, int &yp) -> bool {
+            gy = y;
+            if (periodic) { if (gy < 0) gy = ny - 1; if (gy == ny) gy = 0; }
+            else if (gy < 0 || gy >= ny) return false;
+            ym = gy - 1; yp = gy + 1;
+            if (periodic) { if (ym < 0) ym = ny - 1; if (yp >= ny) yp = 0; }
+            return true;
+        };
+        Pack<T, V> qn[9];                              // PF: the row after this one, in flight
+        if (PF) {
+            int gy, ym, yp;
+            if (row_of(ys - 1, gy, ym, yp)) lap_load_row<T, V>(qn, src, plane, pitch, xl, gy, ym, yp);
+        }
         for (int y = ys - 1; y <= ye; ++y) {
             // ---- phase 1: level t+1 of row y ----------------------------------------------------------
-            int gy = y;
-            bool valid = true;
-            if (periodic) { if (gy < 0) gy = ny - 1; if (gy == ny) gy = 0; }
-            else valid = (gy >= 0 && gy < ny);
+            int gy, ym = 0, yp = 0;
+            const bool valid = row_of(y, gy, ym, yp);
             Pack<T, V> q[9];
             uint32_t solid_now = 0u;
+            if (PF) {
+#pragma unroll
+                for (int j = 0; j < 9; ++j) q[j] = qn[j];
+                int g2, m2, p2;
+                if (y < ye && row_of(y + 1, g2, m2, p2)) lap_load_row<T, V>(qn, src, plane, pitch, xl, g2, m2, p2);
+            }
             if (valid) {
-                int ym = gy - 1, yp = gy + 1;
-                if (periodic) { if (ym < 0) ym = ny - 1; if (yp >= ny) yp = 0; }
-                const T *pc = src + (long long)gy * pitch + xl;
-                const T *pm = src + (long long)ym * pitch + xl + 2 * plane;
-                const T *pp = src + (long long)yp * pitch + xl + 4 * plane;
-                q[0] = load_pack<T, V, 1>(pc);
-                q[1] = load_pack<T, V, 1>(pc + plane);
-                q[3] = load_pack<T, V, 1>(pc + 3 * plane);
-                q[2] = load_pack<T, V, 1>(pm);
-                q[5] = load_pack<T, V, 1>(pm + 3 * plane);
-                q[6] = load_pack<T, V, 1>(pm + 4 * plane);
-                q[4] = load_pack<T, V, 1>(pp);
-                q[7] = load_pack<T, V, 1>(pp + 3 * plane);
-                q[8] = load_pack<T, V, 1>(pp + 4 * plane);
+                if (!PF) lap_load_row<T, V>(q, src, plane, pitch, xl, gy, ym, yp);
                 solid_now = lap_solid_bits<V>(p, x0, xl, gy);
                 if (ghost_w) {                         // memory "continues" into the west neighbour: columns -2, -1
                     const T *G = static_cast<const T *>(p.ghost_w);
@@ -199,7 +237,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) fused_march_kernel(const StepPa
                     }
                 }
                 lap_shift_x<T, V>(q);
-                finish_row<T, V, MATH, 0, MODEL_D2Q9, ROW_REGS_NOFIX, PACKED, true>(p, c, q, src, dst, x0, own0, gy, ym, yp, solid_now, false);
+                finish_row<T, V, MATH, 0, MODEL_D2Q9, ROW_REGS_NOFIX, PACKED, true, ZOV>(p, c, q, src, dst, x0, own0, gy, ym, yp, solid_now, false);
             } else {
 #pragma unroll
                 for (int j = 0; j < 9; ++j)
@@ -212,16 +250,35 @@ __global__ void __launch_bounds__(32 * NW, MINB) fused_march_kernel(const StepPa
                 int rm = r - 1, rp = r + 1;
                 if (periodic) { if (rm < 0) rm = ny - 1; if (rp >= ny) rp = 0; }
                 Pack<T, V> z[9];
-                z[0] = h0; z[1] = h1; z[3] = h3;
-                z[2] = b2; z[5] = b5; z[6] = b6;
+                if (SH) {
+                    const int o = 3 + 3 * (y & 1);     // the slot of row y-2, which row y replaces below
+                    unpack(win[0 * 32], z[0]); unpack(win[1 * 32], z[1]); unpack(win[2 * 32], z[3]);
+                    unpack(win[(o + 0) * 32], z[2]); unpack(win[(o + 1) * 32], z[5]); unpack(win[(o + 2) * 32], z[6]);
+                } else {
+                    z[0] = h0; z[1] = h1; z[3] = h3;
+                    z[2] = b2; z[5] = b5; z[6] = b6;
+                }
                 z[4] = q[4]; z[7] = q[7]; z[8] = q[8];
+                if (SH) {                              // row y takes the slots just read (before z is worked on)
+                    const int o = 3 + 3 * (y & 1);
+                    win[0 * 32] = repack(q[0]); win[1 * 32] = repack(q[1]); win[2 * 32] = repack(q[3]);
+                    win[(o + 0) * 32] = repack(q[2]); win[(o + 1) * 32] = repack(q[5]); win[(o + 2) * 32] = repack(q[6]);
+                }
                 lap_shift_x<T, V>(z);
-                finish_row<T, V, MATH, 0, MODEL_D2Q9, ROW_FROM_TILE, PACKED, true>(p, c, z, src, dst, x0, own0, r, rm, rp, solid_prev, store_ok);
+                finish_row<T, V, MATH, 0, MODEL_D2Q9, ROW_FROM_TILE, PACKED, true, ZOV>(p, c, z, src, dst, x0, own0, r, rm, rp, solid_prev, store_ok);
             }
             // ---- rotate the kept rows --------------------------------------------------------------------
-            b2 = a2; b5 = a5; b6 = a6;
-            a2 = q[2]; a5 = q[5]; a6 = q[6];
-            h0 = q[0]; h1 = q[1]; h3 = q[3];
+            if (SH) {
+                if (y <= ys) {                         // no phase 2 yet: nothing was read, just park the row
+                    const int o = 3 + 3 * (y & 1);
+                    win[0 * 32] = repack(q[0]); win[1 * 32] = repack(q[1]); win[2 * 32] = repack(q[3]);
+                    win[(o + 0) * 32] = repack(q[2]); win[(o + 1) * 32] = repack(q[5]); win[(o + 2) * 32] = repack(q[6]);
+                }
+            } else {
+                b2 = a2; b5 = a5; b6 = a6;
+                a2 = q[2]; a5 = q[5]; a6 = q[6];
+                h0 = q[0]; h1 = q[1]; h3 = q[3];
+            }
             solid_prev = solid_now;
         }
     }

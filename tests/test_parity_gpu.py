@@ -1079,7 +1079,7 @@ def test_run_of_n_steps_takes_half_as_many_launches(gpu, orc):
     from lb_b200 import Lattice
     f0, m = pipe_case(orc, 300, 70, np.float32, mask="blocks", seed=2)
     with Lattice(300, 70, 1.3, 1.01, 1.0, mask=m, f0=f0) as sim:
-        sim.set_temporal_blocking("march.w4b4.s32")
+        sim.set_temporal_blocking("march.w4b5.sh.s32")
         n0 = sim.launch_count
         sim.run(20)
         assert sim.launch_count - n0 == 10
@@ -1114,7 +1114,7 @@ def test_two_update_kernel_on_halo_connected_slabs_is_bit_identical(gpu, orc, bc
                 one.run(n)
                 done += n
                 want[done] = one.fields()
-        for shape in ("march.w4b4.s32", "march.w8b2.s256"):
+        for shape in ("march.w4b5.sh.s32", "march.w4b4.s256"):
             slabs = LocalSlabs(nx, ny, parts, omega=1.4, inlet_rho=1.01, outlet_rho=1.0, **kw)
             try:
                 slabs.set_temporal_blocking(shape)
@@ -1141,7 +1141,7 @@ def test_self_ring_halo_with_two_update_launches(gpu, orc):
     with Lattice(150, 33, 1.6, bc="periodic", west_edge="halo", east_edge="halo") as b:
         b.halo_connect_local("west", b)
         b.halo_connect_local("east", b)
-        for shape in ("march.w4b4.s32", "march.w8b2.s64"):
+        for shape in ("march.w4b5.sh.s32", "march.w4b4.s64"):
             b.set_temporal_blocking(shape)
             b.upload_f(f0)
             b.halo_prime()

@@ -46,7 +46,7 @@ def main():
     ok = True
     for bc in ("pipe", "periodic"):
         for dtype in (np.float32, np.float64):
-            for math, tb in (("strict", "off"), ("strict", "march.w4b4.s64"), ("fast", "march.w4b4.s32"), ("fast", "off")):
+            for math, tb in (("strict", "off"), ("strict", "march.w4b5.sh.s64"), ("fast", "march.w4b4.s32"), ("fast", "off")):
                 nx, ny, steps = 64 * world + 37, 301, 61
                 f0, mask = make_case(bc, dtype, nx, ny, seed=11)
                 slab = SlabLattice(nx, ny, 1.5, 1.01, 1.0, bc=bc, dtype=dtype, math=math, device=local)
@@ -79,7 +79,7 @@ def main():
         single = lb.Pipe_Flow_Cylinder(device=local, **kw)
         single.run(151)
         fs = single.get_fields()
-        for tb in ("off", "march.w4b4.s32"):
+        for tb in ("off", "march.w4b5.sh.s32"):
             np.random.seed(3)
             multi = lb.Pipe_Flow_Cylinder(devices=devs, **kw)        # lb_multi_* underneath: one slab per device
             multi.sim.set_temporal_blocking(tb)

@@ -31,7 +31,7 @@ def run(bc, nx, ny, math, shape, mask, steps, dtype=np.float32, zv=False):
             print(tag, f"{len(d)} differ; first:", d[:12].tolist(), " xs:", sorted(set(d[:, -1].tolist()))[:20], " ys:", sorted(set(d[:, -2].tolist()))[:20],
                   " max|d|:", float(np.abs(got[k].astype(np.float64) - want[k]).max()))
 
-for shape in ("march.w4b4.s32", "march.w4b4.scalar.s32"):
+for shape in ("march.w4b5.sh.s32", "march.w4b4.s32"):
     run("pipe", 5, 4, "strict", shape, "none", 2)
     run("pipe", 2, 2, "strict", shape, "none", 2)
     run("pipe", 300, 70, "strict", shape, "none", 2)
