@@ -268,6 +268,10 @@ __device__ __forceinline__ void finish_row(const StepParams &p, const Consts<T> 
     uint32_t solid_bits = 0;
     bool all_solid = false;
     if constexpr (CALLER_MASK) {
+        // (ncu attributes 80 % of the marching kernel's executed MOVs, 11 % of all its instructions, to the joins
+        // behind this block: swapping whole packs is a renaming the compiler undoes where the paths meet.  The
+        // obvious remedy -- per-node swaps only, in place -- compiled to a kernel 8 % (40 % with the kept rows in
+        // registers) slower: profiles/README.md section 9.)
         solid_bits = solid_in;
         if (p.mask != nullptr && __any_sync(0xffffffffu, solid_bits != 0)) {
             if (__all_sync(0xffffffffu, solid_bits == (1u << V) - 1u)) {     // D2Q9.cl:410-431 on every node of the warp

@@ -16,11 +16,20 @@ static void launch_march(const StepParams &p_in, cudaStream_t st)
 {
     StepParams p = p_in;
     constexpr int OUT = 30 * V;
+    static_assert(NW % 2 == 0, "edge CTAs hold whole (west, east) pairs of work items");
     const int nstrips = (p.nx + OUT - 1) / OUT;
-    p.tiles_x = (nstrips + NW - 1) / NW;
-    p.tiles_y = (p.y_end - p.y_begin + p.seg_rows - 1) / p.seg_rows;  // segments
-    p.edge_tiles_y = p.tiles_y;                        // one edge CTA per segment and side
-    const unsigned grid = (unsigned)p.tiles_x * (unsigned)p.tiles_y;
+    const int nseg = (p.y_end - p.y_begin + p.seg_rows - 1) / p.seg_rows;
+    // strips next to a halo edge: 0 on a single slab, else strip 0 and / or the last one
+    int ne = 0;
+    if (p.edge_first) {
+        const bool w = p.west == EDGE_HALO, e = p.east == EDGE_HALO;
+        ne = (w && e && nstrips > 1) ? 2 : ((w || e) ? 1 : 0);
+    }
+    p.tiles_x = nstrips;
+    p.tiles_y = nseg;
+    p.edge_first = ne;
+    p.edge_tiles_y = (ne * nseg + NW - 1) / NW;      // edge CTAs (each serves both sides when there are two)
+    const unsigned grid = (unsigned)p.edge_tiles_y + (unsigned)(((long long)(nstrips - ne) * nseg + NW - 1) / NW);
     // handles that do not zero obstacle velocities run the instantiation without that code
     if (p.zero_obstacle_velocity) fused_march_kernel<T, V, MATH, NW, MINB, PACKED, PF, -1, SH><<<grid, 32 * NW, 0, st>>>(p);
     else fused_march_kernel<T, V, MATH, NW, MINB, PACKED, PF, 0, SH><<<grid, 32 * NW, 0, st>>>(p);

@@ -91,8 +91,7 @@ __device__ __forceinline__ uint32_t lap_solid_bits(const StepParams &p, int x0, 
     return bits;
 }
 
-// grid: 1-D.  CTA = NW warps = NW adjacent strips of one segment of rows.  Halo launches order the two edge CTA
-// columns first (they wait for / publish the ghost columns), like fused_step_kernel.
+// grid: 1-D.  CTA = NW warps = NW (strip, segment) work items, mostly adjacent strips of one segment of rows.
 // nine aligned vector loads of one row: plane j at the row its population streams from
 template <typename T, int V>
 __device__ __forceinline__ void lap_load_row(Pack<T, V> (&q)[9], const T *__restrict__ src, long long plane, int pitch, int xl,
@@ -125,28 +124,33 @@ __global__ void __launch_bounds__(32 * NW, MINB) fused_march_kernel(const StepPa
     __shared__ VT win_s[SH ? NW * 9 * 32 : 1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-    int bx, seg;
-    if (p.edge_first) {
-        const int b = blockIdx.x;
-        const int n_edge = (p.tiles_x < 2 ? 1 : 2) * p.tiles_y;
-        if (b < n_edge) {
-            if (p.tiles_x < 2) { bx = 0; seg = b; }
-            else { bx = (b & 1) ? p.tiles_x - 1 : 0; seg = b >> 1; }
-        } else {
-            const int r = b - n_edge;
-            seg = r / (p.tiles_x - 2);
-            bx = 1 + (r - seg * (p.tiles_x - 2));
-        }
+    // Work items are (strip, segment) pairs, one per warp, numbered so that no warp slot is left idle by a strip
+    // count that is not a multiple of NW: first the strips next to a halo edge (p.edge_first = 0, 1 or 2 of them per
+    // segment; their CTAs come first in the grid, wait for the neighbours' ghost columns and publish the new ones
+    // as early as possible in the launch), then all other strips, segment after segment.
+    const int nstrips = p.tiles_x, nseg = p.tiles_y, ne = p.edge_first;
+    const int n_edge_ctas = (ne * nseg + NW - 1) / NW;
+    const bool edge_cta = (int)blockIdx.x < n_edge_ctas;
+    int strip, seg;
+    bool active;
+    if (edge_cta) {
+        const int item = blockIdx.x * NW + warp;
+        active = item < ne * nseg;
+        seg = item / ne;
+        const int k = item - seg * ne;
+        strip = (ne == 2) ? (k ? nstrips - 1 : 0) : (p.west == EDGE_HALO ? 0 : nstrips - 1);
     } else {
-        seg = blockIdx.x / p.tiles_x;
-        bx = blockIdx.x - seg * p.tiles_x;
+        const int nint = nstrips - ne;
+        const int item = (blockIdx.x - n_edge_ctas) * NW + warp;
+        active = item < nint * nseg;
+        seg = nint > 0 ? item / nint : 0;
+        strip = item - seg * nint + ((ne > 0 && p.west == EDGE_HALO) ? 1 : 0);
     }
-    const bool halo_w = (p.west == EDGE_HALO) && (bx == 0);
-    const bool halo_e = (p.east == EDGE_HALO) && (bx == p.tiles_x - 1);
+    const bool halo_w = edge_cta && (p.west == EDGE_HALO);
+    const bool halo_e = edge_cta && (p.east == EDGE_HALO);
     if (halo_w && !wait_flag(p.flag_w_local, p.step_id, p.error_word, p.halo_timeout_ns)) return;
     if (halo_e && !wait_flag(p.flag_e_local, p.step_id, p.error_word, p.halo_timeout_ns)) return;
 
-    const int strip = bx * NW + warp;
     const int own0 = strip * OUT;                      // first column this strip stores
     const int x0 = own0 - V + lane * V;                // first column of this thread (lane 0: overlap to the west)
     const T *__restrict__ src = static_cast<const T *>(p.src);
@@ -159,7 +163,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) fused_march_kernel(const StepPa
     const int ye = min(ys + p.seg_rows, p.y_end);      // launches row bands (the rows just outside are only read)
     const int gs = ny + 2;
 
-    if (own0 < nx) {                                   // warp-uniform
+    if (active) {                                      // warp-uniform
         // where this thread's vector is loaded from: itself, or wrapped around a single-slab periodic box
         int xl = x0;
         if (p.west == EDGE_WRAP) { if (xl < 0) xl += nx; else if (xl >= nx) xl -= nx; }

@@ -237,6 +237,18 @@ class Pipe_Flow(object):
             results[name] = a
         return results
 
+    # -- device handles (opencl_dim.py:165-176, :231: `sim.queue`, `sim.u`, `sim.v`, `sim.rho`, `sim.f`, `sim.feq`
+    #    are pyopencl objects there; the visualiser reads `sim.u.get()` every frame, field_visualizer.py:146-157)
+    @property
+    def queue(self):
+        return _Queue(self.sim)
+
+    f = property(lambda self: _DeviceField(self, 'f'))
+    feq = property(lambda self: _DeviceField(self, 'feq'))
+    rho = property(lambda self: _DeviceField(self, 'rho'))
+    u = property(lambda self: _DeviceField(self, 'u'))
+    v = property(lambda self: _DeviceField(self, 'v'))
+
     def get_nondim_fields(self):
         """opencl_dim.py:417-426"""
         fields = self.get_fields()
@@ -250,6 +262,49 @@ class Pipe_Flow(object):
         fields['u'] *= (self.L / self.T)
         fields['v'] *= (self.L / self.T)
         return fields
+
+
+class _Queue:
+    """Stand-in for the `cl.CommandQueue` attribute: `finish()` waits for the device."""
+
+    def __init__(self, sim):
+        self._sim = sim
+
+    def finish(self):
+        self._sim.sync()
+
+    flush = finish
+
+
+class _DeviceField:
+    """Stand-in for a `pyopencl.array.Array` / `cl.Buffer` attribute of the simulation: `.get()` returns the
+    host copy in the reference's shape and order ((nx, ny[, 9]), Fortran), `.ptr` / `.pitch` the device
+    address and row pitch in elements (single-slab lattices) for zero-copy consumers."""
+
+    def __init__(self, owner, name):
+        self._owner, self.name = owner, name
+
+    @property
+    def shape(self):
+        o = self._owner
+        return (o.nx, o.ny, NUM_JUMPERS) if self.name in ('f', 'feq') else (o.nx, o.ny)
+
+    @property
+    def dtype(self):
+        return np.dtype(self._owner.sim.field_dtype(self.name))
+
+    def get(self):
+        a = np.zeros(self.shape, dtype=self.dtype, order='F')
+        self._owner.sim.download(self.name, out=a.T)
+        return a
+
+    @property
+    def ptr(self):
+        return self._owner.sim.device_ptr(self.name)[0]
+
+    @property
+    def pitch(self):
+        return self._owner.sim.device_ptr(self.name)[1]
 
 
 class Pipe_Flow_Cylinder(Pipe_Flow):

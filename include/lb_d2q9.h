@@ -62,8 +62,13 @@ enum lb_bc {
  *   LB_MATH_STRICT  mirrors D2Q9.cl operation by operation (association order,
  *                   IEEE division, no FMA contraction): bit-identical to the
  *                   CPU oracle.
- *   LB_MATH_FAST    same formulas with reciprocal constants and FMA; agrees
- *                   with STRICT to rounding (tolerances in tests/). */
+ *   LB_MATH_FAST    same formulas with reciprocal constants and FMA.  Agrees with
+ *                   STRICT to rounding: rho and u within 1e-5 (relative) for runs of
+ *                   up to 500 steps in fp32, 1e-12 in fp64 (2000 steps).  Longer fp32
+ *                   runs accumulate round-off like a random walk in BOTH arithmetics,
+ *                   which then drift apart (rho 1.5e-5 .. 2e-5, u 5e-5 .. 1.4e-4 of
+ *                   max|u| at 2000 steps) while each stays about as close to the fp64 solution
+ *                   (tests/test_parity_gpu.py::test_fast_math_error_growth_...). */
 enum lb_math { LB_MATH_STRICT = 0, LB_MATH_FAST = 1 };
 
 /* Which of the reference's two step algorithms the handle runs.

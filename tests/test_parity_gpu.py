@@ -1213,3 +1213,79 @@ def test_streamed_run_equals_upload_step_download(gpu, dtype):
             rho = np.empty((ny, nx), dtype=dtype)
             sim.run_streamed(f0, 7, rho=rho)
             assert np.array_equal(rho, want["rho"]) and np.array_equal(sim.download("f"), want["f"])
+
+
+def test_tall_lattice_beyond_the_grid_y_limit(gpu):
+    """ny > 65535: the one-thread-per-node helper kernels (mask, initialiser, feq, single stages) fold their row
+    index over gridDim.z like the step kernels do.  Initial state, a disk mask across the fold, a
+    few steps with both kernels, feq read-back and a stage sequence against the fused step."""
+    from lb_b200 import Lattice
+    nx, ny = 128, 70001
+    sums = []
+    for tb in ("off", "march.w4b5.sh.s256"):
+        with Lattice(nx, ny, 1.5, 1.002, 1.0) as sim:
+            sim.set_temporal_blocking(tb)
+            sim.set_mask_disk(64.0, 65600.0, 30.0)
+            sim.init_synthetic("pipe_ramp", amplitude=1e-3, seed=4)
+            sim.run(5)
+            rho, feq = sim.download("rho"), sim.download("feq")
+            assert np.isfinite(rho).all() and rho[65590:65610].min() > 0.9 and rho[-1].min() > 0.9
+            assert np.isfinite(feq).all() and abs(feq[:, 69000].sum() / (nx * rho[69000].mean()) - 1) < 1e-3
+            sums.append(sim.checksum())
+    assert sums[0] == sums[1]
+    with Lattice(nx, ny, 1.5, 1.002, 1.0) as a, Lattice(nx, ny, 1.5, 1.002, 1.0) as b:
+        for sim in (a, b):
+            sim.set_mask_disk(64.0, 65600.0, 30.0)
+            sim.init_synthetic("pipe_ramp", amplitude=1e-3, seed=4)
+        a.set_temporal_blocking("off")
+        a.run(1)
+        for stage in ("move", "move_bcs", "update_hydro", "update_feq", "collide_particles"):
+            getattr(b, stage)()
+        assert a.checksum() == b.checksum()
+        assert np.array_equal(a.download("u")[65000:], b.download("u")[65000:])
+
+
+def test_fast_math_error_growth_is_what_the_header_states(gpu, orc):
+    """include/lb_d2q9.h states the FAST contract: rho and u within 1e-5 (relative) of STRICT / the oracle up to
+    500 steps; beyond that fp32 round-off accumulates like a random walk in BOTH arithmetics and the two drift
+    apart -- at 2000 steps FAST is still about as close to the fp64 solution as the reference-order arithmetic is
+    (B200, this case: FAST vs STRICT rho 1.5e-5, u 5e-5 of max|u|; vs fp64: rho 3.5e-5 FAST / 2.2e-5 STRICT).
+    This records the figures."""
+    from lb_b200 import Lattice
+    f0, m = pipe_case(orc, 256, 128, np.float32, mask="blocks", inlet_rho=1.02)
+    truth = orc.OpenCLSchemeOracle(f0, 1.3, 1.02, 1.0, mask=m, dtype=np.float64)
+    res = {}
+    with Lattice(256, 128, 1.3, 1.02, 1.0, mask=m, f0=f0, math="strict") as s, \
+            Lattice(256, 128, 1.3, 1.02, 1.0, mask=m, f0=f0, math="fast") as f:
+        done = 0
+        for n in (500, 2000):
+            truth.run(n - done); s.run(n - done); f.run(n - done)
+            done = n
+            sr, fr = s.download("rho"), f.download("rho")
+            su, fu = s.download("u"), f.download("u")
+            umax = float(np.abs(truth.u).max())
+            res[n] = dict(fast_vs_strict_rho=rel_err(fr, sr), fast_vs_strict_u=float(np.abs(fu - su).max()) / umax,
+                          strict_vs_fp64_rho=rel_err(sr, truth.rho), fast_vs_fp64_rho=rel_err(fr, truth.rho),
+                          strict_vs_fp64_u=float(np.abs(su - truth.u).max()) / umax, fast_vs_fp64_u=float(np.abs(fu - truth.u).max()) / umax)
+    print("FAST error growth:", res)
+    assert res[500]["fast_vs_strict_rho"] <= 1e-5
+    assert res[500]["fast_vs_strict_u"] <= 1e-4          # |du| / max|u|; u itself is O(1e-2) here
+    for n in (500, 2000):
+        assert res[n]["fast_vs_fp64_rho"] <= 2.0 * res[n]["strict_vs_fp64_rho"] + 1e-7
+        assert res[n]["fast_vs_fp64_u"] <= 2.0 * res[n]["strict_vs_fp64_u"] + 1e-6
+    assert res[2000]["fast_vs_strict_rho"] <= 1e-4
+
+
+def test_device_handle_attributes_of_the_drop_in_class(gpu):
+    """sim.queue / sim.u / sim.rho / sim.f (pyopencl objects in the reference, opencl_dim.py:165-176; the
+    visualiser calls sim.u.get() every frame) exist here too: .get() is the field of get_fields()."""
+    import lb_b200.dimensionless as lb
+    np.random.seed(1)
+    sim = lb.Pipe_Flow(diameter=1., rho=1., viscosity=1., pressure_grad=-10., pipe_length=3., N=20, time_prefactor=4., verbose=False)
+    sim.run(7)
+    sim.queue.finish()
+    fields = sim.get_fields()
+    for k in ("u", "v", "rho", "f", "feq"):
+        got = getattr(sim, k).get()
+        assert got.flags.f_contiguous and got.shape == fields[k].shape and np.array_equal(got, fields[k]), k
+    assert sim.u.ptr and sim.u.pitch >= sim.nx

@@ -1,0 +1,10 @@
+#!/bin/bash
+set -u
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+S=march.w4b5.sh.s64,march.w4b4.s64
+timeout 600 python tools/tb2_sweep.py --nx 32768 --ny 32768 --steps 20 --reps 3 --shapes $S 2>&1 | tee gpurun_out/r2_flat_sweep_c4.txt
+timeout 300 python tools/tb2_sweep.py --nx 4096 --ny 32768 --steps 20 --reps 3 --shapes $S 2>&1 | tee gpurun_out/r2_flat_sweep_slab.txt
+timeout 300 python tools/tb2_sweep.py --nx 8192 --ny 32768 --steps 20 --reps 3 --shapes $S 2>&1 | tee gpurun_out/r2_flat_sweep_slab4.txt
+timeout 1500 python -m pytest tests/test_parity_gpu.py -x -q -m gpu -k "temporal_blocking or two_update or self_ring or half_as_many or streamed or tall_lattice or fast_math_error or device_handle or bulky or halo_timeout or slab" > gpurun_out/r2_flat_tests.txt 2>&1
+tail -5 gpurun_out/r2_flat_tests.txt
