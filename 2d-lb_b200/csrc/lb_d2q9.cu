@@ -611,7 +611,9 @@ static int tb2_find(const char *name)
 static int tb2_auto_shape(const lb_sim *sim)
 {
     if ((long long)sim->cfg.global_nx * sim->cfg.ny < (1ll << 22) || sim->cfg.ny < 64) return 0;
-    const int k = tb2_find(sim->elem == 4 ? g_tb_auto_f32 : g_tb_auto_f64);
+    // (slabs of one lattice may run different SHAPES -- only the launch sequence has to agree -- so the choice
+    // may depend on whether this slab has a mask)
+    const int k = tb2_find((sim->elem == 4 ? g_tb_auto_f32 : g_tb_auto_f64)[sim->mask != nullptr]);
     return (k > 0 && !tb_refusal(sim, k)) ? k : 0;
 }
 

@@ -197,7 +197,13 @@ __device__ __forceinline__ bool wait_flag(const unsigned int *flag, unsigned int
 //      profiles/r2_march_regs_vs_smem_window_bc_inline_vs_call.txt.)
 enum : int { ROW_FULL = 0, ROW_TO_REGISTERS = 1, ROW_FROM_TILE = 2, ROW_REGS_NOFIX = 3 };
 
-template <typename T, int V, int MATH, int STP, int MODEL, int ROLE = ROW_FULL, bool PACKED = false, bool CALLER_MASK = false, int ZOV = -1>
+//      MASKED (with CALLER_MASK): -1 = look at p.mask at run time and branch (pack swap for all-solid warps, per-node
+//      swaps otherwise); 0 = the handle has no mask, no obstacle code at all; 1 = it has one, and the bounce-back swap
+//      is eight selects per node, always executed, no branch.  The branchy form renames whole register packs on one
+//      of its paths, and where the paths join the compiler moves them back: ncu attributed 80 % of the marching
+//      kernel's executed MOVs -- 11 % of all its instructions -- to those joins (profiles/README.md section 9).
+template <typename T, int V, int MATH, int STP, int MODEL, int ROLE = ROW_FULL, bool PACKED = false, bool CALLER_MASK = false, int ZOV = -1,
+          int MASKED = -1>
 __device__ __forceinline__ void finish_row(const StepParams &p, const Consts<T> &c, Pack<T, V> (&q)[9],
                                            const T *__restrict__ src, T *__restrict__ dst,
                                            int x0, int span0, int y, int ym, int yp,
@@ -267,11 +273,23 @@ __device__ __forceinline__ void finish_row(const StepParams &p, const Consts<T> 
     //     whole register packs -- a compile-time renaming, no mask bytes loaded, no per-node selects.
     uint32_t solid_bits = 0;
     bool all_solid = false;
-    if constexpr (CALLER_MASK) {
-        // (ncu attributes 80 % of the marching kernel's executed MOVs, 11 % of all its instructions, to the joins
-        // behind this block: swapping whole packs is a renaming the compiler undoes where the paths meet.  The
-        // obvious remedy -- per-node swaps only, in place -- compiled to a kernel 8 % (40 % with the kept rows in
-        // registers) slower: profiles/README.md section 9.)
+    if constexpr (CALLER_MASK && MASKED == 0) {
+        // no mask on this handle: nothing to do
+    } else if constexpr (CALLER_MASK && MASKED == 1) {
+        solid_bits = solid_in;
+        const bool zov_ = ZOV < 0 ? (p.zero_obstacle_velocity != 0) : (ZOV != 0);
+        if (zov_) all_solid = __all_sync(0xffffffffu, solid_bits == (1u << V) - 1u);
+#pragma unroll
+        for (int e = 0; e < V; ++e) {                     // D2Q9.cl:410-431, as selects
+            const bool sd = (solid_bits >> e) & 1u;
+            const T f1 = q[1].v[e], f2 = q[2].v[e], f3 = q[3].v[e], f4 = q[4].v[e];
+            const T f5 = q[5].v[e], f6 = q[6].v[e], f7 = q[7].v[e], f8 = q[8].v[e];
+            q[1].v[e] = sd ? f3 : f1; q[3].v[e] = sd ? f1 : f3;
+            q[2].v[e] = sd ? f4 : f2; q[4].v[e] = sd ? f2 : f4;
+            q[5].v[e] = sd ? f7 : f5; q[7].v[e] = sd ? f5 : f7;
+            q[6].v[e] = sd ? f8 : f6; q[8].v[e] = sd ? f6 : f8;
+        }
+    } else if constexpr (CALLER_MASK) {
         solid_bits = solid_in;
         if (p.mask != nullptr && __any_sync(0xffffffffu, solid_bits != 0)) {
             if (__all_sync(0xffffffffu, solid_bits == (1u << V) - 1u)) {     // D2Q9.cl:410-431 on every node of the warp

@@ -36,5 +36,5 @@ struct LbTbShape {
 };
 extern const LbTbShape g_tb_shapes[];
 extern const int g_ntb;
-extern const char *const g_tb_auto_f32;   // names of the shapes lb_step picks on its own
-extern const char *const g_tb_auto_f64;
+extern const char *const g_tb_auto_f32[2];   // names of the shapes lb_step picks on its own: [no mask, mask]
+extern const char *const g_tb_auto_f64[2];

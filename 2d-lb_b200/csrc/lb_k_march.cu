@@ -11,7 +11,8 @@
 
 using namespace lb;
 
-template <typename T, int V, int MATH, int NW, int MINB, bool PACKED, bool PF = false, bool SH = false>
+// BF: branch-free obstacle handling (three instantiations: no mask / mask / mask + run-time velocity zeroing)
+template <typename T, int V, int MATH, int NW, int MINB, bool PACKED, bool PF = false, bool SH = false, bool BF = false>
 static void launch_march(const StepParams &p_in, cudaStream_t st)
 {
     StepParams p = p_in;
@@ -30,12 +31,20 @@ static void launch_march(const StepParams &p_in, cudaStream_t st)
     p.edge_first = ne;
     p.edge_tiles_y = (ne * nseg + NW - 1) / NW;      // edge CTAs (each serves both sides when there are two)
     const unsigned grid = (unsigned)p.edge_tiles_y + (unsigned)(((long long)(nstrips - ne) * nseg + NW - 1) / NW);
+    if (BF) {
+        if (p.mask == nullptr) fused_march_kernel<T, V, MATH, NW, MINB, PACKED, PF, 0, SH, 0><<<grid, 32 * NW, 0, st>>>(p);
+        else if (p.zero_obstacle_velocity) fused_march_kernel<T, V, MATH, NW, MINB, PACKED, PF, -1, SH, 1><<<grid, 32 * NW, 0, st>>>(p);
+        else fused_march_kernel<T, V, MATH, NW, MINB, PACKED, PF, 0, SH, 1><<<grid, 32 * NW, 0, st>>>(p);
+        return;
+    }
     // handles that do not zero obstacle velocities run the instantiation without that code
     if (p.zero_obstacle_velocity) fused_march_kernel<T, V, MATH, NW, MINB, PACKED, PF, -1, SH><<<grid, 32 * NW, 0, st>>>(p);
     else fused_march_kernel<T, V, MATH, NW, MINB, PACKED, PF, 0, SH><<<grid, 32 * NW, 0, st>>>(p);
 }
 // name: march.w<warps per CTA>b<CTAs per SM>[.sh | .scalar | .pf].s<rows per segment>
 //   .sh      the kept rows of the intermediate level in shared memory (thread-private slots): the shipped form
+//   .sh.bf   ... and the bounce-back swap as selects instead of branches (one instantiation per "has a mask" /
+//            "zeroes obstacle velocities"): the shipped form on lattices WITH an obstacle mask
 //   (none)   ... in registers
 //   .scalar  registers, scalar fp32 collision instead of the packed one (A/B)
 //   .pf      registers, software-prefetched loads (LB_EXPERIMENTS; measured slower)
@@ -54,6 +63,11 @@ static void launch_march(const StepParams &p_in, cudaStream_t st)
     {"march.w" #NW "b" #MINB ".sh.s" #S, LB_TB_MARCH, S, NW, 0, 0, 0,                                            \
      {{launch_march<float, 4, MATH_STRICT, NW, MINB, true, false, true>, launch_march<float, 4, MATH_FAST, NW, MINB, true, false, true>},   \
       {launch_march<double, 2, MATH_STRICT, NW, MINB, false, false, true>, launch_march<double, 2, MATH_FAST, NW, MINB, false, false, true>}}, \
+     {{nullptr, nullptr}, {nullptr, nullptr}}, {{nullptr, nullptr}, {nullptr, nullptr}}}
+#define MARCHBF(NW, MINB, S)                                                                                     \
+    {"march.w" #NW "b" #MINB ".sh.bf.s" #S, LB_TB_MARCH, S, NW, 0, 0, 0,                                         \
+     {{launch_march<float, 4, MATH_STRICT, NW, MINB, true, false, true, true>, launch_march<float, 4, MATH_FAST, NW, MINB, true, false, true, true>},   \
+      {launch_march<double, 2, MATH_STRICT, NW, MINB, false, false, true, true>, launch_march<double, 2, MATH_FAST, NW, MINB, false, false, true, true>}}, \
      {{nullptr, nullptr}, {nullptr, nullptr}}, {{nullptr, nullptr}, {nullptr, nullptr}}}
 #define MARCH_S(NW, MINB, PACKED, PN) MARCH(NW, MINB, PACKED, PN, 32), MARCH(NW, MINB, PACKED, PN, 64), MARCH(NW, MINB, PACKED, PN, 128), MARCH(NW, MINB, PACKED, PN, 256)
 
@@ -117,6 +131,7 @@ static void launch_tb2v(const StepParams &p, dim3 grid, size_t smem, cudaStream_
 const LbTbShape g_tb_shapes[] = {
     {"off", LB_TB_OFF, 0, 0, 0, 0, 0, {{nullptr, nullptr}, {nullptr, nullptr}}, {{nullptr, nullptr}, {nullptr, nullptr}}, {{nullptr, nullptr}, {nullptr, nullptr}}},
     MARCHSH_S(4, 5),
+    MARCHBF(4, 5, 32), MARCHBF(4, 5, 64), MARCHBF(4, 6, 64),
     MARCH_S(4, 4, true, ""),
     MARCH(4, 4, false, ".scalar", 64),
 #ifdef LB_EXPERIMENTS
@@ -135,5 +150,6 @@ const LbTbShape g_tb_shapes[] = {
 #endif
 };
 const int g_ntb = (int)(sizeof(g_tb_shapes) / sizeof(g_tb_shapes[0]));
-const char *const g_tb_auto_f32 = "march.w4b5.sh.s64";
-const char *const g_tb_auto_f64 = "march.w4b5.sh.s64";
+// measured best per case (profiles/README.md section 9.3): [0] lattices without an obstacle mask, [1] with one
+const char *const g_tb_auto_f32[2] = {"march.w4b5.sh.s64", "march.w4b6.sh.bf.s64"};
+const char *const g_tb_auto_f64[2] = {"march.w4b5.sh.s64", "march.w4b5.sh.bf.s64"};

@@ -116,7 +116,7 @@ __device__ __forceinline__ void lap_load_row(Pack<T, V> (&q)[9], const T *__rest
 // SH: the kept rows of the intermediate level live in shared memory instead of registers -- nine 16-byte slots per
 // thread, private to it (no other thread reads them: no synchronisation, no bank conflicts) -- which brings the
 // kernel under 100 registers and 20 instead of 16 warps onto an SM.
-template <typename T, int V, int MATH, int NW, int MINB, bool PACKED, bool PF = false, int ZOV = -1, bool SH = false>
+template <typename T, int V, int MATH, int NW, int MINB, bool PACKED, bool PF = false, int ZOV = -1, bool SH = false, int MASKED = -1>
 __global__ void __launch_bounds__(32 * NW, MINB) fused_march_kernel(const StepParams p)
 {
     constexpr int OUT = 30 * V;
@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) fused_march_kernel(const StepPa
             }
             if (valid) {
                 if (!PF) lap_load_row<T, V>(q, src, plane, pitch, xl, gy, ym, yp);
-                solid_now = lap_solid_bits<V>(p, x0, xl, gy);
+                if (MASKED != 0) solid_now = lap_solid_bits<V>(p, x0, xl, gy);
                 if (ghost_w) {                         // memory "continues" into the west neighbour: columns -2, -1
                     const T *G = static_cast<const T *>(p.ghost_w);
 #pragma unroll
@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) fused_march_kernel(const StepPa
                     }
                 }
                 lap_shift_x<T, V>(q);
-                finish_row<T, V, MATH, 0, MODEL_D2Q9, ROW_REGS_NOFIX, PACKED, true, ZOV>(p, c, q, src, dst, x0, own0, gy, ym, yp, solid_now, false);
+                finish_row<T, V, MATH, 0, MODEL_D2Q9, ROW_REGS_NOFIX, PACKED, true, ZOV, MASKED>(p, c, q, src, dst, x0, own0, gy, ym, yp, solid_now, false);
             } else {
 #pragma unroll
                 for (int j = 0; j < 9; ++j)
@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) fused_march_kernel(const StepPa
                     win[(o + 0) * 32] = repack(q[2]); win[(o + 1) * 32] = repack(q[5]); win[(o + 2) * 32] = repack(q[6]);
                 }
                 lap_shift_x<T, V>(z);
-                finish_row<T, V, MATH, 0, MODEL_D2Q9, ROW_FROM_TILE, PACKED, true, ZOV>(p, c, z, src, dst, x0, own0, r, rm, rp, solid_prev, store_ok);
+                finish_row<T, V, MATH, 0, MODEL_D2Q9, ROW_FROM_TILE, PACKED, true, ZOV, MASKED>(p, c, z, src, dst, x0, own0, r, rm, rp, solid_prev, store_ok);
             }
             // ---- rotate the kept rows --------------------------------------------------------------------
             if (SH) {

@@ -44,12 +44,12 @@ def test_every_evidence_file_named_in_the_profiles_readme_exists():
     import re
     prof = os.path.join(ROOT, "profiles")
     text = open(os.path.join(prof, "README.md")).read()
-    names = set(re.findall(r"`((?:history/)?r1_[A-Za-z0-9_.\-]+\.(?:txt|json|csv))`", text))
-    assert len(names) > 30
+    names = set(re.findall(r"`((?:history/)?r[12]_[A-Za-z0-9_.\-]+\.(?:txt|json|csv))`", text))
+    assert len(names) > 40
     missing = sorted(n for n in names if not os.path.exists(os.path.join(prof, n)))
     assert not missing, missing
     traffic = json.load(open(os.path.join(prof, "traffic.json")))
-    for key in ("f32", "f64", "f32_tb2"):
-        assert traffic[key]["dram_bytes_per_lattice_update"] > 0
+    for key in ("f32", "f64", "f32_march"):
+        assert traffic[key]["dram_bytes_per_node_per_launch"] > 0 and len(traffic[key]["grid"]) == 2
         src = traffic[key]["source"].split(" ")[0]
         assert os.path.exists(os.path.join(ROOT, src)), src

@@ -38,6 +38,9 @@ def main():
     print(f"# {a.nx}x{a.ny} {a.dtype} {a.math} {a.bc}, {a.steps} steps per run")
     base, want = None, None
     wanted = [w for w in a.shapes.split(",") if w]
+    if "auto" in wanted:                # the shape lb_step picks on this lattice by itself
+        sim.set_temporal_blocking("auto")
+        wanted = [w for w in wanted if w != "auto"] + [sim.temporal_blocking]
     for k, name in enumerate(names):
         if wanted and name != "off" and name not in wanted:
             continue
