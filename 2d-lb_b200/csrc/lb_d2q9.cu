@@ -612,8 +612,18 @@ static int tb2_auto_shape(const lb_sim *sim)
 {
     if ((long long)sim->cfg.global_nx * sim->cfg.ny < (1ll << 22) || sim->cfg.ny < 64) return 0;
     // (slabs of one lattice may run different SHAPES -- only the launch sequence has to agree -- so the choice
-    // may depend on whether this slab has a mask)
-    const int k = tb2_find((sim->elem == 4 ? g_tb_auto_f32 : g_tb_auto_f64)[sim->mask != nullptr]);
+    // may depend on what this slab looks like)
+    // Segment height: a warp walks `seg` rows of one strip.  Short segments cost two extra phase-1 rows each, long
+    // ones leave too few (strip, segment) work items to fill and balance 148 SMs x 20-24 warps; measured best is
+    // around 50 000 items (profiles/r2_march_segment_height_*.txt), i.e. 8 rows on a 4096 x 1024 lattice, 16 on a
+    // 4096 x 32768 slab, 64 on C4.
+    const int out = sim->elem == 4 ? 120 : 60;
+    const long long nstrips = (sim->cfg.nx + out - 1) / out;
+    const long long want = nstrips * sim->cfg.ny / 49152;
+    int seg = 8;
+    while (seg < 64 && 2 * seg <= want) seg *= 2;
+    const std::string name = std::string((sim->elem == 4 ? g_tb_auto_f32 : g_tb_auto_f64)[sim->mask != nullptr]) + ".s" + std::to_string(seg);
+    const int k = tb2_find(name.c_str());
     return (k > 0 && !tb_refusal(sim, k)) ? k : 0;
 }
 

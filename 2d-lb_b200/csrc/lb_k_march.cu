@@ -58,7 +58,7 @@ static void launch_march(const StepParams &p_in, cudaStream_t st)
      {{launch_march<float, 4, MATH_STRICT, NW, MINB, true, true>, launch_march<float, 4, MATH_FAST, NW, MINB, true, true>},   \
       {launch_march<double, 2, MATH_STRICT, NW, MINB, false, true>, launch_march<double, 2, MATH_FAST, NW, MINB, false, true>}}, \
      {{nullptr, nullptr}, {nullptr, nullptr}}, {{nullptr, nullptr}, {nullptr, nullptr}}}
-#define MARCHSH_S(NW, MINB) MARCHSH(NW, MINB, 32), MARCHSH(NW, MINB, 64), MARCHSH(NW, MINB, 128), MARCHSH(NW, MINB, 256)
+#define MARCHSH_S(NW, MINB) MARCHSH(NW, MINB, 8), MARCHSH(NW, MINB, 16), MARCHSH(NW, MINB, 32), MARCHSH(NW, MINB, 64), MARCHSH(NW, MINB, 128), MARCHSH(NW, MINB, 256)
 #define MARCHSH(NW, MINB, S)                                                                                     \
     {"march.w" #NW "b" #MINB ".sh.s" #S, LB_TB_MARCH, S, NW, 0, 0, 0,                                            \
      {{launch_march<float, 4, MATH_STRICT, NW, MINB, true, false, true>, launch_march<float, 4, MATH_FAST, NW, MINB, true, false, true>},   \
@@ -131,7 +131,8 @@ static void launch_tb2v(const StepParams &p, dim3 grid, size_t smem, cudaStream_
 const LbTbShape g_tb_shapes[] = {
     {"off", LB_TB_OFF, 0, 0, 0, 0, 0, {{nullptr, nullptr}, {nullptr, nullptr}}, {{nullptr, nullptr}, {nullptr, nullptr}}, {{nullptr, nullptr}, {nullptr, nullptr}}},
     MARCHSH_S(4, 5),
-    MARCHBF(4, 5, 32), MARCHBF(4, 5, 64), MARCHBF(4, 6, 64),
+    MARCHBF(4, 5, 8), MARCHBF(4, 5, 16), MARCHBF(4, 5, 32), MARCHBF(4, 5, 64), MARCHBF(4, 5, 128),
+    MARCHBF(4, 6, 8), MARCHBF(4, 6, 16), MARCHBF(4, 6, 32), MARCHBF(4, 6, 64), MARCHBF(4, 6, 128),
     MARCH_S(4, 4, true, ""),
     MARCH(4, 4, false, ".scalar", 64),
 #ifdef LB_EXPERIMENTS
@@ -150,6 +151,7 @@ const LbTbShape g_tb_shapes[] = {
 #endif
 };
 const int g_ntb = (int)(sizeof(g_tb_shapes) / sizeof(g_tb_shapes[0]));
-// measured best per case (profiles/README.md section 9.3): [0] lattices without an obstacle mask, [1] with one
-const char *const g_tb_auto_f32[2] = {"march.w4b5.sh.s64", "march.w4b6.sh.bf.s64"};
-const char *const g_tb_auto_f64[2] = {"march.w4b5.sh.s64", "march.w4b5.sh.bf.s64"};
+// measured best per case (profiles/README.md section 9.3): [0] lattices without an obstacle mask, [1] with one;
+// lb_step appends the segment height (".s<rows>", chosen from the lattice size)
+const char *const g_tb_auto_f32[2] = {"march.w4b5.sh", "march.w4b6.sh.bf"};
+const char *const g_tb_auto_f64[2] = {"march.w4b5.sh", "march.w4b5.sh.bf"};
