@@ -1,11 +1,20 @@
 #!/bin/bash
-# Short version of gpu_scaling.sh for a tight GPU budget: C4 at N=1 (kernel only) and N=NG, same box.
+# Quick 8-GPU confirmation (gpurun --gpus 8 -- 'bash tools/gpu_scaling_quick.sh'): C4 at N = 8 and N = 1 on the same
+# box and C5 at N = 8.  The full set (bit-identity check, N = 4, 2, the one-update kernel) is tools/gpu_scaling.sh.
 set -u
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 NG=$(nvidia-smi -L | wc -l)
 TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
-timeout 300 python bench.py --gpus 1 --steps 100 --warmup 5 --no-e2e --no-cpu-baseline > gpurun_out/q_bench_c4_n1.json 2> gpurun_out/q_bench_c4_n1.err
-timeout 300 $TR --nproc-per-node $NG --master-port 29561 bench.py --gpus $NG --steps 100 --warmup 5 > gpurun_out/q_bench_c4_n$NG.json 2> gpurun_out/q_bench_c4_n$NG.err
-for f in gpurun_out/q_bench_c4_n*.json; do cut -c1-170 $f; done
-tail -n 3 gpurun_out/q_bench_c4_n$NG.err
+timeout 400 $TR --nproc-per-node $NG --master-port 29538 bench.py --gpus $NG --steps 100 --warmup 5 --no-e2e > gpurun_out/r2_final_scaling_c4_n$NG.json 2> gpurun_out/r2_final_scaling_c4_n$NG.err
+timeout 400 python bench.py --gpus 1 --steps 100 --warmup 5 --no-cpu-baseline --no-e2e > gpurun_out/r2_final_scaling_c4_n1.json 2> gpurun_out/r2_final_scaling_c4_n1.err
+timeout 400 $TR --nproc-per-node $NG --master-port 29541 bench.py --gpus $NG --workload c5 --steps 100 --warmup 5 --no-e2e > gpurun_out/r2_final_scaling_c5_n$NG.json 2> gpurun_out/r2_final_scaling_c5_n$NG.err
+for f in gpurun_out/r2_final_scaling_*.json; do python - "$f" <<'PY'
+import json,sys
+try:
+    d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+    print(sys.argv[1].split("/")[-1], "N", d["n_gpus"], "value", round(d["value"]), "ms", round(d["ms_per_step"],4), "launches", d["gpu_launches"], "checksum", d["checks"]["checksum"], d["config"]["kernel"][:52], d["clocks"])
+except Exception as e:
+    print(sys.argv[1], "unreadable", e)
+PY
+done
