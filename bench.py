@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Benchmark of the D2Q9 hot path (one fused collide-and-stream kernel per lattice update).
+"""Benchmark of the D2Q9 hot path (one fused collide-and-stream kernel per lattice update -- per TWO updates on
+lattices of at least 2^22 nodes, where lb_step runs the marching kernel).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c4|c2|c3|c5] [--impl reference]
 
@@ -17,10 +18,14 @@ the whole grid.  Workloads are BASELINE.json's configs:
   c5           channel flow 16384x16384 fp64 PER GPU, weak scaling
   pub          the reference's published benchmark through the drop-in class API (vs_baseline = / 317.5 MLUPS)
 `value`  : device-resident throughput, CUDA events around K launches, max over ranks.
-`e2e`    : the same K steps through the C-ABI with HOST buffers: lb_upload_f from pinned memory,
-           lb_step(K), lb_download of rho, u, v -- all inside the timed region.
-`roofline`: 72 B (fp32) / 144 B (fp64) per lattice update over the average launch duration,
-           against MEASURED_PEAKS.json's hbm_gbs.
+`e2e`    : the same K steps through the C-ABI with HOST buffers: upload of f from pinned memory, K steps,
+           read-back of rho, u, v -- all inside the timed region (N = 1: one pipelined lb_run_streamed call;
+           N > 1: lb_upload_f + lb_halo_prime + lb_step + lb_download per rank).
+`roofline`: achieved = ALGORITHMIC bytes per launch (72 B fp32 / 144 B fp64 per lattice update x updates per
+           launch) over the average launch duration, against MEASURED_PEAKS.json's hbm_gbs; `traffic` = the
+           kernel's measured DRAM bytes per launch (ncu, profiles/traffic.json) and `frac_on_measured_traffic`
+           what that amounts to -- the two-update kernel moves about half the algorithmic bytes.
+`checks.checksum`: exact 64-bit checksum of the final populations, summed over ranks: equal at every N.
 `cpu_baseline`: the unmodified reference Cython path (oracle/_ref) on one host core, bounded sample.
 `--impl reference`: the reference's CPU path on all host cores (independent replicas; the
            reference has no threaded path), same metric/config keys.

@@ -222,10 +222,11 @@ int lb_set_mask_disk(lb_sim *sim, double cx, double cy, double r);
  *    odd; the launch that ends the run also stores rho, u, v.  Results are bit-identical to the one-update
  *    kernel in both math modes, on single slabs and on halo-connected slabs (which then exchange two columns
  *    every second step instead of one column every step).
- *    shape -1 = automatic (default): the measured-best shape when the WHOLE lattice (global_nx x ny) has at
- *    least 2^22 nodes and ny >= 64, the graph-batched one-update kernel below that; 0 = off;
- *    1 .. lb_tb2_shape_count()-1 = a compiled shape by index (lb_tb2_shape_name:
- *    "march.w<warps per CTA>b<CTAs per SM>[.scalar].s<rows per segment>").  Serves LB_SCHEME_OPENCL /
+ *    shape -1 = automatic (default): when the WHOLE lattice (global_nx x ny) has at least 2^22 nodes and
+ *    ny >= 64, the measured-best shape for this slab -- branch-free obstacle code where there is a mask, a
+ *    segment height of 8 to 64 rows that gives about 50 000 (strip, segment) work items -- and the
+ *    graph-batched one-update kernel below that size; 0 = off; 1 .. lb_tb2_shape_count()-1 = a compiled shape
+ *    by index (lb_tb2_shape_name: "march.w<warps per CTA>b<CTAs per SM>[.sh[.bf] | .scalar].s<rows per segment>").  Serves LB_SCHEME_OPENCL /
  *    LB_MODEL_D2Q9 lattices; a single-slab periodic box needs nx to be a multiple of the vector width (4 fp32 /
  *    2 fp64 cells).  All slabs of one lattice must use the same setting.  lb_temporal_blocking returns the
  *    shape lb_step will use (0 = one-update kernel). */
