@@ -21,7 +21,7 @@ using namespace lb;
 // =====================================================================================
 struct HaloLayout {
     size_t ghost_bytes;     // one ghost column: GHOST_SLOTS*(ny+2) elements, rounded to 256 B
-    size_t mask_bytes;      // one mask column: ny bytes, rounded to 256 B
+    size_t mask_bytes;      // the mask of one neighbour's GHOST_COLS-1 outermost columns: [c][ny] bytes, rounded to 256 B
     size_t off_ghost_w[2], off_ghost_e[2];
     size_t off_mask_w, off_mask_e;
     size_t off_flag_w, off_flag_e, off_done_w, off_done_e, off_error;
@@ -32,7 +32,7 @@ static HaloLayout halo_layout(int ny, int elem)
 {
     HaloLayout h;
     h.ghost_bytes = (((size_t)GHOST_SLOTS * (ny + 2) * elem) + 255) / 256 * 256;
-    h.mask_bytes = ((size_t)ny + 255) / 256 * 256;
+    h.mask_bytes = ((size_t)(GHOST_COLS - 1) * ny + 255) / 256 * 256;
     size_t o = 0;
     for (int p = 0; p < 2; ++p) { h.off_ghost_w[p] = o; o += h.ghost_bytes; }
     for (int p = 0; p < 2; ++p) { h.off_ghost_e[p] = o; o += h.ghost_bytes; }
@@ -365,40 +365,26 @@ __global__ void k_checksum(int nx, int ny, int pitch, long long plane, const T *
     if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
 }
 
-// copies the current state's two outermost columns (nine-slot layout, lb_fused.cuh StepParams) and the
-// obstacle mask of the boundary column into the neighbours' arenas, then publishes the flag
+// copies the current state's GHOST_COLS outermost columns (all nine populations; layout: lb_fused.cuh StepParams)
+// and the obstacle mask of the outermost GHOST_COLS-1 columns into the neighbours' arenas, then publishes the flag
 template <typename T>
 __global__ void k_halo_prime(int nx, int ny, int pitch, long long plane, const T *f, const uint8_t *mask, int mask_pitch,
                              T *out_w, T *out_e, uint8_t *mask_w, uint8_t *mask_e,
                              unsigned int *flag_w_remote, unsigned int *flag_e_remote, unsigned int *error_word, unsigned int value)
 {
     const int gs = ny + 2;
-    const int c1 = nx > 1 ? 1 : 0, c2 = nx > 1 ? nx - 2 : 0;
     for (int y = threadIdx.x; y < ny; y += blockDim.x) {
         const long long row = (long long)y * pitch;
-        if (out_w) {
-            out_w[0 * gs + y + 1] = f[3 * plane + row];
-            out_w[1 * gs + y + 1] = f[6 * plane + row];
-            out_w[2 * gs + y + 1] = f[7 * plane + row];
-            out_w[3 * gs + y + 1] = f[0 * plane + row];
-            out_w[4 * gs + y + 1] = f[2 * plane + row];
-            out_w[5 * gs + y + 1] = f[4 * plane + row];
-            out_w[6 * gs + y + 1] = f[3 * plane + row + c1];
-            out_w[7 * gs + y + 1] = f[6 * plane + row + c1];
-            out_w[8 * gs + y + 1] = f[7 * plane + row + c1];
-            mask_w[y] = mask ? mask[(long long)y * mask_pitch] : 0;
-        }
-        if (out_e) {
-            out_e[0 * gs + y + 1] = f[1 * plane + row + nx - 1];
-            out_e[1 * gs + y + 1] = f[5 * plane + row + nx - 1];
-            out_e[2 * gs + y + 1] = f[8 * plane + row + nx - 1];
-            out_e[3 * gs + y + 1] = f[0 * plane + row + nx - 1];
-            out_e[4 * gs + y + 1] = f[2 * plane + row + nx - 1];
-            out_e[5 * gs + y + 1] = f[4 * plane + row + nx - 1];
-            out_e[6 * gs + y + 1] = f[1 * plane + row + c2];
-            out_e[7 * gs + y + 1] = f[5 * plane + row + c2];
-            out_e[8 * gs + y + 1] = f[8 * plane + row + c2];
-            mask_e[y] = mask ? mask[(long long)y * mask_pitch + nx - 1] : 0;
+        for (int c = 0; c < GHOST_COLS; ++c) {
+            if (c >= nx) break;                       // a slab narrower than the ghost: those columns never get read
+            for (int j = 0; j < 9; ++j) {
+                if (out_w) out_w[(c * 9 + j) * gs + y + 1] = f[j * plane + row + c];
+                if (out_e) out_e[(c * 9 + j) * gs + y + 1] = f[j * plane + row + (nx - 1 - c)];
+            }
+            if (c < GHOST_COLS - 1) {
+                if (out_w) mask_w[c * ny + y] = mask ? mask[(long long)y * mask_pitch + c] : 0;
+                if (out_e) mask_e[c * ny + y] = mask ? mask[(long long)y * mask_pitch + (nx - 1 - c)] : 0;
+            }
         }
     }
     if (threadIdx.x == 0) *error_word = 0u;           // a re-primed handle starts from a clean slate
@@ -560,6 +546,8 @@ static int launch_step(lb_sim *sim, int src_idx, int write_moments, int y_begin 
 
 // ---- two lattice updates per launch (lb_march.cuh; with -DLB_EXPERIMENTS also lb_tb2.cuh, lb_tb2v.cuh) -------
 static inline int tb_kind(int shape) { return (shape > 0 && shape < g_ntb) ? g_tb_shapes[shape].kind : LB_TB_OFF; }
+// lattice updates per launch of a marching shape
+static inline int tb_depth(int shape) { return (tb_kind(shape) == LB_TB_MARCH && g_tb_shapes[shape].depth > 2) ? g_tb_shapes[shape].depth : 2; }
 
 static size_t tb2_smem_bytes(const lb_sim *sim, int shape)
 {
@@ -582,6 +570,11 @@ static const char *tb_refusal(const lb_sim *sim, int shape)
     if (g_variants[sim->variant].launch_tma) return "two-update kernels do not combine with a TMA-staged one-update variant";
     const int span = sim->elem == 4 ? 128 : 64;
     if (kind == LB_TB_MARCH) {
+        if (!g_tb_shapes[shape].launch_march[sim->cfg.dtype == LB_F64][sim->cfg.math == LB_MATH_FAST])
+            return "this shape is not compiled for the handle's dtype (three updates per launch: fp32 only)";
+        if (uses_halo(sim) && sim->cfg.nx < tb_depth(shape))
+            return "a halo-connected slab must be at least as many columns wide as the launch is updates deep";
+        if (sim->cfg.ny < tb_depth(shape)) return "the lattice must be at least as many rows high as the launch is updates deep";
         const bool rim = !strncmp(g_tb_shapes[shape].name, "rim", 3);       // -DLB_EXPERIMENTS: lb_march_rim.cuh
         const int need = rim ? span : (sim->elem == 4 ? 4 : 2);
         if (sim->cfg.west_edge == LB_EDGE_WRAP && sim->cfg.nx % need)
@@ -608,22 +601,26 @@ static int tb2_find(const char *name)
 // The shape used when the caller did not choose (tb2_shape == -1): the marching kernel on lattices large
 // enough to be HBM-bound; small lattices keep the graph-batched one-update kernel.  The decision uses only
 // what every slab of a decomposed lattice knows (global width, height), so all slabs decide alike.
-static int tb2_auto_shape(const lb_sim *sim)
+static int tb2_auto_shape(const lb_sim *sim, bool size_gate = true, bool allow3 = true)
 {
-    if ((long long)sim->cfg.global_nx * sim->cfg.ny < (1ll << 22) || sim->cfg.ny < 64) return 0;
+    if (size_gate && ((long long)sim->cfg.global_nx * sim->cfg.ny < (1ll << 22) || sim->cfg.ny < 64)) return 0;
     // (slabs of one lattice may run different SHAPES -- only the launch sequence has to agree -- so the choice
     // may depend on what this slab looks like)
-    // Segment height: a warp walks `seg` rows of one strip.  Short segments cost two extra phase-1 rows each, long
-    // ones leave too few (strip, segment) work items to fill and balance 148 SMs x 20-24 warps; measured best is
-    // around 50 000 items (profiles/r2_march_segment_height_*.txt), i.e. 8 rows on a 4096 x 1024 lattice, 16 on a
-    // 4096 x 32768 slab, 64 on C4.
+    // Segment height: a warp walks `seg` rows of one strip.  Short segments cost 2 (K-1) extra level-1 rows each, long
+    // ones leave too few (strip, segment) work items to fill and balance 148 SMs x 16-24 warps (profiles/
+    // r2_march_segment_height_*.txt, r2_march3_*.txt).  fp32 lattices with enough rows for segments of 16 or more
+    // run THREE updates per launch; smaller ones and fp64 two, with segments down to 8 rows (8 on a 4096 x 1024
+    // lattice, 16 on a 4096 x 32768 slab in fp64, 64 on C4).
     const int out = sim->elem == 4 ? 120 : 60;
-    const long long nstrips = (sim->cfg.nx + out - 1) / out;
-    const long long want = nstrips * sim->cfg.ny / 49152;
-    int seg = 8;
-    while (seg < 64 && 2 * seg <= want) seg *= 2;
-    const std::string name = std::string((sim->elem == 4 ? g_tb_auto_f32 : g_tb_auto_f64)[sim->mask != nullptr]) + ".s" + std::to_string(seg);
-    const int k = tb2_find(name.c_str());
+    const long long items_per_row = (sim->cfg.nx + out - 1) / out;
+    auto pow2_floor = [](long long want, int lo, int hi) { int s = lo; while (s < hi && 2 * s <= want) s *= 2; return s; };
+    std::string name;
+    const long long want3 = items_per_row * sim->cfg.ny / 24576;
+    if (allow3 && sim->elem == 4 && want3 >= 16) name = std::string(g_tb_auto_f32_3) + ".s" + std::to_string(pow2_floor(want3, 16, 64));
+    else name = std::string((sim->elem == 4 ? g_tb_auto_f32 : g_tb_auto_f64)[sim->mask != nullptr]) + ".s" +
+                std::to_string(pow2_floor(items_per_row * sim->cfg.ny / 49152, 8, 64));
+    int k = tb2_find(name.c_str());
+    if (k > 0 && tb_refusal(sim, k) && tb_depth(k) > 2) return tb2_auto_shape(sim, size_gate, false);   // e.g. a 2-column slab
     return (k > 0 && !tb_refusal(sim, k)) ? k : 0;
 }
 
@@ -633,8 +630,8 @@ static int tb2_effective_shape(const lb_sim *sim)
     return tb2_auto_shape(sim);
 }
 
-// two steps: reads buffer src_idx, writes the other one.  The marching kernel can store the moments of the
-// second step; the round-1 tiles cannot (write_moments must be 0 for them).
+// one launch of a two-update (three-update: tb_depth) shape: reads buffer src_idx, writes the other one.  The marching
+// kernel can store the moments of its last step; the round-1 tiles cannot (write_moments must be 0 for them).
 static int launch_two_steps(lb_sim *sim, int src_idx, int shape, int write_moments, int y_begin = 0, int y_end = -1)
 {
     const LbTbShape &t = g_tb_shapes[shape];
@@ -1135,6 +1132,28 @@ static int ensure_graph(lb_sim *sim)
 
 }  // extern "C"
 
+// the two-update shape that accompanies a three-update one (a run of 3a + 2 steps starts with one pair)
+static int pair_shape(const lb_sim *sim, int shape)
+{
+    if (tb_depth(shape) == 2) return shape;
+    const int k = tb2_auto_shape(sim, false, false);
+    return (k > 0 && tb_depth(k) == 2) ? k : 0;
+}
+
+// How n steps are cut into launches with marching shape `shape` (d = 2 or 3 updates per launch): the remainder
+// first -- one single-update launch, or one pair -- then n / d full launches.  Depths never decrease (lb_run_streamed
+// relies on it), and every slab of a lattice computes the same plan.
+static std::vector<int> plan_launches(const lb_sim *sim, int shape, int n_steps)
+{
+    std::vector<int> plan;
+    const int d = tb_depth(shape);
+    int lead = n_steps % d;
+    if (lead == 2 && !pair_shape(sim, shape)) { plan.push_back(1); lead = 1; }
+    if (lead) plan.push_back(lead);
+    for (int k = 0; k < n_steps / d; ++k) plan.push_back(d);
+    return plan;
+}
+
 // n_steps lattice updates.  `final`: the run ends here, so its last launch stores rho, u, v; lb_multi_step
 // enqueues long runs in chunks and passes false for all but the last one.
 static int step_impl(lb_sim *sim, int n_steps, bool final)
@@ -1154,18 +1173,18 @@ static int step_impl(lb_sim *sim, int n_steps, bool final)
     if (sim->cfg.scheme != LB_SCHEME_OPENCL) return cython_steps(sim, n_steps);
     const int tb = tb2_effective_shape(sim);
     if (tb_kind(tb) == LB_TB_MARCH) {
-        // every step of the run inside two-update launches: an odd run starts with one single step, and the
-        // launch that ends the run also stores rho, u, v (the moments of the run's last step)
+        // every step of the run inside multi-update launches (plan_launches); the launch that ends the run also
+        // stores rho, u, v (the moments of the run's last step)
+        const std::vector<int> plan = plan_launches(sim, tb, n_steps);
         int remaining = n_steps;
-        if (remaining & 1) {
-            int rc = launch_step(sim, sim->cur, final && remaining == 1);
+        for (size_t j = 0; j < plan.size(); ++j) {
+            const int d = plan[j];
+            const bool last = final && j + 1 == plan.size();
+            int rc;
+            if (d == 1) rc = launch_step(sim, sim->cur, last);
+            else rc = launch_two_steps(sim, sim->cur, d == tb_depth(tb) ? tb : pair_shape(sim, tb), last);
             if (rc) return rc;
-            sim->cur ^= 1; sim->state_index++; --remaining;
-        }
-        for (; remaining > 0; remaining -= 2) {
-            int rc = launch_two_steps(sim, sim->cur, tb, final && remaining == 2);
-            if (rc) return rc;
-            sim->cur ^= 1; sim->state_index += 2;
+            sim->cur ^= 1; sim->state_index += d; remaining -= d;
         }
         return LB_OK;
     }
@@ -1235,9 +1254,10 @@ int lb_run_streamed(lb_sim *sim, const void *host_f, int n_steps, void *host_rho
         CU(cudaStreamCreateWithFlags(&sim->s_up, cudaStreamNonBlocking));
         CU(cudaStreamCreateWithFlags(&sim->s_down, cudaStreamNonBlocking));
     }
-    // launch depths: an odd run starts with one single-update launch
-    std::vector<int> depth, reach;         // d_j and D_j = d_0 + ... + d_j
-    for (int left = n_steps; left > 0;) { const int d = (left & 1) ? 1 : 2; depth.push_back(d); left -= d; reach.push_back(n_steps - left); }
+    // launch depths d_j (non-decreasing: the remainder first) and D_j = d_0 + ... + d_j
+    const std::vector<int> depth = plan_launches(sim, tb, n_steps);
+    std::vector<int> reach;
+    for (int d : depth) reach.push_back((reach.empty() ? 0 : reach.back()) + d);
     const int L = (int)depth.size();
     int band = ((ny + 23) / 24 + 63) / 64 * 64;        // about 24 bands, whole segments
     const int nb = (ny + band - 1) / band;
@@ -1266,7 +1286,8 @@ int lb_run_streamed(lb_sim *sim, const void *host_f, int n_steps, void *host_rho
             if (j == L - 1) { lo_last = lo; hi_last = std::max(lo, hi); }
             if (hi <= lo) continue;
             const int src_idx = A ^ (j & 1);
-            const int rc = depth[j] == 1 ? launch_step(sim, src_idx, j == L - 1, lo, hi) : launch_two_steps(sim, src_idx, tb, j == L - 1, lo, hi);
+            const int rc = depth[j] == 1 ? launch_step(sim, src_idx, j == L - 1, lo, hi)
+                                         : launch_two_steps(sim, src_idx, depth[j] == tb_depth(tb) ? tb : pair_shape(sim, tb), j == L - 1, lo, hi);
             if (rc) return rc;
             done_to[j] = hi;
         }
@@ -1836,13 +1857,12 @@ int lb_multi_step(lb_multi *m, int n_steps)
     if (!m->primed) { int rc = multi_prime(m); if (rc) return rc; }
     if (m->concurrent) {
         // one slab per device: enqueue bounded chunks round-robin; the kernels of neighbouring devices
-        // synchronise among themselves through the peer-memory flags.  Chunks are even, so every slab issues
-        // the same sequence of single-update / two-update launches.
-        const int CHUNK = 32;
+        // synchronise among themselves through the peer-memory flags.  Every slab cuts a chunk into the same
+        // sequence of launches (plan_launches); 30 is a multiple of both launch depths, the remainder goes first.
+        const int CHUNK = 30;
         int done = 0;
         while (done < n_steps) {
-            int chunk = std::min(CHUNK, n_steps - done);
-            if (done == 0 && (n_steps & 1) && chunk > 1 && !(chunk & 1)) chunk -= 1;   // the odd step goes first
+            const int chunk = (done == 0 && n_steps % CHUNK) ? n_steps % CHUNK : std::min(CHUNK, n_steps - done);
             const bool last = done + chunk == n_steps;
             for (size_t k = 0; k < n; ++k) MS(k, step_impl(m->slabs[k], chunk, last));
             done += chunk;
@@ -1852,15 +1872,12 @@ int lb_multi_step(lb_multi *m, int n_steps)
     // slabs sharing a device share its stream: advance in lock-step, ONE LAUNCH per slab at a time -- a slab's
     // launch waits in-kernel for what its neighbour's previous launch published, and on one stream that
     // launch must already be enqueued ahead of it
-    const bool two = tb_kind(tb2_effective_shape(m->slabs[0])) == LB_TB_MARCH;
-    int remaining = n_steps;
-    if (!two || (remaining & 1)) {
-        const int singles = two ? 1 : remaining;
-        for (int i = 0; i < singles; ++i, --remaining)
-            for (size_t k = 0; k < n; ++k) MS(k, step_impl(m->slabs[k], 1, remaining == 1));
-    }
-    for (; remaining > 0; remaining -= 2)
-        for (size_t k = 0; k < n; ++k) MS(k, step_impl(m->slabs[k], 2, remaining == 2));
+    const int tb = tb2_effective_shape(m->slabs[0]);
+    std::vector<int> plan;
+    if (tb_kind(tb) == LB_TB_MARCH) plan = plan_launches(m->slabs[0], tb, n_steps);
+    else plan.assign(n_steps, 1);
+    for (size_t j = 0; j < plan.size(); ++j)
+        for (size_t k = 0; k < n; ++k) MS(k, step_impl(m->slabs[k], plan[j], j + 1 == plan.size()));
     return LB_OK;
 }
 

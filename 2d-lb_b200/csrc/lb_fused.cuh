@@ -40,17 +40,17 @@ struct StepParams {
     Consts<float> cf;         // per-launch constants, precomputed on the host in both types
     Consts<double> cd;
     Consts<F2> c2;            // cf with both lanes of every packed register set (lb_f32x2.cuh)
-    // x-slab halo (EDGE_HALO): ghost columns are [GHOST_SLOTS][ny+2] (slot, y+1), all values post-collision:
-    //   slots 0-2  the three populations entering my slab from the neighbour's boundary column
-    //              (1,5,8 of the west neighbour's last column / 3,6,7 of the east neighbour's first column)
-    //   slots 3-5  populations 0,2,4 of that same column                      } what a two-update launch needs on
-    //   slots 6-8  the same three entering populations, one column further in } top, to advance the neighbour's
-    //                                                                           boundary column by one level itself
+    // x-slab halo (EDGE_HALO): a ghost arena holds the neighbour's GHOST_COLS outermost columns, all nine
+    // post-collision populations of each, as [column c][population j][y + 1]: c = 0 is the neighbour's boundary
+    // column (its last column for the west ghost, its first for the east ghost), c = 1 the one behind it, ...  A
+    // one-update launch reads three values per row of column 0 (the populations entering this slab); a K-update
+    // launch of the marching kernel patches them into its overlap lane "as if memory continued beyond the slab" and
+    // advances the neighbour's outermost K-1 columns itself (K <= GHOST_COLS).
     const void *ghost_w;      // filled by the west neighbour (read)
     const void *ghost_e;      // filled by the east neighbour (read)
-    void *out_w;              // west neighbour's east ghost column (written from my columns 0, 1)
-    void *out_e;              // east neighbour's west ghost column (written from my columns nx-1, nx-2)
-    const uint8_t *gmask_w, *gmask_e;   // [ny] obstacle mask of the neighbours' boundary columns (nullptr: none)
+    void *out_w;              // west neighbour's east ghost arena (written from my columns 0, 1, 2)
+    void *out_e;              // east neighbour's west ghost arena (written from my columns nx-1, nx-2, nx-3)
+    const uint8_t *gmask_w, *gmask_e;   // [GHOST_COLS - 1][ny] obstacle mask of the neighbours' outermost columns (nullptr: none)
     unsigned int *flag_w_local, *flag_e_local;     // polled: neighbour's data for this step is in
     unsigned int *flag_w_remote, *flag_e_remote;   // published: my data for the next step is out
     unsigned int *done_w, *done_e;                 // edge-tile completion counters (local)
@@ -64,7 +64,7 @@ struct StepParams {
     int y_begin, y_end;       // rows this launch updates (whole lattice: 0, ny); band launches of lb_step_banded
     int seg_rows;             // marching kernel (lb_march.cuh): rows per segment (within y_begin .. y_end)
 };
-enum : int { GHOST_SLOTS = 9 };
+enum : int { GHOST_COLS = 3, GHOST_SLOTS = 9 * GHOST_COLS };
 
 template <typename T> __device__ __forceinline__ const Consts<T> &consts_in(const StepParams &p);
 template <> __device__ __forceinline__ const Consts<float> &consts_in<float>(const StepParams &p) { return p.cf; }
@@ -229,10 +229,10 @@ __device__ __forceinline__ void finish_row(const StepParams &p, const Consts<T> 
                 a5 = src[5 * plane + (long long)ym * pitch + (nx - 1)];
                 a8 = src[8 * plane + (long long)yp * pitch + (nx - 1)];
             } else {
-                const T *gw = static_cast<const T *>(p.ghost_w);
-                a1 = __ldcv(gw + 0 * (ny + 2) + (y + 1));
-                a5 = __ldcv(gw + 1 * (ny + 2) + (ym + 1));
-                a8 = __ldcv(gw + 2 * (ny + 2) + (yp + 1));
+                const T *gw = static_cast<const T *>(p.ghost_w);          // column 0 of the ghost: populations 1, 5, 8
+                a1 = __ldcv(gw + 1 * (ny + 2) + (y + 1));
+                a5 = __ldcv(gw + 5 * (ny + 2) + (ym + 1));
+                a8 = __ldcv(gw + 8 * (ny + 2) + (yp + 1));
             }
             q[1].v[0] = a1; q[5].v[0] = a5; q[8].v[0] = a8;
         }
@@ -243,10 +243,10 @@ __device__ __forceinline__ void finish_row(const StepParams &p, const Consts<T> 
                 a6 = src[6 * plane + (long long)ym * pitch];
                 a7 = src[7 * plane + (long long)yp * pitch];
             } else {
-                const T *ge = static_cast<const T *>(p.ghost_e);
-                a3 = __ldcv(ge + 0 * (ny + 2) + (y + 1));
-                a6 = __ldcv(ge + 1 * (ny + 2) + (ym + 1));
-                a7 = __ldcv(ge + 2 * (ny + 2) + (yp + 1));
+                const T *ge = static_cast<const T *>(p.ghost_e);          // column 0 of the ghost: populations 3, 6, 7
+                a3 = __ldcv(ge + 3 * (ny + 2) + (y + 1));
+                a6 = __ldcv(ge + 6 * (ny + 2) + (ym + 1));
+                a7 = __ldcv(ge + 7 * (ny + 2) + (yp + 1));
             }
 #pragma unroll
             for (int e = 0; e < V; ++e)
@@ -437,28 +437,28 @@ __device__ __forceinline__ void finish_row(const StepParams &p, const Consts<T> 
         }
     }
 
-    // --- publish my two outermost columns into the neighbours' ghost columns (layout: StepParams) ---
-    const int gs = ny + 2;                            // ghost slot stride
-    if (p.west == EDGE_HALO && x0 <= 1) {
+    // --- publish my GHOST_COLS outermost columns, all nine populations, into the neighbours' ghost arenas ---
+    const int gs = ny + 2;                            // rows per (column, population) of a ghost arena
+    if (p.west == EDGE_HALO && x0 < GHOST_COLS) {
         T *ow = static_cast<T *>(p.out_w) + (y + 1);
 #pragma unroll
         for (int e = 0; e < V; ++e) {
-            if (x0 + e == 0) {
-                ow[0 * gs] = q[3].v[e]; ow[1 * gs] = q[6].v[e]; ow[2 * gs] = q[7].v[e];
-                ow[3 * gs] = q[0].v[e]; ow[4 * gs] = q[2].v[e]; ow[5 * gs] = q[4].v[e];
+            const int col = x0 + e;                   // my column `col` is column `col` of the west neighbour's east ghost
+            if (col >= 0 && col < GHOST_COLS && col < nx) {
+#pragma unroll
+                for (int j = 0; j < 9; ++j) ow[(col * 9 + j) * gs] = q[j].v[e];
             }
-            if (x0 + e == 1) { ow[6 * gs] = q[3].v[e]; ow[7 * gs] = q[6].v[e]; ow[8 * gs] = q[7].v[e]; }
         }
     }
-    if (p.east == EDGE_HALO && x0 + V > nx - 2 && x0 < nx) {
+    if (p.east == EDGE_HALO && x0 + V > nx - GHOST_COLS && x0 < nx) {
         T *oe = static_cast<T *>(p.out_e) + (y + 1);
 #pragma unroll
         for (int e = 0; e < V; ++e) {
-            if (x0 + e == nx - 1) {
-                oe[0 * gs] = q[1].v[e]; oe[1 * gs] = q[5].v[e]; oe[2 * gs] = q[8].v[e];
-                oe[3 * gs] = q[0].v[e]; oe[4 * gs] = q[2].v[e]; oe[5 * gs] = q[4].v[e];
+            const int col = (nx - 1) - (x0 + e);      // my column nx-1-col is column `col` of the east neighbour's west ghost
+            if (col >= 0 && col < GHOST_COLS && x0 + e >= 0) {
+#pragma unroll
+                for (int j = 0; j < 9; ++j) oe[(col * 9 + j) * gs] = q[j].v[e];
             }
-            if (x0 + e == nx - 2) { oe[6 * gs] = q[1].v[e]; oe[7 * gs] = q[5].v[e]; oe[8 * gs] = q[8].v[e]; }
         }
     }
 }

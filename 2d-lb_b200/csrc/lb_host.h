@@ -33,8 +33,10 @@ struct LbTbShape {
     void (*launch_march[2][2])(const lb::StepParams &, cudaStream_t);
     void (*launch_rows[2][2])(const lb::StepParams &, dim3, size_t, cudaStream_t);
     void (*launch_cells[2][2])(const lb::Tb2Params &, dim3, size_t, cudaStream_t);
+    int depth;                 // LB_TB_MARCH: lattice updates per launch (0 = the default, two)
 };
 extern const LbTbShape g_tb_shapes[];
 extern const int g_ntb;
 extern const char *const g_tb_auto_f32[2];   // names of the shapes lb_step picks on its own: [no mask, mask]
 extern const char *const g_tb_auto_f64[2];
+extern const char *const g_tb_auto_f32_3;    // ... for three updates per launch

@@ -61,6 +61,24 @@ __device__ __forceinline__ void lap_shift_x(Pack<T, V> (&q)[9])
     q[3].v[V - 1] = s3; q[6].v[V - 1] = s6; q[7].v[V - 1] = s7;
 }
 
+// "Memory continues beyond the slab": the elements of this thread that are columns of the neighbour slab take the
+// neighbour's published level-t values, every population from the row it streams from.  `e0` is the element index of
+// the neighbour's boundary column (ghost column 0), `dir` = -1 towards lower elements (west edge) / +1 (east edge).
+template <typename T, int V, int NCOLS>
+__device__ __forceinline__ void lap_patch_ghost(Pack<T, V> (&q)[9], const T *__restrict__ G, int gs, int e0, int dir, int gy, int ym, int yp)
+{
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+        const int c = (e - e0) * dir;                  // ghost column held by element e
+        if (c >= 0 && c < NCOLS) {
+            const T *g = G + (long long)c * 9 * gs;
+            q[0].v[e] = __ldcv(g + 0 * gs + gy + 1); q[1].v[e] = __ldcv(g + 1 * gs + gy + 1); q[3].v[e] = __ldcv(g + 3 * gs + gy + 1);
+            q[2].v[e] = __ldcv(g + 2 * gs + ym + 1); q[5].v[e] = __ldcv(g + 5 * gs + ym + 1); q[6].v[e] = __ldcv(g + 6 * gs + ym + 1);
+            q[4].v[e] = __ldcv(g + 4 * gs + yp + 1); q[7].v[e] = __ldcv(g + 7 * gs + yp + 1); q[8].v[e] = __ldcv(g + 8 * gs + yp + 1);
+        }
+    }
+}
+
 // one bit per node of the thread: is (x0 + e, y) solid?  Columns beyond a halo edge take the neighbour's mask
 // column; the mask rows are zero-padded up to the pitch.
 template <int V>
@@ -80,13 +98,17 @@ __device__ __forceinline__ uint32_t lap_solid_bits(const StepParams &p, int x0, 
     }
     if (p.west == EDGE_HALO && x0 < 0 && p.gmask_w != nullptr) {
 #pragma unroll
-        for (int e = 0; e < V; ++e)
-            if (x0 + e == -1 && p.gmask_w[y] == 1) bits |= 1u << e;
+        for (int e = 0; e < V; ++e) {
+            const int c = -1 - (x0 + e);               // the neighbour's column c from its edge
+            if (c >= 0 && c < GHOST_COLS - 1 && p.gmask_w[c * p.ny + y] == 1) bits |= 1u << e;
+        }
     }
-    if (p.east == EDGE_HALO && x0 + V > p.nx && x0 <= p.nx && p.gmask_e != nullptr) {
+    if (p.east == EDGE_HALO && x0 + V > p.nx && x0 < p.nx + GHOST_COLS - 1 && p.gmask_e != nullptr) {
 #pragma unroll
-        for (int e = 0; e < V; ++e)
-            if (x0 + e == p.nx && p.gmask_e[y] == 1) bits |= 1u << e;
+        for (int e = 0; e < V; ++e) {
+            const int c = (x0 + e) - p.nx;
+            if (c >= 0 && c < GHOST_COLS - 1 && p.gmask_e[c * p.ny + y] == 1) bits |= 1u << e;
+        }
     }
     return bits;
 }
@@ -214,32 +236,8 @@ __global__ void __launch_bounds__(32 * NW, MINB) fused_march_kernel(const StepPa
             if (valid) {
                 if (!PF) lap_load_row<T, V>(q, src, plane, pitch, xl, gy, ym, yp);
                 if (MASKED != 0) solid_now = lap_solid_bits<V>(p, x0, xl, gy);
-                if (ghost_w) {                         // memory "continues" into the west neighbour: columns -2, -1
-                    const T *G = static_cast<const T *>(p.ghost_w);
-#pragma unroll
-                    for (int e = 0; e < V; ++e) {
-                        if (x0 + e == -1) {
-                            q[1].v[e] = __ldcv(G + 0 * gs + gy + 1); q[5].v[e] = __ldcv(G + 1 * gs + ym + 1); q[8].v[e] = __ldcv(G + 2 * gs + yp + 1);
-                            q[0].v[e] = __ldcv(G + 3 * gs + gy + 1); q[2].v[e] = __ldcv(G + 4 * gs + ym + 1); q[4].v[e] = __ldcv(G + 5 * gs + yp + 1);
-                        }
-                        if (x0 + e == -2) {
-                            q[1].v[e] = __ldcv(G + 6 * gs + gy + 1); q[5].v[e] = __ldcv(G + 7 * gs + ym + 1); q[8].v[e] = __ldcv(G + 8 * gs + yp + 1);
-                        }
-                    }
-                }
-                if (ghost_e) {                         // ... and into the east neighbour: columns nx, nx+1
-                    const T *G = static_cast<const T *>(p.ghost_e);
-#pragma unroll
-                    for (int e = 0; e < V; ++e) {
-                        if (x0 + e == nx) {
-                            q[3].v[e] = __ldcv(G + 0 * gs + gy + 1); q[6].v[e] = __ldcv(G + 1 * gs + ym + 1); q[7].v[e] = __ldcv(G + 2 * gs + yp + 1);
-                            q[0].v[e] = __ldcv(G + 3 * gs + gy + 1); q[2].v[e] = __ldcv(G + 4 * gs + ym + 1); q[4].v[e] = __ldcv(G + 5 * gs + yp + 1);
-                        }
-                        if (x0 + e == nx + 1) {
-                            q[3].v[e] = __ldcv(G + 6 * gs + gy + 1); q[6].v[e] = __ldcv(G + 7 * gs + ym + 1); q[7].v[e] = __ldcv(G + 8 * gs + yp + 1);
-                        }
-                    }
-                }
+                if (ghost_w) lap_patch_ghost<T, V, 2>(q, static_cast<const T *>(p.ghost_w), gs, -1 - x0, -1, gy, ym, yp);
+                if (ghost_e) lap_patch_ghost<T, V, 2>(q, static_cast<const T *>(p.ghost_e), gs, nx - x0, +1, gy, ym, yp);
                 lap_shift_x<T, V>(q);
                 finish_row<T, V, MATH, 0, MODEL_D2Q9, ROW_REGS_NOFIX, PACKED, true, ZOV, MASKED>(p, c, q, src, dst, x0, own0, gy, ym, yp, solid_now, false);
             } else {
@@ -289,6 +287,162 @@ __global__ void __launch_bounds__(32 * NW, MINB) fused_march_kernel(const StepPa
 
     // --- release the neighbours for their next launch (same hand-shake as fused_step_kernel) ---
     if (halo_w || halo_e) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence_system();
+            if (halo_w) {
+                const unsigned int old = atomicAdd(p.done_w, 1u);
+                if (old == (unsigned int)p.edge_tiles_y - 1u) {
+                    __threadfence_system();
+                    *p.done_w = 0u;
+                    st_release_sys(p.flag_w_remote, p.step_id + 1u);
+                }
+            }
+            if (halo_e) {
+                const unsigned int old = atomicAdd(p.done_e, 1u);
+                if (old == (unsigned int)p.edge_tiles_y - 1u) {
+                    __threadfence_system();
+                    *p.done_e = 0u;
+                    st_release_sys(p.flag_e_remote, p.step_id + 1u);
+                }
+            }
+        }
+    }
+}
+
+// ---- K updates per pass ------------------------------------------------------------------------------------------
+// The same march with K time levels in flight (K = 2 or 3; the V-wide overlap lanes carry enough columns for K <= V):
+// at iteration y level 1 works on row y, level 2 on row y-1, ..., level K on row y-K+1, which is stored.  Level l takes
+// populations 0,1,3 of its row and 2,5,6 of the row above from the kept rows of level l-1 (nine thread-private
+// shared-memory slots per level), and 4,7,8 from what level l-1 produced a moment ago in this very iteration.  DRAM
+// sees 9 loads + 9 stores per K updates; a segment of S rows costs S + 2(K-1) level-1 rows.  Slab edges: the
+// neighbour's K outermost columns are patched into the overlap lane (they are all published, lb_fused.cuh
+// StepParams), and levels 1 .. K-1 of them are advanced here exactly as the neighbour advances them.
+template <typename T, int V, int MATH, int NW, int MINB, bool PACKED, int K, int ZOV, int MASKED>
+__global__ void __launch_bounds__(32 * NW, MINB) fused_march_k_kernel(const StepParams p)
+{
+    static_assert(K >= 2 && K <= V && K <= GHOST_COLS, "overlap lanes and ghost arenas carry min(V, GHOST_COLS) columns");
+    constexpr int OUT = 30 * V;
+    using VT = typename VecOf<T, V>::type;
+    __shared__ VT win_s[NW * (K - 1) * 9 * 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    const int nstrips = p.tiles_x, nseg = p.tiles_y, ne = p.edge_first;     // work items: see fused_march_kernel
+    const int n_edge_ctas = (ne * nseg + NW - 1) / NW;
+    const bool edge_cta = (int)blockIdx.x < n_edge_ctas;
+    int strip, seg;
+    bool active;
+    if (edge_cta) {
+        const int item = blockIdx.x * NW + warp;
+        active = item < ne * nseg;
+        seg = item / ne;
+        const int k = item - seg * ne;
+        strip = (ne == 2) ? (k ? nstrips - 1 : 0) : (p.west == EDGE_HALO ? 0 : nstrips - 1);
+    } else {
+        const int nint = nstrips - ne;
+        const int item = (blockIdx.x - n_edge_ctas) * NW + warp;
+        active = item < nint * nseg;
+        seg = nint > 0 ? item / nint : 0;
+        strip = item - seg * nint + ((ne > 0 && p.west == EDGE_HALO) ? 1 : 0);
+    }
+    const bool halo_w = edge_cta && (p.west == EDGE_HALO);
+    const bool halo_e = edge_cta && (p.east == EDGE_HALO);
+    if (halo_w && !wait_flag(p.flag_w_local, p.step_id, p.error_word, p.halo_timeout_ns)) return;
+    if (halo_e && !wait_flag(p.flag_e_local, p.step_id, p.error_word, p.halo_timeout_ns)) return;
+
+    const int own0 = strip * OUT;
+    const int x0 = own0 - V + lane * V;
+    const T *__restrict__ src = static_cast<const T *>(p.src);
+    T *__restrict__ dst = static_cast<T *>(p.dst);
+    const long long plane = p.plane;
+    const int nx = p.nx, ny = p.ny, pitch = p.pitch;
+    const Consts<T> &c = consts_in<T>(p);
+    const bool periodic = (p.bc == BC_PERIODIC);
+    const int ys = p.y_begin + seg * p.seg_rows;
+    const int ye = min(ys + p.seg_rows, p.y_end);
+    const int gs = ny + 2;
+
+    if (active) {
+        int xl = x0;
+        if (p.west == EDGE_WRAP) { if (xl < 0) xl += nx; else if (xl >= nx) xl -= nx; }
+        const bool store_ok = lane != 0 && lane != 31;
+        const bool ghost_w = (p.west == EDGE_HALO) && x0 < 0;
+        const bool ghost_e = (p.east == EDGE_HALO) && x0 + V > nx && x0 < nx + K;
+        // slots of level l (1 .. K-1): 0-2 = populations 0,1,3 of its latest row, 3-5 / 6-8 = populations 2,5,6 of its
+        // rows of even / odd index
+        VT *win = win_s + warp * (K - 1) * 9 * 32 + lane;
+        {
+            Pack<T, V> zero;
+#pragma unroll
+            for (int e = 0; e < V; ++e) zero.v[e] = (T)0;
+#pragma unroll
+            for (int k = 0; k < (K - 1) * 9; ++k) win[k * 32] = repack(zero);
+        }
+        // rows wrap on a periodic box (by up to K-1 rows beyond either end); outside a pipe there is nothing
+        auto row_of = [&](int y, int &gy, int &ym, int &yp) -> bool {
+            gy = y;
+            if (periodic) { if (gy < 0) gy += ny; if (gy >= ny) gy -= ny; }
+            else if (gy < 0 || gy >= ny) return false;
+            ym = gy - 1; yp = gy + 1;
+            if (periodic) { if (ym < 0) ym = ny - 1; if (yp >= ny) yp = 0; }
+            return true;
+        };
+        uint32_t solid[K];                             // solid[l-1]: obstacle bits of the row level l works on
+#pragma unroll
+        for (int l = 0; l < K; ++l) solid[l] = 0u;
+        for (int y = ys - (K - 1); y <= ye + K - 2; ++y) {
+            // ---- level 1: row y, from global memory -------------------------------------------------------
+            Pack<T, V> cur[9];
+            {
+                int gy, ym = 0, yp = 0;
+                if (row_of(y, gy, ym, yp)) {
+                    lap_load_row<T, V>(cur, src, plane, pitch, xl, gy, ym, yp);
+                    if (MASKED != 0) solid[0] = lap_solid_bits<V>(p, x0, xl, gy);
+                    if (ghost_w) lap_patch_ghost<T, V, K>(cur, static_cast<const T *>(p.ghost_w), gs, -1 - x0, -1, gy, ym, yp);
+                    if (ghost_e) lap_patch_ghost<T, V, K>(cur, static_cast<const T *>(p.ghost_e), gs, nx - x0, +1, gy, ym, yp);
+                    lap_shift_x<T, V>(cur);
+                    finish_row<T, V, MATH, 0, MODEL_D2Q9, ROW_REGS_NOFIX, PACKED, true, ZOV, MASKED>(p, c, cur, src, dst, x0, own0, gy, ym, yp, solid[0], false);
+                } else {
+                    solid[0] = 0u;
+#pragma unroll
+                    for (int j = 0; j < 9; ++j)
+#pragma unroll
+                        for (int e = 0; e < V; ++e) cur[j].v[e] = (T)0;
+                }
+            }
+            // ---- levels 2 .. K: row y-l+1, from the kept rows of level l-1 and what it produced just now ----
+#pragma unroll
+            for (int l = 2; l <= K; ++l) {
+                const int r = y - (l - 1);
+                const bool act = y >= ys - K + 2 * l - 1;          // warp-uniform: does level l have to produce row r?
+                VT *w = win + (l - 2) * 9 * 32;
+                const int o = 3 + 3 * ((r + 1) & 1);               // the slot of row r-1, which row r+1 replaces below
+                Pack<T, V> z[9];
+                unpack(w[0 * 32], z[0]); unpack(w[1 * 32], z[1]); unpack(w[2 * 32], z[3]);
+                unpack(w[(o + 0) * 32], z[2]); unpack(w[(o + 1) * 32], z[5]); unpack(w[(o + 2) * 32], z[6]);
+                z[4] = cur[4]; z[7] = cur[7]; z[8] = cur[8];
+                w[0 * 32] = repack(cur[0]); w[1 * 32] = repack(cur[1]); w[2 * 32] = repack(cur[3]);
+                w[(o + 0) * 32] = repack(cur[2]); w[(o + 1) * 32] = repack(cur[5]); w[(o + 2) * 32] = repack(cur[6]);
+                int gr = 0, rm = 0, rp = 0;
+                const bool live = act && row_of(r, gr, rm, rp);
+                if (l < K) {
+                    if (live) {
+                        lap_shift_x<T, V>(z);
+                        finish_row<T, V, MATH, 0, MODEL_D2Q9, ROW_REGS_NOFIX, PACKED, true, ZOV, MASKED>(p, c, z, src, dst, x0, own0, gr, rm, rp, solid[l - 1], false);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 9; ++j) cur[j] = z[j];     // (not live: values nobody will use)
+                } else if (live) {
+                    lap_shift_x<T, V>(z);
+                    finish_row<T, V, MATH, 0, MODEL_D2Q9, ROW_FROM_TILE, PACKED, true, ZOV, MASKED>(p, c, z, src, dst, x0, own0, gr, rm, rp, solid[K - 1], store_ok);
+                }
+            }
+#pragma unroll
+            for (int l = K - 1; l > 0; --l) solid[l] = solid[l - 1];
+        }
+    }
+
+    if (halo_w || halo_e) {                            // release the neighbours for their next launch
         __syncthreads();
         if (threadIdx.x == 0) {
             __threadfence_system();

@@ -112,24 +112,24 @@ __device__ __forceinline__ void march_rim_node(const StepParams &p, const Consts
     if (beyond_w && p.west == EDGE_HALO) {
         // the west neighbour's last column: its own populations from the ghost slots, 3,6,7 from my column 0
         const T *G = static_cast<const T *>(p.ghost_w);
-        g[0] = __ldcv(G + 3 * gs + gy + 1);
-        g[2] = __ldcv(G + 4 * gs + ym + 1);
-        g[4] = __ldcv(G + 5 * gs + yp + 1);
-        g[1] = __ldcv(G + 6 * gs + gy + 1);
-        g[5] = __ldcv(G + 7 * gs + ym + 1);
-        g[8] = __ldcv(G + 8 * gs + yp + 1);
+        g[0] = __ldcv(G + 0 * gs + gy + 1);
+        g[2] = __ldcv(G + 2 * gs + ym + 1);
+        g[4] = __ldcv(G + 4 * gs + yp + 1);
+        g[1] = __ldcv(G + (9 + 1) * gs + gy + 1);
+        g[5] = __ldcv(G + (9 + 5) * gs + ym + 1);
+        g[8] = __ldcv(G + (9 + 8) * gs + yp + 1);
         g[3] = __ldg(src + 3 * plane + rc);
         g[6] = __ldg(src + 6 * plane + rm);
         g[7] = __ldg(src + 7 * plane + rp);
         if (p.gmask_w != nullptr) solid = p.gmask_w[gy] == 1;
     } else if (beyond_e && p.east == EDGE_HALO) {
         const T *G = static_cast<const T *>(p.ghost_e);
-        g[0] = __ldcv(G + 3 * gs + gy + 1);
-        g[2] = __ldcv(G + 4 * gs + ym + 1);
-        g[4] = __ldcv(G + 5 * gs + yp + 1);
-        g[3] = __ldcv(G + 6 * gs + gy + 1);
-        g[6] = __ldcv(G + 7 * gs + ym + 1);
-        g[7] = __ldcv(G + 8 * gs + yp + 1);
+        g[0] = __ldcv(G + 0 * gs + gy + 1);
+        g[2] = __ldcv(G + 2 * gs + ym + 1);
+        g[4] = __ldcv(G + 4 * gs + yp + 1);
+        g[3] = __ldcv(G + (9 + 3) * gs + gy + 1);
+        g[6] = __ldcv(G + (9 + 6) * gs + ym + 1);
+        g[7] = __ldcv(G + (9 + 7) * gs + yp + 1);
         g[1] = __ldg(src + 1 * plane + rc + (nx - 1));
         g[5] = __ldg(src + 5 * plane + rm + (nx - 1));
         g[8] = __ldg(src + 8 * plane + rp + (nx - 1));
@@ -156,11 +156,11 @@ __device__ __forceinline__ void march_rim_node(const StepParams &p, const Consts
         // are in ghost slots 0-2 (only when the strip next to the edge is one column wide; kept for safety)
         if (x == 0 && p.west == EDGE_HALO) {
             const T *G = static_cast<const T *>(p.ghost_w);
-            g[1] = __ldcv(G + 0 * gs + gy + 1); g[5] = __ldcv(G + 1 * gs + ym + 1); g[8] = __ldcv(G + 2 * gs + yp + 1);
+            g[1] = __ldcv(G + 1 * gs + gy + 1); g[5] = __ldcv(G + 5 * gs + ym + 1); g[8] = __ldcv(G + 8 * gs + yp + 1);
         }
         if (x == nx - 1 && p.east == EDGE_HALO) {
             const T *G = static_cast<const T *>(p.ghost_e);
-            g[3] = __ldcv(G + 0 * gs + gy + 1); g[6] = __ldcv(G + 1 * gs + ym + 1); g[7] = __ldcv(G + 2 * gs + yp + 1);
+            g[3] = __ldcv(G + 3 * gs + gy + 1); g[6] = __ldcv(G + 6 * gs + ym + 1); g[7] = __ldcv(G + 7 * gs + yp + 1);
         }
         if (p.mask != nullptr) solid = p.mask[(long long)gy * p.mask_pitch + x] == 1;
         gx = x;

@@ -501,16 +501,17 @@ def main():
     if rank == 0:
         tb2 = lat.temporal_blocking
         two = tb2 != "off"
-        updates_per_launch = 2 if two else 1
+        updates_per_launch = 1 if not two else (3 if tb2.startswith("march3") else 2)
         kernel = ("fused_step_kernel (one lattice update per launch)" if not two else
-                  f"fused_march_kernel shape {tb2} (two lattice updates per launch, the intermediate time level in "
-                  "registers; an odd run starts with one fused_step_kernel launch)")
+                  f"fused_march{'_k' if updates_per_launch == 3 else ''}_kernel shape {tb2} ({'three' if updates_per_launch == 3 else 'two'} "
+                  "lattice updates per launch, the intermediate time levels on chip; a run whose length is not a multiple of that "
+                  "starts with one shorter launch)")
         # measured DRAM traffic of ONE launch of the dominant kernel (ncu --set full, dram__bytes_read.sum +
         # dram__bytes_write.sum), recorded per lattice node in profiles/traffic.json with the capture's own grid
         traffic, traffic_note = None, None
         try:
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
-                t = json.load(fh).get(wl["dtype"] + ("_march" if two else ""))
+                t = json.load(fh).get(wl["dtype"] + ("" if not two else ("_march3" if updates_per_launch == 3 else "_march")))
             if t:
                 traffic = t["dram_bytes_per_node_per_launch"] * cells_local
                 same = list(t.get("grid", [])) == [slab.nx, gny]
@@ -540,10 +541,10 @@ def main():
                          "bytes_per_lattice_update": bytes_per_lu, "updates_per_launch": updates_per_launch,
                          "launch_ms": launch_dur_ms, "algorithmic_bytes_per_launch": cells_local * bytes_per_lu * updates_per_launch,
                          "per": "GPU, " + kernel.split(" ")[0],
-                         "note": None if not two else "achieved = ALGORITHMIC bytes (9 loads + 9 stores per update, two updates "
-                                 "per launch) / launch duration; the kernel keeps the intermediate level on chip and moves about "
-                                 "half of that through HBM (traffic), so frac can exceed 1 -- frac_on_measured_traffic is the "
-                                 "share of the measured HBM peak the kernel's real DRAM traffic amounts to",
+                         "note": None if not two else "achieved = ALGORITHMIC bytes (9 loads + 9 stores per update x updates per "
+                                 "launch) / launch duration; the kernel keeps the intermediate levels on chip and moves a half "
+                                 "or a third of that through HBM (traffic), so frac can exceed 1 -- frac_on_measured_traffic is "
+                                 "the share of the measured HBM peak the kernel's real DRAM traffic amounts to",
                          "pattern_copy_ceiling": ceiling,
                          "frac_of_pattern_copy_ceiling": (achieved / ceiling["GB/s"]) if ceiling and ceiling.get("GB/s") else None},
             "cpu_baseline": cpu,

@@ -31,14 +31,12 @@ def run(bc, nx, ny, math, shape, mask, steps, dtype=np.float32, zv=False):
             print(tag, f"{len(d)} differ; first:", d[:12].tolist(), " xs:", sorted(set(d[:, -1].tolist()))[:20], " ys:", sorted(set(d[:, -2].tolist()))[:20],
                   " max|d|:", float(np.abs(got[k].astype(np.float64) - want[k]).max()))
 
-for shape in ("march.w4b5.sh.s32", "march.w4b4.s32"):
-    run("pipe", 5, 4, "strict", shape, "none", 2)
-    run("pipe", 2, 2, "strict", shape, "none", 2)
-    run("pipe", 300, 70, "strict", shape, "none", 2)
-    run("pipe", 300, 70, "fast", shape, "none", 2)
-    run("pipe", 300, 70, "fast", shape, "touching", 2)
-    run("pipe", 300, 70, "fast", shape, "touching", 6)
-    run("periodic", 128, 5, "strict", shape, None, 2)
-    run("periodic", 256, 37, "strict", shape, None, 2)
-    run("periodic", 384, 70, "strict", shape, None, 4)
-    run("periodic", 384, 70, "fast", shape, None, 4)
+for shape in ("march3.w4b5.s32", "march3.w4b4.s8"):
+    run("pipe", 5, 4, "strict", shape, "none", 3)
+    run("pipe", 300, 70, "strict", shape, "none", 3)
+    run("pipe", 300, 70, "strict", shape, "touching", 3)
+    run("pipe", 300, 70, "fast", shape, "touching", 9)
+    run("pipe", 700, 41, "strict", shape, "bulky", 6, zv=True)
+    run("periodic", 128, 5, "strict", shape, None, 3)
+    run("periodic", 256, 37, "strict", shape, None, 6)
+    run("periodic", 384, 70, "fast", shape, None, 8)
