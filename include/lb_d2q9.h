@@ -216,20 +216,24 @@ int lb_init_synthetic(lb_sim *sim, int kind, double u0, double amplitude, uint64
 /* solid disk in GLOBAL coordinates (centre cx,cy, radius r): mask = (gx-cx)^2+(y-cy)^2 < r^2 */
 int lb_set_mask_disk(lb_sim *sim, double cx, double cy, double r);
 
-/* -- two lattice updates per pass through HBM (csrc/lb_march.cuh).  lb_step runs a run's steps two at a
- *    time in one launch -- the intermediate time level lives in registers, so only 36 B (fp32) / 72 B (fp64)
- *    per lattice update cross the HBM interface -- preceded by one single-update launch when n_steps is
- *    odd; the launch that ends the run also stores rho, u, v.  Results are bit-identical to the one-update
- *    kernel in both math modes, on single slabs and on halo-connected slabs (which then exchange two columns
- *    every second step instead of one column every step).
+/* -- several lattice updates per pass through HBM (csrc/lb_march.cuh).  lb_step runs a run's steps two or three
+ *    at a time in one launch -- the intermediate time levels live on chip, so only 38 B (two updates per launch)
+ *    or 26 B (three) per lattice update cross the HBM interface in fp32 instead of 72 -- preceded by one shorter
+ *    launch when n_steps is not a multiple of the launch depth; the launch that ends the run also stores
+ *    rho, u, v.  Results are bit-identical to the one-update kernel in both math modes, on single slabs and on
+ *    halo-connected slabs (which then exchange their three outermost columns once per launch instead of one
+ *    column every step).
  *    shape -1 = automatic (default): when the WHOLE lattice (global_nx x ny) has at least 2^22 nodes and
- *    ny >= 64, the measured-best shape for this slab -- branch-free obstacle code where there is a mask, a
- *    segment height of 8 to 64 rows that gives about 50 000 (strip, segment) work items -- and the
+ *    ny >= 64, the measured-best shape for this slab -- three updates per launch in fp32 where the slab is
+ *    large enough for segments of 16+ rows, two otherwise and in fp64; branch-free obstacle code where there is
+ *    a mask; a segment height of 8 to 64 rows that gives 25 000 - 50 000 (strip, segment) work items -- and the
  *    graph-batched one-update kernel below that size; 0 = off; 1 .. lb_tb2_shape_count()-1 = a compiled shape
- *    by index (lb_tb2_shape_name: "march.w<warps per CTA>b<CTAs per SM>[.sh[.bf] | .scalar].s<rows per segment>").  Serves LB_SCHEME_OPENCL /
+ *    by index (lb_tb2_shape_name: "march.w<warps per CTA>b<CTAs per SM>[.sh[.bf] | .scalar].s<rows per segment>"
+ *    = two updates per launch, "march3.w..b...s.." = three).  Serves LB_SCHEME_OPENCL /
  *    LB_MODEL_D2Q9 lattices; a single-slab periodic box needs nx to be a multiple of the vector width (4 fp32 /
- *    2 fp64 cells).  All slabs of one lattice must use the same setting.  lb_temporal_blocking returns the
- *    shape lb_step will use (0 = one-update kernel). */
+ *    2 fp64 cells); three updates per launch: fp32, slabs at least 3 columns wide.  All slabs of one lattice must
+ *    use shapes of the same depth (the automatic choice does).  lb_temporal_blocking returns the shape lb_step will
+ *    use (0 = one-update kernel). */
 int lb_set_temporal_blocking(lb_sim *sim, int shape);
 int lb_temporal_blocking(const lb_sim *sim);
 int lb_tb2_shape_count(void);
@@ -268,11 +272,11 @@ int lb_device_ptr(lb_sim *sim, int field, void **ptr, int64_t *pitch_elems);
 void *lb_stream(lb_sim *sim);
 
 /* -- x-slab halo exchange over NVLink peer memory (new design; the reference is single-device).
- *    Each slab owns a halo arena: two ghost columns x two parities x nine values per row
- *    (the 3 populations entering the slab from the neighbour's boundary column, that
- *    column's populations 0,2,4, and the 3 entering populations one column further in --
- *    what a two-update launch needs to advance the neighbour's boundary column itself),
- *    the neighbours' mask columns, and launch flags.  A slab's boundary threads store those
+ *    Each slab owns a halo arena: two ghost arenas x two parities x all nine populations
+ *    of the neighbour's three outermost columns (a one-update launch reads three values
+ *    per row of them; a K-update launch patches K columns into its overlap lane and
+ *    advances the neighbour's outermost K-1 columns itself), the neighbours' mask
+ *    columns, and launch flags.  A slab's boundary threads store those
  *    values straight into the NEIGHBOUR's arena inside the fused kernel and then publish a
  *    flag there; the neighbour's boundary tiles poll their local flag before reading. */
 #define LB_IPC_HANDLE_BYTES 64
