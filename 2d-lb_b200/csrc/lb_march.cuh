@@ -1,5 +1,6 @@
-// The marching kernel, overlapped strips: TWO lattice updates per pass through HBM, one warp per column strip,
-// the intermediate time level in registers, no shared memory, no barrier, no scalar gathers.
+// The marching kernel, overlapped strips: TWO (fused_march_kernel) or K = 3 (fused_march_k_kernel, at the end of this
+// file) lattice updates per pass through HBM, one warp per column strip, the intermediate time levels in registers or
+// in thread-private shared-memory slots, no barrier, no scalar gathers.  The description below is the two-update form.
 //
 // A warp LOADS SPAN = 32*V consecutive columns (128 fp32 / 64 fp64 cells) of every row it walks over and
 // STORES the middle OUT = 30*V of them (120 / 60): strip k loads columns [k*OUT - V, k*OUT + 31*V) and owns
