@@ -144,6 +144,24 @@ def test_mask_ingestion(tmp_path):
     assert r.shape == (160, 80) and r.sum() == 800 and r[60:100, 20:40].all()
     assert np.array_equal(masks.resample(m, 80, 40), m)
     assert np.array_equal(masks.unpack(masks.pack(m)), m)
+    # anti-aliased route (grey resize, then threshold): identity at the same size, area-exact when shrinking by an
+    # integer factor, mean-preserving, and equal to nearest neighbour on a mask whose edges fall on the coarse grid
+    grey = m.astype(np.float64)
+    assert np.array_equal(masks.resize(grey, 80, 40), grey)
+    half = masks.resize(grey, 40, 20)
+    assert half.shape == (40, 20) and np.allclose(half, grey.reshape(40, 2, 20, 2).mean(axis=(1, 3)))
+    third = masks.resize(grey, 27, 13)
+    assert abs(third.mean() - grey.mean()) < 1e-12 and third.min() >= 0 and third.max() <= 1 + 1e-12
+    up = masks.resize(grey, 160, 80)
+    assert up.shape == (160, 80) and abs(up.mean() - grey.mean()) < 2e-3 and up[70:90, 25:35].min() == 1.0
+    aa = masks.from_image(str(path), 40, 20, antialias=True)
+    assert np.array_equal(aa, masks.from_image(str(path), 40, 20))
+    img2 = np.zeros((40, 80), np.uint8)
+    img2[11:20, 31:50] = 255                          # odd edges: the coarse cells on the rim are half covered
+    Image.fromarray(img2).save(tmp_path / "m2.png")
+    a2 = masks.from_image(str(tmp_path / "m2.png"), 40, 20, antialias=True, threshold=0.4)
+    # 36 fully covered coarse cells + 4 + 9 half covered ones on the two rims (>= 40 %: solid); the corner (25 %) is not
+    assert a2.sum() == 49 and a2[16:25, 6:10].all() and a2[15, 6:10].all() and a2[16:25, 5].all() and not a2[15, 5]
     g = np.load(os.path.join(ROOT, "tests", "golden", "cs205_binary_mask.npz"))
     src = masks.unpack(g)
     assert src.shape == (800, 400) and abs(src.mean() - 0.087) < 0.001      # 8.7 % solid
