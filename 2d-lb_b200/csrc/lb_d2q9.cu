@@ -615,7 +615,7 @@ static int tb2_auto_shape(const lb_sim *sim, bool size_gate = true, bool allow3 
     const long long items_per_row = (sim->cfg.nx + out - 1) / out;
     auto pow2_floor = [](long long want, int lo, int hi) { int s = lo; while (s < hi && 2 * s <= want) s *= 2; return s; };
     std::string name;
-    const long long want3 = items_per_row * sim->cfg.ny / 24576;
+    const long long want3 = items_per_row * sim->cfg.ny / 12288;     // three updates per launch like long segments
     if (allow3 && sim->elem == 4 && want3 >= 16) name = std::string(g_tb_auto_f32_3) + ".s" + std::to_string(pow2_floor(want3, 16, 64));
     else name = std::string((sim->elem == 4 ? g_tb_auto_f32 : g_tb_auto_f64)[sim->mask != nullptr]) + ".s" +
                 std::to_string(pow2_floor(items_per_row * sim->cfg.ny / 49152, 8, 64));
