@@ -571,7 +571,7 @@ static const char *tb_refusal(const lb_sim *sim, int shape)
     const int span = sim->elem == 4 ? 128 : 64;
     if (kind == LB_TB_MARCH) {
         if (!g_tb_shapes[shape].launch_march[sim->cfg.dtype == LB_F64][sim->cfg.math == LB_MATH_FAST])
-            return "this shape is not compiled for the handle's dtype (three updates per launch: fp32 only)";
+            return "this shape is not compiled for the handle's dtype";
         if (uses_halo(sim) && sim->cfg.nx < tb_depth(shape))
             return "a halo-connected slab must be at least as many columns wide as the launch is updates deep";
         if (sim->cfg.ny < tb_depth(shape)) return "the lattice must be at least as many rows high as the launch is updates deep";
@@ -580,6 +580,8 @@ static const char *tb_refusal(const lb_sim *sim, int shape)
         if (sim->cfg.west_edge == LB_EDGE_WRAP && sim->cfg.nx % need)
             return rim ? "the rim-gather marching kernel needs nx to be a multiple of the strip width (128 fp32 / 64 fp64 cells) on a single-slab periodic box"
                        : "the marching kernel needs nx to be a multiple of the vector width (4 fp32 / 2 fp64 cells) on a single-slab periodic box";
+        if (sim->cfg.west_edge == LB_EDGE_WRAP && sim->elem == 8 && tb_depth(shape) > 2 && sim->cfg.nx < 4)
+            return "three fp64 updates per launch need a periodic box at least 4 cells wide";
         return nullptr;
     }
     // the round-1 shared-memory tiles: single slab only
@@ -601,6 +603,9 @@ static int tb2_find(const char *name)
 // The shape used when the caller did not choose (tb2_shape == -1): the marching kernel on lattices large
 // enough to be HBM-bound; small lattices keep the graph-batched one-update kernel.  The decision uses only
 // what every slab of a decomposed lattice knows (global width, height), so all slabs decide alike.
+#ifndef LB_MARCH3_MAX_SEG
+#define LB_MARCH3_MAX_SEG 64
+#endif
 static int tb2_auto_shape(const lb_sim *sim, bool size_gate = true, bool allow3 = true)
 {
     if (size_gate && ((long long)sim->cfg.global_nx * sim->cfg.ny < (1ll << 22) || sim->cfg.ny < 64)) return 0;
@@ -608,17 +613,17 @@ static int tb2_auto_shape(const lb_sim *sim, bool size_gate = true, bool allow3 
     // may depend on what this slab looks like)
     // Segment height: a warp walks `seg` rows of one strip.  Short segments cost 2 (K-1) extra level-1 rows each, long
     // ones leave too few (strip, segment) work items to fill and balance 148 SMs x 16-24 warps (profiles/
-    // r2_march_segment_height_*.txt, r2_march3_*.txt).  fp32 lattices with enough rows for segments of 16 or more
-    // run THREE updates per launch; smaller ones and fp64 two, with segments down to 8 rows (8 on a 4096 x 1024
-    // lattice, 16 on a 4096 x 32768 slab in fp64, 64 on C4).
-    const int out = sim->elem == 4 ? 120 : 60;
-    const long long items_per_row = (sim->cfg.nx + out - 1) / out;
+    // r2_march_segment_height_*.txt, r2_march3_*.txt).  Lattices with enough rows for segments of 16 or more run
+    // THREE updates per launch (fp64 with two overlap lanes per side: 56 stored columns per strip); smaller ones two,
+    // with segments down to 8 rows (8 on a 4096 x 1024 lattice, 64 and more on C4 and C5).
+    const bool f32 = sim->elem == 4;
+    auto items_per_row = [&](int out) { return (long long)((sim->cfg.nx + out - 1) / out); };
     auto pow2_floor = [](long long want, int lo, int hi) { int s = lo; while (s < hi && 2 * s <= want) s *= 2; return s; };
     std::string name;
-    const long long want3 = items_per_row * sim->cfg.ny / 12288;     // three updates per launch like long segments
-    if (allow3 && sim->elem == 4 && want3 >= 16) name = std::string(g_tb_auto_f32_3) + ".s" + std::to_string(pow2_floor(want3, 16, 64));
-    else name = std::string((sim->elem == 4 ? g_tb_auto_f32 : g_tb_auto_f64)[sim->mask != nullptr]) + ".s" +
-                std::to_string(pow2_floor(items_per_row * sim->cfg.ny / 49152, 8, 64));
+    const long long want3 = items_per_row(f32 ? 120 : 56) * sim->cfg.ny / 12288;     // three updates per launch like long segments
+    if (allow3 && want3 >= 16) name = std::string(f32 ? g_tb_auto_f32_3 : g_tb_auto_f64_3) + ".s" + std::to_string(pow2_floor(want3, 16, LB_MARCH3_MAX_SEG));
+    else name = std::string((f32 ? g_tb_auto_f32 : g_tb_auto_f64)[sim->mask != nullptr]) + ".s" +
+                std::to_string(pow2_floor(items_per_row(f32 ? 120 : 60) * sim->cfg.ny / 49152, 8, 64));
     int k = tb2_find(name.c_str());
     if (k > 0 && tb_refusal(sim, k) && tb_depth(k) > 2) return tb2_auto_shape(sim, size_gate, false);   // e.g. a 2-column slab
     return (k > 0 && !tb_refusal(sim, k)) ? k : 0;

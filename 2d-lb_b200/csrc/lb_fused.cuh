@@ -61,6 +61,9 @@ struct StepParams {
     int edge_first;           // 1-D grid with the two edge tile columns first (halo overlap); else 2-D/3-D grid
     int edge_rows;            // rows per warp in an edge tile (tall tiles: few participants in the hand-shake)
     int edge_tiles_y;         // edge tiles per side
+    int east_pair;            // one-update kernel: the tile column before the last one holds some of the GHOST_COLS
+                              // easternmost columns and takes part in the east hand-shake (done_e_count CTAs in all)
+    int done_e_count;
     int y_begin, y_end;       // rows this launch updates (whole lattice: 0, ny); band launches of lb_step_banded
     int seg_rows;             // marching kernel (lb_march.cuh): rows per segment (within y_begin .. y_end)
 };
@@ -495,7 +498,7 @@ __global__ void __launch_bounds__(32 * WX * WY, MINB) fused_step_kernel(const St
         by = blockIdx.z * gridDim.y + blockIdx.y;
     }
     const bool halo_w = (p.west == EDGE_HALO) && (bx == 0);
-    const bool halo_e = (p.east == EDGE_HALO) && (bx == p.tiles_x - 1);
+    const bool halo_e = (p.east == EDGE_HALO) && (bx == p.tiles_x - 1 || (p.east_pair && bx == p.tiles_x - 2));
     if (halo_w && !wait_flag(p.flag_w_local, p.step_id, p.error_word, p.halo_timeout_ns)) return;
     if (halo_e && !wait_flag(p.flag_e_local, p.step_id, p.error_word, p.halo_timeout_ns)) return;
 
@@ -584,7 +587,7 @@ __global__ void __launch_bounds__(32 * WX * WY, MINB) fused_step_kernel(const St
             }
             if (halo_e) {
                 const unsigned int old = atomicAdd(p.done_e, 1u);
-                if (old == (unsigned int)p.edge_tiles_y - 1u) {
+                if (old == (unsigned int)p.done_e_count - 1u) {
                     __threadfence_system();
                     *p.done_e = 0u;
                     st_release_sys(p.flag_e_remote, p.step_id + 1u);

@@ -40,3 +40,4 @@ extern const int g_ntb;
 extern const char *const g_tb_auto_f32[2];   // names of the shapes lb_step picks on its own: [no mask, mask]
 extern const char *const g_tb_auto_f64[2];
 extern const char *const g_tb_auto_f32_3;    // ... for three updates per launch
+extern const char *const g_tb_auto_f64_3;

@@ -24,7 +24,10 @@ static void launch_march(const StepParams &p_in, cudaStream_t st)
     int ne = 0;
     if (p.edge_first) {
         const bool w = p.west == EDGE_HALO, e = p.east == EDGE_HALO;
-        ne = (w && e && nstrips > 1) ? 2 : ((w || e) ? 1 : 0);
+        // a last strip narrower than the published columns shares them with the strip before it: both are edge strips
+        const int ne_e = !e ? 0 : (nstrips > 1 && p.nx - (nstrips - 1) * OUT < GHOST_COLS) ? 2 : 1;
+        ne = (w ? 1 : 0) + ne_e;
+        if (ne > nstrips) ne = nstrips;
     }
     p.tiles_x = nstrips;
     p.tiles_y = nseg;
@@ -41,35 +44,38 @@ static void launch_march(const StepParams &p_in, cudaStream_t st)
     if (p.zero_obstacle_velocity) fused_march_kernel<T, V, MATH, NW, MINB, PACKED, PF, -1, SH><<<grid, 32 * NW, 0, st>>>(p);
     else fused_march_kernel<T, V, MATH, NW, MINB, PACKED, PF, 0, SH><<<grid, 32 * NW, 0, st>>>(p);
 }
-// K updates per launch (fused_march_k_kernel): kept rows in shared memory, branch-free obstacle code, fp32 only for
-// K = 3 (the fp64 overlap lane carries two columns)
-template <typename T, int V, int MATH, int NW, int MINB, bool PACKED, int K>
+// K updates per launch (fused_march_k_kernel): kept rows in shared memory, branch-free obstacle code; fp64 with two
+// overlap lanes per side (its lane carries two columns, three levels need three)
+template <typename T, int V, int MATH, int NW, int MINB, bool PACKED, int K, int OVL = 1>
 static void launch_march_k(const StepParams &p_in, cudaStream_t st)
 {
     StepParams p = p_in;
-    constexpr int OUT = 30 * V;
+    constexpr int OUT = (32 - 2 * OVL) * V;
     const int nstrips = (p.nx + OUT - 1) / OUT;
     const int nseg = (p.y_end - p.y_begin + p.seg_rows - 1) / p.seg_rows;
     int ne = 0;
     if (p.edge_first) {
         const bool w = p.west == EDGE_HALO, e = p.east == EDGE_HALO;
-        ne = (w && e && nstrips > 1) ? 2 : ((w || e) ? 1 : 0);
+        // a last strip narrower than the published columns shares them with the strip before it: both are edge strips
+        const int ne_e = !e ? 0 : (nstrips > 1 && p.nx - (nstrips - 1) * OUT < GHOST_COLS) ? 2 : 1;
+        ne = (w ? 1 : 0) + ne_e;
+        if (ne > nstrips) ne = nstrips;
     }
     p.tiles_x = nstrips;
     p.tiles_y = nseg;
     p.edge_first = ne;
     p.edge_tiles_y = (ne * nseg + NW - 1) / NW;
     const unsigned grid = (unsigned)p.edge_tiles_y + (unsigned)(((long long)(nstrips - ne) * nseg + NW - 1) / NW);
-    if (p.mask == nullptr) fused_march_k_kernel<T, V, MATH, NW, MINB, PACKED, K, 0, 0><<<grid, 32 * NW, 0, st>>>(p);
-    else if (p.zero_obstacle_velocity) fused_march_k_kernel<T, V, MATH, NW, MINB, PACKED, K, -1, 1><<<grid, 32 * NW, 0, st>>>(p);
-    else fused_march_k_kernel<T, V, MATH, NW, MINB, PACKED, K, 0, 1><<<grid, 32 * NW, 0, st>>>(p);
+    if (p.mask == nullptr) fused_march_k_kernel<T, V, MATH, NW, MINB, PACKED, K, 0, 0, OVL><<<grid, 32 * NW, 0, st>>>(p);
+    else if (p.zero_obstacle_velocity) fused_march_k_kernel<T, V, MATH, NW, MINB, PACKED, K, -1, 1, OVL><<<grid, 32 * NW, 0, st>>>(p);
+    else fused_march_k_kernel<T, V, MATH, NW, MINB, PACKED, K, 0, 1, OVL><<<grid, 32 * NW, 0, st>>>(p);
 }
 #define MARCH3(NW, MINB, S)                                                                                      \
     {"march3.w" #NW "b" #MINB ".s" #S, LB_TB_MARCH, S, NW, 0, 0, 0,                                               \
      {{launch_march_k<float, 4, MATH_STRICT, NW, MINB, true, 3>, launch_march_k<float, 4, MATH_FAST, NW, MINB, true, 3>}, \
-      {nullptr, nullptr}},                                                                                       \
+      {launch_march_k<double, 2, MATH_STRICT, NW, MINB, false, 3, 2>, launch_march_k<double, 2, MATH_FAST, NW, MINB, false, 3, 2>}}, \
      {{nullptr, nullptr}, {nullptr, nullptr}}, {{nullptr, nullptr}, {nullptr, nullptr}}, 3}
-#define MARCH3_S(NW, MINB) MARCH3(NW, MINB, 8), MARCH3(NW, MINB, 16), MARCH3(NW, MINB, 32), MARCH3(NW, MINB, 64)
+#define MARCH3_S(NW, MINB) MARCH3(NW, MINB, 8), MARCH3(NW, MINB, 16), MARCH3(NW, MINB, 32), MARCH3(NW, MINB, 64), MARCH3(NW, MINB, 128)
 
 // name: march.w<warps per CTA>b<CTAs per SM>[.sh | .scalar | .pf].s<rows per segment>
 //   .sh      the kept rows of the intermediate level in shared memory (thread-private slots): the shipped form
@@ -186,4 +192,5 @@ const int g_ntb = (int)(sizeof(g_tb_shapes) / sizeof(g_tb_shapes[0]));
 // lb_step appends the segment height (".s<rows>", chosen from the lattice size)
 const char *const g_tb_auto_f32[2] = {"march.w4b5.sh", "march.w4b6.sh.bf"};
 const char *const g_tb_auto_f64[2] = {"march.w4b5.sh", "march.w4b5.sh.bf"};
-const char *const g_tb_auto_f32_3 = "march3.w4b4";   // three updates per launch (fp32, large lattices)
+const char *const g_tb_auto_f32_3 = "march3.w4b4";   // three updates per launch (large lattices)
+const char *const g_tb_auto_f64_3 = "march3.w4b5";

@@ -36,6 +36,9 @@ static void launch_variant(const StepParams &p_in, cudaStream_t st)
         const unsigned n_edge = (p.tiles_x < 2 ? 1u : 2u) * (unsigned)p.edge_tiles_y;
         const unsigned n_int = p.tiles_x > 2 ? (unsigned)(p.tiles_x - 2) * (unsigned)p.tiles_y : 0u;
         grid = dim3(n_edge + n_int, 1, 1);
+        // a last tile column narrower than the published columns shares them with the column before it
+        p.east_pair = p.east == EDGE_HALO && p.tiles_x >= 2 && p.nx - (p.tiles_x - 1) * SPAN * WX < GHOST_COLS;
+        p.done_e_count = p.edge_tiles_y + (p.east_pair ? (p.tiles_x == 2 ? p.edge_tiles_y : p.tiles_y) : 0);
     }
     else {
         const unsigned gy = p.tiles_y < 65535 ? p.tiles_y : 65535;

@@ -148,8 +148,8 @@ __global__ void __launch_bounds__(32 * NW, MINB) fused_march_kernel(const StepPa
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
     // Work items are (strip, segment) pairs, one per warp, numbered so that no warp slot is left idle by a strip
-    // count that is not a multiple of NW: first the strips next to a halo edge (p.edge_first = 0, 1 or 2 of them per
-    // segment; their CTAs come first in the grid, wait for the neighbours' ghost columns and publish the new ones
+    // count that is not a multiple of NW: first the strips next to a halo edge (p.edge_first = 0 .. 3 of them per
+    // segment -- a last strip narrower than GHOST_COLS columns makes the one before it an edge strip too; their CTAs come first in the grid, wait for the neighbours' ghost columns and publish the new ones
     // as early as possible in the launch), then all other strips, segment after segment.
     const int nstrips = p.tiles_x, nseg = p.tiles_y, ne = p.edge_first;
     const int n_edge_ctas = (ne * nseg + NW - 1) / NW;
@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) fused_march_kernel(const StepPa
         active = item < ne * nseg;
         seg = item / ne;
         const int k = item - seg * ne;
-        strip = (ne == 2) ? (k ? nstrips - 1 : 0) : (p.west == EDGE_HALO ? 0 : nstrips - 1);
+        strip = (k == 0 && p.west == EDGE_HALO) ? 0 : nstrips - (ne - k);      // west strip, then the east one(s)
     } else {
         const int nint = nstrips - ne;
         const int item = (blockIdx.x - n_edge_ctas) * NW + warp;
@@ -319,11 +319,13 @@ __global__ void __launch_bounds__(32 * NW, MINB) fused_march_kernel(const StepPa
 // sees 9 loads + 9 stores per K updates; a segment of S rows costs S + 2(K-1) level-1 rows.  Slab edges: the
 // neighbour's K outermost columns are patched into the overlap lane (they are all published, lb_fused.cuh
 // StepParams), and levels 1 .. K-1 of them are advanced here exactly as the neighbour advances them.
-template <typename T, int V, int MATH, int NW, int MINB, bool PACKED, int K, int ZOV, int MASKED>
+// OVL = overlap lanes per side: a strip stores (32 - 2 OVL) V columns and has OVL V columns of overlap on each side,
+// enough for K <= OVL V levels (fp32: one lane of four columns; fp64 with three levels: two lanes of two).
+template <typename T, int V, int MATH, int NW, int MINB, bool PACKED, int K, int ZOV, int MASKED, int OVL = 1>
 __global__ void __launch_bounds__(32 * NW, MINB) fused_march_k_kernel(const StepParams p)
 {
-    static_assert(K >= 2 && K <= V && K <= GHOST_COLS, "overlap lanes and ghost arenas carry min(V, GHOST_COLS) columns");
-    constexpr int OUT = 30 * V;
+    static_assert(K >= 2 && K <= OVL * V && K <= GHOST_COLS, "overlap lanes carry OVL*V columns, ghost arenas GHOST_COLS");
+    constexpr int OUT = (32 - 2 * OVL) * V;
     using VT = typename VecOf<T, V>::type;
     __shared__ VT win_s[NW * (K - 1) * 9 * 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -338,7 +340,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) fused_march_k_kernel(const Step
         active = item < ne * nseg;
         seg = item / ne;
         const int k = item - seg * ne;
-        strip = (ne == 2) ? (k ? nstrips - 1 : 0) : (p.west == EDGE_HALO ? 0 : nstrips - 1);
+        strip = (k == 0 && p.west == EDGE_HALO) ? 0 : nstrips - (ne - k);      // west strip, then the east one(s)
     } else {
         const int nint = nstrips - ne;
         const int item = (blockIdx.x - n_edge_ctas) * NW + warp;
@@ -352,7 +354,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) fused_march_k_kernel(const Step
     if (halo_e && !wait_flag(p.flag_e_local, p.step_id, p.error_word, p.halo_timeout_ns)) return;
 
     const int own0 = strip * OUT;
-    const int x0 = own0 - V + lane * V;
+    const int x0 = own0 - OVL * V + lane * V;
     const T *__restrict__ src = static_cast<const T *>(p.src);
     T *__restrict__ dst = static_cast<T *>(p.dst);
     const long long plane = p.plane;
@@ -366,7 +368,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) fused_march_k_kernel(const Step
     if (active) {
         int xl = x0;
         if (p.west == EDGE_WRAP) { if (xl < 0) xl += nx; else if (xl >= nx) xl -= nx; }
-        const bool store_ok = lane != 0 && lane != 31;
+        const bool store_ok = lane >= OVL && lane < 32 - OVL;
         const bool ghost_w = (p.west == EDGE_HALO) && x0 < 0;
         const bool ghost_e = (p.east == EDGE_HALO) && x0 + V > nx && x0 < nx + K;
         // slots of level l (1 .. K-1): 0-2 = populations 0,1,3 of its latest row, 3-5 / 6-8 = populations 2,5,6 of its

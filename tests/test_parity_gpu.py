@@ -1045,9 +1045,9 @@ def test_temporal_blocking_is_bit_identical(gpu, orc, dtype, math):
                     # a single-slab periodic box must be a whole number of strips wide (the round-1 tiles of
                     # an LB_EXPERIMENTS build have their own limits: shared memory in double, tile width)
                     # marching kernel: whole vectors (its rim-gather ancestor, LB_EXPERIMENTS: whole strips); three
-                    # updates per launch: fp32 only, lattices at least three rows high
+                    # updates per launch: lattices at least three rows high
                     need = {"march": 4 if dtype == np.float32 else 2, "rim.w": 128 if dtype == np.float32 else 64}.get(shape[:5])
-                    three = shape.startswith("march3") and (dtype == np.float64 or ny < 3)
+                    three = shape.startswith("march3") and ny < 3
                     assert need is None or three or (bc == "periodic" and nx % need), (shape, bc, nx)
                     continue
                 assert sim.temporal_blocking == shape
@@ -1122,8 +1122,8 @@ def test_two_update_kernel_on_halo_connected_slabs_is_bit_identical(gpu, orc, bc
                 done += n
                 want[done] = one.fields()
         for shape in ("march.w4b5.sh.s32", "march.w4b4.s256", "march3.w4b5.s16"):
-            if shape.startswith("march3") and (dtype == np.float64 or nx // parts < 3):
-                continue                      # three updates per launch: fp32, slabs at least three columns wide
+            if shape.startswith("march3") and nx // parts < 3:
+                continue                      # three updates per launch: slabs at least three columns wide
             slabs = LocalSlabs(nx, ny, parts, omega=1.4, inlet_rho=1.01, outlet_rho=1.0, **kw)
             try:
                 slabs.set_temporal_blocking(shape)
@@ -1138,6 +1138,43 @@ def test_two_update_kernel_on_halo_connected_slabs_is_bit_identical(gpu, orc, bc
                         assert np.array_equal(slabs.download(k), want[done][k]), (nx, ny, shape, done, k)
             finally:
                 slabs.close()
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_slabs_whose_last_strip_is_narrower_than_the_published_columns(gpu, orc, dtype):
+    """Slab widths one or two columns past a whole number of strips (120 / 60 / 56 stored columns per warp) or tiles
+    (256 / 128 columns per CTA of the one-update kernel): the three columns a slab publishes to its east neighbour --
+    and the ghost columns its deeper levels read -- then belong to TWO strips, and both take part in the hand-shake.
+    One-, two- and three-update launches mixed in one run (run(4) with three updates per launch = 1 + 3)."""
+    from lb_b200 import Lattice
+    from lb_b200.lattice import LocalSlabs
+    widths = (121, 122, 242, 257, 258) if dtype == np.float32 else (121, 122, 57, 58, 113, 170, 129, 258)
+    ny = 37
+    for w in widths:
+        for parts in (2, 3):
+            nx = w * parts
+            f0, m = pipe_case(orc, nx, ny, dtype, mask="touching", seed=w)
+            kw = dict(bc="pipe", dtype=dtype, math="strict", zero_obstacle_velocity=False)
+            with Lattice(nx, ny, 1.4, 1.01, 1.0, mask=m, f0=f0, **kw) as one:
+                want = {}
+                done = 0
+                for n in (4, 2, 6, 1):
+                    one.run(n)
+                    done += n
+                    want[done] = one.download("f")
+            for shape in ("off", "march.w4b5.sh.s32", "march3.w4b5.s16"):
+                slabs = LocalSlabs(nx, ny, parts, omega=1.4, inlet_rho=1.01, outlet_rho=1.0, **kw)
+                try:
+                    slabs.set_temporal_blocking(shape)
+                    slabs.set_mask(m)
+                    slabs.upload_f(f0)
+                    done = 0
+                    for n in (4, 2, 6, 1):
+                        slabs.run(n)
+                        done += n
+                        assert np.array_equal(slabs.download("f"), want[done]), (w, parts, shape, done)
+                finally:
+                    slabs.close()
 
 
 def test_self_ring_halo_with_two_update_launches(gpu, orc):
