@@ -526,7 +526,7 @@ def main():
             "vs_baseline": None, "dtype": wl["dtype"], "data": "synthetic",
             "config": {"workload": f"{args.workload}: {wl['desc']}", "global_grid": [gnx, gny],
                        "per_gpu_grid": [slab.nx, gny], "bc": wl["bc"], "omega": wl["omega"], "math": args.math,
-                       "decomposition": f"x-slabs x{world}, peer-memory halos over NVLink (9 values per face row per launch)",
+                       "decomposition": f"x-slabs x{world}, peer-memory halos over NVLink (27 values per face row per launch)",
                        "kernel": kernel,
                        "l2": f"inputs larger than L2: {2 * 9 * cells_local * elem / 1e9:.1f} GB ping-pong working set per GPU vs 126 MB",
                        "published_reference_mlups_other_hw": PUBLISHED_REFERENCE_MLUPS},

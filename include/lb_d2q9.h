@@ -218,20 +218,21 @@ int lb_set_mask_disk(lb_sim *sim, double cx, double cy, double r);
 
 /* -- several lattice updates per pass through HBM (csrc/lb_march.cuh).  lb_step runs a run's steps two or three
  *    at a time in one launch -- the intermediate time levels live on chip, so only 38 B (two updates per launch)
- *    or 26 B (three) per lattice update cross the HBM interface in fp32 instead of 72 -- preceded by one shorter
+ *    or 26 B (three) per lattice update cross the HBM interface in fp32 instead of 72 (fp64: twice that) -- preceded by one shorter
  *    launch when n_steps is not a multiple of the launch depth; the launch that ends the run also stores
  *    rho, u, v.  Results are bit-identical to the one-update kernel in both math modes, on single slabs and on
  *    halo-connected slabs (which then exchange their three outermost columns once per launch instead of one
  *    column every step).
  *    shape -1 = automatic (default): when the WHOLE lattice (global_nx x ny) has at least 2^22 nodes and
- *    ny >= 64, the measured-best shape for this slab -- three updates per launch in fp32 where the slab is
- *    large enough for segments of 16+ rows, two otherwise and in fp64; branch-free obstacle code where there is
+ *    ny >= 64, the measured-best shape for this slab -- three updates per launch where the slab is
+ *    large enough for segments of 16+ rows, two otherwise; branch-free obstacle code where there is
  *    a mask; a segment height of 8 to 64 rows that gives 25 000 - 50 000 (strip, segment) work items -- and the
  *    graph-batched one-update kernel below that size; 0 = off; 1 .. lb_tb2_shape_count()-1 = a compiled shape
  *    by index (lb_tb2_shape_name: "march.w<warps per CTA>b<CTAs per SM>[.sh[.bf] | .scalar].s<rows per segment>"
  *    = two updates per launch, "march3.w..b...s.." = three).  Serves LB_SCHEME_OPENCL /
  *    LB_MODEL_D2Q9 lattices; a single-slab periodic box needs nx to be a multiple of the vector width (4 fp32 /
- *    2 fp64 cells); three updates per launch: fp32, slabs at least 3 columns wide.  All slabs of one lattice must
+ *    2 fp64 cells); three updates per launch: slabs at least 3 columns wide and 3 rows high (fp64 strips then
+ *    store 56 of 64 loaded columns, two overlap lanes per side).  All slabs of one lattice must
  *    use shapes of the same depth (the automatic choice does).  lb_temporal_blocking returns the shape lb_step will
  *    use (0 = one-update kernel). */
 int lb_set_temporal_blocking(lb_sim *sim, int shape);

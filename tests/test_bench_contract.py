@@ -49,7 +49,7 @@ def test_every_evidence_file_named_in_the_profiles_readme_exists():
     missing = sorted(n for n in names if not os.path.exists(os.path.join(prof, n)))
     assert not missing, missing
     traffic = json.load(open(os.path.join(prof, "traffic.json")))
-    for key in ("f32", "f64", "f32_march", "f64_march", "f32_march3"):
+    for key in ("f32", "f64", "f32_march", "f64_march", "f32_march3", "f64_march3"):
         assert traffic[key]["dram_bytes_per_node_per_launch"] > 0 and len(traffic[key]["grid"]) == 2
         src = traffic[key]["source"].split(" ")[0]
         assert os.path.exists(os.path.join(ROOT, src)), src
