@@ -48,28 +48,30 @@ def main():
         for dtype in (np.float32, np.float64):
             for math, tb in (("strict", "off"), ("strict", "march.w4b5.sh.s64"), ("fast", "march.w4b4.s32"), ("fast", "off"),
                              ("strict", "march3.w4b5.s16")):
-                nx, ny, steps = 64 * world + 37, 301, 61
-                f0, mask = make_case(bc, dtype, nx, ny, seed=11)
-                slab = SlabLattice(nx, ny, 1.5, 1.01, 1.0, bc=bc, dtype=dtype, math=math, device=local)
-                slab.lat.set_temporal_blocking(tb)
-                if mask is not None:
-                    slab.set_mask(mask)
-                slab.upload_f(f0)
-                slab.run(steps)
-                slab.run(steps - 1)
-                got = {k: slab.gather(k) for k in ("f", "rho", "u")}
-                mass = slab.total_mass()
-                slab.close()
-                if rank == 0:
-                    with Lattice(nx, ny, 1.5, 1.01, 1.0, mask=mask, f0=f0, bc=bc, dtype=dtype, math=math, device=local) as one:
-                        one.set_temporal_blocking("off")
-                        one.run(2 * steps - 1)
-                        same = all(np.array_equal(got[k], one.download(k)) for k in got)
-                        m1 = one.total_mass()
-                    print(f"[check_multigpu] N={world} {bc:8s} {np.dtype(dtype).name} {math:6s} {tb:15s}: "
-                          f"{'bit-identical' if same else 'MISMATCH'}  mass {mass:.10e} vs {m1:.10e}", flush=True)
-                    ok = ok and same
-                dist.barrier()
+                # 121-122 columns per slab: the published columns spread over the last TWO strips of a slab
+                for nx in (64 * world + 37, 121 * world + world // 2):
+                    ny, steps = 301, 61
+                    f0, mask = make_case(bc, dtype, nx, ny, seed=11)
+                    slab = SlabLattice(nx, ny, 1.5, 1.01, 1.0, bc=bc, dtype=dtype, math=math, device=local)
+                    slab.lat.set_temporal_blocking(tb)
+                    if mask is not None:
+                        slab.set_mask(mask)
+                    slab.upload_f(f0)
+                    slab.run(steps)
+                    slab.run(steps - 1)
+                    got = {k: slab.gather(k) for k in ("f", "rho", "u")}
+                    mass = slab.total_mass()
+                    slab.close()
+                    if rank == 0:
+                        with Lattice(nx, ny, 1.5, 1.01, 1.0, mask=mask, f0=f0, bc=bc, dtype=dtype, math=math, device=local) as one:
+                            one.set_temporal_blocking("off")
+                            one.run(2 * steps - 1)
+                            same = all(np.array_equal(got[k], one.download(k)) for k in got)
+                            m1 = one.total_mass()
+                        print(f"[check_multigpu] N={world} {bc:8s} {nx}x{ny} {np.dtype(dtype).name} {math:6s} {tb:15s}: "
+                              f"{'bit-identical' if same else 'MISMATCH'}  mass {mass:.10e} vs {m1:.10e}", flush=True)
+                        ok = ok and same
+                    dist.barrier()
     # single-process multi-device path behind the drop-in classes (rank 0 drives all visible GPUs)
     if rank == 0 and torch.cuda.device_count() >= 2:
         import lb_b200.dimensionless as lb
