@@ -646,6 +646,9 @@ static int launch_two_steps(lb_sim *sim, int src_idx, int shape, int write_momen
         fill_params(sim, p, src_idx, write_moments);
         if (y_end >= 0) { p.y_begin = y_begin; p.y_end = y_end; }
         p.seg_rows = t.seg_rows;
+#ifdef LB_SEG_ROWS_ENV                                 // side builds of tools/seg_sweep.sh: any segment height
+        if (const char *e = getenv("LB_SEG_ROWS")) p.seg_rows = atoi(e) > 0 ? atoi(e) : p.seg_rows;
+#endif
         t.launch_march[di][mi](p, sim->stream);
     } else if (t.kind == LB_TB_ROWS) {
         StepParams p;
