@@ -55,6 +55,7 @@ struct lb_sim {
     bool prestream_done = false;  // cython / opencl_old schemes: is the next step's BC + swap already applied to `cur`
     float *frozen = nullptr;      // opencl_old: the populations `move` never writes (lb_oldcl.cuh)
     int tb2_shape = -1;           // two updates per launch: -1 = automatic, 0 = off, else index into g_tb_shapes
+    int sm_count = 148;           // SMs of the device (segment heights that fill whole waves of CTAs)
     int pitch = 0;                // row pitch in elements (multiple of 512 B)
     long long plane = 0;          // elements per plane
     size_t buf_bytes = 0;         // bytes of one guarded 9-plane buffer
@@ -635,6 +636,32 @@ static int tb2_effective_shape(const lb_sim *sim)
     return tb2_auto_shape(sim);
 }
 
+// Rows per segment of a marching launch.  A hand-picked shape runs with the height in its name.  The automatic choice
+// starts from that height too; on lattices of a few waves of CTAs it takes the height (6 .. 64 rows) with the best
+// "fill of the last wave x useful rows per segment" instead: on C2 (4096 x 1024) 11-row segments make 823 CTAs for 888
+// slots, one full wave, where 8-row ones make 1.26 waves -- +10 % (profiles/r2_seg_sweep.txt; lattices of many waves
+// show no such effect there and keep the power of two).
+static int tb2_segment_rows(const lb_sim *sim, int shape)
+{
+    const LbTbShape &t = g_tb_shapes[shape];
+    if (t.kind != LB_TB_MARCH || sim->tb2_shape >= 0 || t.minb <= 0 || t.nw <= 0) return t.seg_rows;
+    const int K = tb_depth(shape), ny = sim->cfg.ny;
+    const int out = sim->elem == 4 ? 120 : (K > 2 ? 56 : 60);
+    const long long nstrips = (sim->cfg.nx + out - 1) / out;
+    const long long slots = (long long)sim->sm_count * t.minb;               // CTAs resident at once
+    auto ctas = [&](int S) { return (nstrips * ((ny + S - 1) / S) + t.nw - 1) / t.nw; };
+    if (ctas(t.seg_rows) > 3 * slots) return t.seg_rows;
+    auto fill = [&](int S) {
+        const long long c = ctas(S), waves = (c + slots - 1) / slots;
+        return (double)c / (double)(waves * slots) * (double)S / (double)(S + 2 * (K - 1));
+    };
+    int best = t.seg_rows;
+    double best_fill = fill(best) * 1.02;                                    // a clear gain, or the power of two stays
+    for (int S = 6; S <= 64; ++S)
+        if (fill(S) > best_fill) { best = S; best_fill = fill(S); }
+    return best;
+}
+
 // one launch of a two-update (three-update: tb_depth) shape: reads buffer src_idx, writes the other one.  The marching
 // kernel can store the moments of its last step; the round-1 tiles cannot (write_moments must be 0 for them).
 static int launch_two_steps(lb_sim *sim, int src_idx, int shape, int write_moments, int y_begin = 0, int y_end = -1)
@@ -645,7 +672,7 @@ static int launch_two_steps(lb_sim *sim, int src_idx, int shape, int write_momen
         StepParams p;
         fill_params(sim, p, src_idx, write_moments);
         if (y_end >= 0) { p.y_begin = y_begin; p.y_end = y_end; }
-        p.seg_rows = t.seg_rows;
+        p.seg_rows = tb2_segment_rows(sim, shape);
 #ifdef LB_SEG_ROWS_ENV                                 // side builds of tools/seg_sweep.sh: any segment height
         if (const char *e = getenv("LB_SEG_ROWS")) p.seg_rows = atoi(e) > 0 ? atoi(e) : p.seg_rows;
 #endif
@@ -680,6 +707,7 @@ extern "C" {
 
 int lb_temporal_blocking(const lb_sim *sim) { return sim ? tb2_effective_shape(sim) : 0; }
 int lb_tb2_shape_count(void) { return g_ntb; }
+int lb_segment_rows(const lb_sim *sim) { const int k = sim ? tb2_effective_shape(sim) : 0; return k > 0 ? tb2_segment_rows(sim, k) : 0; }
 const char *lb_tb2_shape_name(int shape) { return (shape >= 0 && shape < g_ntb) ? g_tb_shapes[shape].name : nullptr; }
 
 int lb_set_temporal_blocking(lb_sim *sim, int shape)
@@ -815,6 +843,7 @@ int lb_create(const lb_config *cfg, lb_sim **out)
         if (e__ != cudaSuccess) return bail(LB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
     } while (0)
     CUC(cudaSetDevice(cfg->device));
+    { int n = 0; if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, cfg->device) == cudaSuccess && n > 0) sim->sm_count = n; else cudaGetLastError(); }
     if (cfg->stream) sim->stream = (cudaStream_t)cfg->stream;
     else { CUC(cudaStreamCreateWithFlags(&sim->stream, cudaStreamNonBlocking)); sim->own_stream = true; }
     const size_t guard = (size_t)2 * sim->pitch * sim->elem;

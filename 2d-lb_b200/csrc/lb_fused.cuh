@@ -282,6 +282,14 @@ __device__ __forceinline__ void finish_row(const StepParams &p, const Consts<T> 
         solid_bits = solid_in;
         const bool zov_ = ZOV < 0 ? (p.zero_obstacle_velocity != 0) : (ZOV != 0);
         if (zov_) all_solid = __all_sync(0xffffffffu, solid_bits == (1u << V) - 1u);
+        // fp64 (two instructions per select) skips them by a warp-uniform branch when no node of the warp's row is solid:
+        // +3 % on C5; in fp32 the same branch costs 1-4 % (profiles/r2_ab_bf_skip.txt; -DLB_BF_SKIP builds it there too)
+#ifdef LB_BF_SKIP
+        constexpr bool skip_if_fluid = true;
+#else
+        constexpr bool skip_if_fluid = sizeof(T) == 8;
+#endif
+        if (!skip_if_fluid || __any_sync(0xffffffffu, solid_bits != 0))
 #pragma unroll
         for (int e = 0; e < V; ++e) {                     // D2Q9.cl:410-431, as selects
             const bool sd = (solid_bits >> e) & 1u;

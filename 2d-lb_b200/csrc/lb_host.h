@@ -34,6 +34,7 @@ struct LbTbShape {
     void (*launch_rows[2][2])(const lb::StepParams &, dim3, size_t, cudaStream_t);
     void (*launch_cells[2][2])(const lb::Tb2Params &, dim3, size_t, cudaStream_t);
     int depth;                 // LB_TB_MARCH: lattice updates per launch (0 = the default, two)
+    int minb;                  // LB_TB_MARCH: CTAs per SM the kernel is compiled for (__launch_bounds__)
 };
 extern const LbTbShape g_tb_shapes[];
 extern const int g_ntb;

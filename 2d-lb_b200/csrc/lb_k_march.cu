@@ -74,7 +74,7 @@ static void launch_march_k(const StepParams &p_in, cudaStream_t st)
     {"march3.w" #NW "b" #MINB ".s" #S, LB_TB_MARCH, S, NW, 0, 0, 0,                                               \
      {{launch_march_k<float, 4, MATH_STRICT, NW, MINB, true, 3>, launch_march_k<float, 4, MATH_FAST, NW, MINB, true, 3>}, \
       {launch_march_k<double, 2, MATH_STRICT, NW, MINB, false, 3, 2>, launch_march_k<double, 2, MATH_FAST, NW, MINB, false, 3, 2>}}, \
-     {{nullptr, nullptr}, {nullptr, nullptr}}, {{nullptr, nullptr}, {nullptr, nullptr}}, 3}
+     {{nullptr, nullptr}, {nullptr, nullptr}}, {{nullptr, nullptr}, {nullptr, nullptr}}, 3, MINB}
 #define MARCH3_S(NW, MINB) MARCH3(NW, MINB, 8), MARCH3(NW, MINB, 16), MARCH3(NW, MINB, 32), MARCH3(NW, MINB, 64), MARCH3(NW, MINB, 128)
 
 // name: march.w<warps per CTA>b<CTAs per SM>[.sh | .scalar | .pf].s<rows per segment>
@@ -88,23 +88,23 @@ static void launch_march_k(const StepParams &p_in, cudaStream_t st)
     {"march.w" #NW "b" #MINB PN ".s" #S, LB_TB_MARCH, S, NW, 0, 0, 0,                                             \
      {{launch_march<float, 4, MATH_STRICT, NW, MINB, PACKED>, launch_march<float, 4, MATH_FAST, NW, MINB, PACKED>},       \
       {launch_march<double, 2, MATH_STRICT, NW, MINB, false>, launch_march<double, 2, MATH_FAST, NW, MINB, false>}},      \
-     {{nullptr, nullptr}, {nullptr, nullptr}}, {{nullptr, nullptr}, {nullptr, nullptr}}}
+     {{nullptr, nullptr}, {nullptr, nullptr}}, {{nullptr, nullptr}, {nullptr, nullptr}}, 0, MINB}
 #define MARCHPF(NW, MINB, S)                                                                                     \
     {"march.w" #NW "b" #MINB ".pf.s" #S, LB_TB_MARCH, S, NW, 0, 0, 0,                                            \
      {{launch_march<float, 4, MATH_STRICT, NW, MINB, true, true>, launch_march<float, 4, MATH_FAST, NW, MINB, true, true>},   \
       {launch_march<double, 2, MATH_STRICT, NW, MINB, false, true>, launch_march<double, 2, MATH_FAST, NW, MINB, false, true>}}, \
-     {{nullptr, nullptr}, {nullptr, nullptr}}, {{nullptr, nullptr}, {nullptr, nullptr}}}
+     {{nullptr, nullptr}, {nullptr, nullptr}}, {{nullptr, nullptr}, {nullptr, nullptr}}, 0, MINB}
 #define MARCHSH_S(NW, MINB) MARCHSH(NW, MINB, 8), MARCHSH(NW, MINB, 16), MARCHSH(NW, MINB, 32), MARCHSH(NW, MINB, 64), MARCHSH(NW, MINB, 128), MARCHSH(NW, MINB, 256)
 #define MARCHSH(NW, MINB, S)                                                                                     \
     {"march.w" #NW "b" #MINB ".sh.s" #S, LB_TB_MARCH, S, NW, 0, 0, 0,                                            \
      {{launch_march<float, 4, MATH_STRICT, NW, MINB, true, false, true>, launch_march<float, 4, MATH_FAST, NW, MINB, true, false, true>},   \
       {launch_march<double, 2, MATH_STRICT, NW, MINB, false, false, true>, launch_march<double, 2, MATH_FAST, NW, MINB, false, false, true>}}, \
-     {{nullptr, nullptr}, {nullptr, nullptr}}, {{nullptr, nullptr}, {nullptr, nullptr}}}
+     {{nullptr, nullptr}, {nullptr, nullptr}}, {{nullptr, nullptr}, {nullptr, nullptr}}, 0, MINB}
 #define MARCHBF(NW, MINB, S)                                                                                     \
     {"march.w" #NW "b" #MINB ".sh.bf.s" #S, LB_TB_MARCH, S, NW, 0, 0, 0,                                         \
      {{launch_march<float, 4, MATH_STRICT, NW, MINB, true, false, true, true>, launch_march<float, 4, MATH_FAST, NW, MINB, true, false, true, true>},   \
       {launch_march<double, 2, MATH_STRICT, NW, MINB, false, false, true, true>, launch_march<double, 2, MATH_FAST, NW, MINB, false, false, true, true>}}, \
-     {{nullptr, nullptr}, {nullptr, nullptr}}, {{nullptr, nullptr}, {nullptr, nullptr}}}
+     {{nullptr, nullptr}, {nullptr, nullptr}}, {{nullptr, nullptr}, {nullptr, nullptr}}, 0, MINB}
 #define MARCH_S(NW, MINB, PACKED, PN) MARCH(NW, MINB, PACKED, PN, 32), MARCH(NW, MINB, PACKED, PN, 64), MARCH(NW, MINB, PACKED, PN, 128), MARCH(NW, MINB, PACKED, PN, 256)
 
 #ifdef LB_EXPERIMENTS

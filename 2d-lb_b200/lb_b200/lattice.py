@@ -271,6 +271,11 @@ class Lattice:
         k = N.lib().lb_temporal_blocking(self._h)
         return N.lib().lb_tb2_shape_name(k).decode()
 
+    @property
+    def segment_rows(self):
+        """Rows per (strip, segment) work item of the marching kernel's launches on this lattice (0: one-update kernel)."""
+        return int(N.lib().lb_segment_rows(self._h))
+
     def copy_ceiling_ms(self, reps=10):
         """ms per launch of an arithmetic-free kernel with the fused step's memory access pattern (the
         practical HBM ceiling of this device for this lattice; populations are left untouched)."""

@@ -503,7 +503,7 @@ def main():
         two = tb2 != "off"
         updates_per_launch = 1 if not two else (3 if tb2.startswith("march3") else 2)
         kernel = ("fused_step_kernel (one lattice update per launch)" if not two else
-                  f"fused_march{'_k' if updates_per_launch == 3 else ''}_kernel shape {tb2} ({'three' if updates_per_launch == 3 else 'two'} "
+                  f"fused_march{'_k' if updates_per_launch == 3 else ''}_kernel shape {tb2}, {lat.segment_rows}-row segments ({'three' if updates_per_launch == 3 else 'two'} "
                   "lattice updates per launch, the intermediate time levels on chip; a run whose length is not a multiple of that "
                   "starts with one shorter launch)")
         # measured DRAM traffic of ONE launch of the dominant kernel (ncu --set full, dram__bytes_read.sum +

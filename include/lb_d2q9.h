@@ -234,9 +234,12 @@ int lb_set_mask_disk(lb_sim *sim, double cx, double cy, double r);
  *    2 fp64 cells); three updates per launch: slabs at least 3 columns wide and 3 rows high (fp64 strips then
  *    store 56 of 64 loaded columns, two overlap lanes per side).  All slabs of one lattice must
  *    use shapes of the same depth (the automatic choice does).  lb_temporal_blocking returns the shape lb_step will
- *    use (0 = one-update kernel). */
+ *    use (0 = one-update kernel); lb_segment_rows the rows per segment of its launches (0 with the one-update
+ *    kernel): the height in the shape's name, except that the automatic choice, on lattices of three waves of CTAs or
+ *    fewer, takes the height between 6 and 64 rows that fills the last wave best (C2: 11 rows, one wave). */
 int lb_set_temporal_blocking(lb_sim *sim, int shape);
 int lb_temporal_blocking(const lb_sim *sim);
+int lb_segment_rows(const lb_sim *sim);
 int lb_tb2_shape_count(void);
 const char *lb_tb2_shape_name(int shape);
 

@@ -1177,6 +1177,31 @@ def test_slabs_whose_last_strip_is_narrower_than_the_published_columns(gpu, orc,
                     slabs.close()
 
 
+def test_automatic_segment_height_on_a_lattice_of_few_waves(gpu, orc):
+    """C2's grid (4096 x 1024, obstacles): the automatic choice keeps the two-update shape but takes a segment height that
+    fills whole waves of CTAs (any height gives the same bits); a hand-picked shape keeps the height in its name;
+    a large lattice keeps the power of two."""
+    from lb_b200 import Lattice
+    f0, m = pipe_case(orc, 4096, 1024, np.float32, mask="blocks", seed=5)
+    with Lattice(4096, 1024, 1.5, 1.01, 1.0, mask=m, f0=f0) as sim:
+        name = sim.temporal_blocking
+        assert name.startswith("march.") and 6 <= sim.segment_rows <= 64
+        auto_rows = sim.segment_rows
+        sim.run(6)
+        got = sim.fields()
+        sim.set_temporal_blocking(name)
+        assert sim.segment_rows == int(name.rsplit(".s", 1)[1])
+        sim.set_temporal_blocking("off")
+        assert sim.segment_rows == 0
+        sim.upload_f(f0)
+        sim.run(6)
+        want = sim.fields()
+        for k in ("f", "rho", "u", "v"):
+            assert np.array_equal(got[k], want[k]), (k, auto_rows)
+    with Lattice(8192, 4096, 1.5, 1.01, 1.0) as big:
+        assert big.temporal_blocking.startswith("march3.") and big.segment_rows == int(big.temporal_blocking.rsplit(".s", 1)[1])
+
+
 def test_self_ring_halo_with_two_update_launches(gpu, orc):
     """A periodic slab whose halo edges are connected to itself, marching kernel: equals in-kernel wrap."""
     from lb_b200 import Lattice

@@ -15,3 +15,16 @@ print({k: d["roofline"][k] for k in ("achieved","frac","traffic","frac_on_measur
 print(d["checks"]["checksum"], d["clocks"], d["cpu_baseline"]["value"])
 PY
 cat gpurun_out/bench_default.time
+if [ "${1:-}" = "more" ]; then   # the other workloads' lines
+  for w in c2 c5 pub c3; do
+    timeout 600 python bench.py --workload $w --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/bench_$w.json 2> gpurun_out/bench_$w.err
+    python - $w <<'PY'
+import json,sys
+try:
+    d=json.loads(open(f"gpurun_out/bench_{sys.argv[1]}.json").read().strip().splitlines()[-1])
+    print(sys.argv[1], "value", round(d["value"]), "ms", round(d["ms_per_step"],4), "e2e", d["e2e"] and round(d["e2e"]["value"]), "launches", d["gpu_launches"], d["config"]["kernel"][:75])
+except Exception as e:
+    print(sys.argv[1], "unreadable", e)
+PY
+  done
+fi

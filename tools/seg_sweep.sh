@@ -2,6 +2,8 @@
 # Segment heights that are not powers of two (side build with -DLB_SEG_ROWS_ENV: build/liblb_d2q9_seg.so reads
 # LB_SEG_ROWS): does a height that fills the last wave of CTAs pay?  The N=8 slab shape of C4 (three updates per
 # launch), C2 (two), C4 with FAST math for the record.
+# Build the side library first (where nvcc is):
+#   PYTHONPATH=2d-lb_b200 python -c "from lb_b200 import build; build.build_library(extra_flags=['-DLB_SEG_ROWS_ENV'], out='$PWD/build/liblb_d2q9_seg.so', tag='.seg')"
 set -u
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
