@@ -464,6 +464,7 @@ static void fill_params(lb_sim *s, StepParams &p, int src_idx, int write_moments
     p.c2 = pack_consts(p.cf);
     p.y_begin = 0; p.y_end = s->cfg.ny;
     p.edge_rows = s->edge_rows;
+    p.sm_count = s->sm_count;
     if (uses_halo(s)) {
         // launch number `halo_epoch` reads the ghost columns of parity epoch&1 once the flag says epoch+1,
         // writes the neighbours' columns of the other parity and publishes epoch+2 there
@@ -662,6 +663,19 @@ static int tb2_segment_rows(const lb_sim *sim, int shape)
     return best;
 }
 
+// ... and the height of the segments at the END of such a launch (0: all alike).  A launch of many waves ends with a
+// tail in which ever fewer SMs still work on their last 64-row items (half an item's duration on average: 6 % of
+// a launch on a 4096 x 32768 slab, 1 % on C4); cutting the last rows -- two waves of work items' worth, see
+// march_segments in lb_k_march.cu -- into segments a quarter as high shortens that tail four times.
+static int tb2_short_segment_rows(const lb_sim *sim, int shape)
+{
+    const LbTbShape &t = g_tb_shapes[shape];
+    if (t.kind != LB_TB_MARCH || sim->tb2_shape >= 0 || t.minb <= 0 || t.nw <= 0) return 0;
+    const int S1 = tb2_segment_rows(sim, shape);
+    if (S1 != t.seg_rows || S1 < 32) return 0;        // few waves: the height already fills them
+    return S1 / 4;
+}
+
 // one launch of a two-update (three-update: tb_depth) shape: reads buffer src_idx, writes the other one.  The marching
 // kernel can store the moments of its last step; the round-1 tiles cannot (write_moments must be 0 for them).
 static int launch_two_steps(lb_sim *sim, int src_idx, int shape, int write_moments, int y_begin = 0, int y_end = -1)
@@ -673,6 +687,7 @@ static int launch_two_steps(lb_sim *sim, int src_idx, int shape, int write_momen
         fill_params(sim, p, src_idx, write_moments);
         if (y_end >= 0) { p.y_begin = y_begin; p.y_end = y_end; }
         p.seg_rows = tb2_segment_rows(sim, shape);
+        p.seg_rows2 = tb2_short_segment_rows(sim, shape);
 #ifdef LB_SEG_ROWS_ENV                                 // side builds of tools/seg_sweep.sh: any segment height
         if (const char *e = getenv("LB_SEG_ROWS")) p.seg_rows = atoi(e) > 0 ? atoi(e) : p.seg_rows;
 #endif

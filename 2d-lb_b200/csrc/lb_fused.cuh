@@ -66,6 +66,9 @@ struct StepParams {
     int done_e_count;
     int y_begin, y_end;       // rows this launch updates (whole lattice: 0, ny); band launches of lb_step_banded
     int seg_rows;             // marching kernel (lb_march.cuh): rows per segment (within y_begin .. y_end)
+    int seg_rows2, seg_tall;  // ... the first seg_tall segments are seg_rows high, the rest seg_rows2 (shorter work items at
+                              // the end of the grid: a shorter tail; seg_rows2 = 0 on entry to the launcher: uniform)
+    int sm_count;
 };
 enum : int { GHOST_COLS = 3, GHOST_SLOTS = 9 * GHOST_COLS };
 

@@ -182,8 +182,10 @@ __global__ void __launch_bounds__(32 * NW, MINB) fused_march_kernel(const StepPa
     const int nx = p.nx, ny = p.ny, pitch = p.pitch;
     const Consts<T> &c = consts_in<T>(p);
     const bool periodic = (p.bc == BC_PERIODIC);
-    const int ys = p.y_begin + seg * p.seg_rows;       // whole lattice: y_begin = 0, y_end = ny; lb_run_streamed
-    const int ye = min(ys + p.seg_rows, p.y_end);      // launches row bands (the rows just outside are only read)
+    // whole lattice: y_begin = 0, y_end = ny; lb_run_streamed launches row bands (the rows just outside are only read)
+    const bool tall = seg < p.seg_tall;
+    const int ys = p.y_begin + (tall ? seg * p.seg_rows : p.seg_tall * p.seg_rows + (seg - p.seg_tall) * p.seg_rows2);
+    const int ye = min(ys + (tall ? p.seg_rows : p.seg_rows2), p.y_end);
     const int gs = ny + 2;
 
     if (active) {                                      // warp-uniform
@@ -361,8 +363,9 @@ __global__ void __launch_bounds__(32 * NW, MINB) fused_march_k_kernel(const Step
     const int nx = p.nx, ny = p.ny, pitch = p.pitch;
     const Consts<T> &c = consts_in<T>(p);
     const bool periodic = (p.bc == BC_PERIODIC);
-    const int ys = p.y_begin + seg * p.seg_rows;
-    const int ye = min(ys + p.seg_rows, p.y_end);
+    const bool tall = seg < p.seg_tall;
+    const int ys = p.y_begin + (tall ? seg * p.seg_rows : p.seg_tall * p.seg_rows + (seg - p.seg_tall) * p.seg_rows2);
+    const int ye = min(ys + (tall ? p.seg_rows : p.seg_rows2), p.y_end);
     const int gs = ny + 2;
 
     if (active) {

@@ -1202,6 +1202,33 @@ def test_automatic_segment_height_on_a_lattice_of_few_waves(gpu, orc):
         assert big.temporal_blocking.startswith("march3.") and big.segment_rows == int(big.temporal_blocking.rsplit(".s", 1)[1])
 
 
+@pytest.mark.parametrize("dtype,nx,ny", [(np.float32, 8192, 8192), (np.float64, 8192, 4096), (np.float32, 2400, 30000)])
+def test_automatic_launches_with_short_segments_at_the_end(gpu, dtype, nx, ny):
+    """Lattices of many waves of CTAs: the automatic launches cut their last rows into shorter segments (a shorter tail).
+    Same bits as the one-update kernel and as the uniformly segmented shape of the same name, with obstacles, for run
+    lengths that mix one-, two- and three-update launches; pipe and periodic."""
+    from lb_b200 import Lattice
+    for bc in ("pipe", "periodic"):
+        sums = {}
+        for tb in ("auto", "named", "off"):
+            kw = dict(bc=bc, dtype=dtype) if bc == "periodic" else dict(dtype=dtype)
+            args = (nx, ny, 1.6) if bc == "periodic" else (nx, ny, 1.6, 1.003, 1.0)
+            with Lattice(*args, **kw) as sim:
+                if bc == "pipe":
+                    sim.set_mask_disk(nx / 3.0, ny - 40.0, 37.0)          # an obstacle inside the short segments
+                sim.init_synthetic("pipe_ramp" if bc == "pipe" else "shear_layers", u0=0.04, amplitude=1e-3, seed=4)
+                name = sim.temporal_blocking
+                assert name.startswith("march3.") and sim.segment_rows >= 32, name
+                if tb == "named":
+                    sim.set_temporal_blocking(name)
+                elif tb == "off":
+                    sim.set_temporal_blocking("off")
+                sim.run(7)
+                sim.run(6)
+                sums[tb] = (sim.checksum(), sim.total_mass())
+        assert sums["auto"] == sums["off"] == sums["named"], (bc, sums)
+
+
 def test_self_ring_halo_with_two_update_launches(gpu, orc):
     """A periodic slab whose halo edges are connected to itself, marching kernel: equals in-kernel wrap."""
     from lb_b200 import Lattice

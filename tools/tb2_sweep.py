@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--no-mask", action="store_true")
     ap.add_argument("--shapes", default="", help="comma-separated tile names (default: all)")
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--auto-first", action="store_true", help="time the automatic choice before the named shapes")
     a = ap.parse_args()
     dtype = np.float32 if a.dtype == "f32" else np.float64
     elem = 4 if a.dtype == "f32" else 8
@@ -38,12 +39,11 @@ def main():
     print(f"# {a.nx}x{a.ny} {a.dtype} {a.math} {a.bc}, {a.steps} steps per run")
     base, want = None, None
     wanted = [w for w in a.shapes.split(",") if w]
-    if "auto" in wanted:                # the shape lb_step picks on this lattice by itself
+    runs = [(k, name) for k, name in enumerate(names) if not wanted or name == "off" or name in wanted]
+    if "auto" in wanted:                # what lb_step does on this lattice by itself (shape, segment heights)
         sim.set_temporal_blocking("auto")
-        wanted = [w for w in wanted if w != "auto"] + [sim.temporal_blocking]
-    for k, name in enumerate(names):
-        if wanted and name != "off" and name not in wanted:
-            continue
+        runs.insert(1 if a.auto_first else len(runs), (-1, f"auto:{sim.temporal_blocking.replace('march', 'm')}/{sim.segment_rows}"))
+    for k, name in runs:
         try:
             sim.set_temporal_blocking(k)
         except native.LBError as exc:
