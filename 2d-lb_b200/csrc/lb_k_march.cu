@@ -38,7 +38,6 @@ static void launch_march(const StepParams &p_in, cudaStream_t st)
 {
     StepParams p = p_in;
     constexpr int OUT = 30 * V;
-    static_assert(NW % 2 == 0, "edge CTAs hold whole (west, east) pairs of work items");
     const int nstrips = (p.nx + OUT - 1) / OUT;
     const int nseg = march_segments<NW, MINB>(p, nstrips);
     // strips next to a halo edge: 0 on a single slab, else strip 0 and / or the last one

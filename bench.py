@@ -20,7 +20,8 @@ the whole grid.  Workloads are BASELINE.json's configs:
 `value`  : device-resident throughput, CUDA events around K launches, max over ranks.
 `e2e`    : the same K steps through the C-ABI with HOST buffers: upload of f from pinned memory, K steps,
            read-back of rho, u, v -- all inside the timed region (N = 1: one pipelined lb_run_streamed call;
-           N > 1: lb_upload_f + lb_halo_prime + lb_step + lb_download per rank).
+           N > 1: lb_upload_f + lb_halo_prime + lb_step + lb_download per rank); `equals_resident_run`: the
+           populations the pipelined call leaves behind have the checksum of upload + run (checked untimed, N = 1).
 `roofline`: achieved = ALGORITHMIC bytes per launch (72 B fp32 / 144 B fp64 per lattice update x updates per
            launch) over the average launch duration, against MEASURED_PEAKS.json's hbm_gbs; `traffic` = the
            kernel's measured DRAM bytes per launch (ncu, profiles/traffic.json) and `frac_on_measured_traffic`
@@ -481,9 +482,15 @@ def main():
         e2e_call()                           # warm-up (page-locks, graph builds)
         ms_e2e = timed(e2e_call)
         ok = bool(np.isfinite(m_np[0]).all())
+        same = None
+        if world == 1:                       # the pipelined call against upload + run, untimed: the same bits?
+            c_streamed = lat.checksum()
+            lat.upload_f(f_np)
+            lat.run(args.steps)
+            same = c_streamed == lat.checksum()
         e2e = {"value": cells_global * args.steps / (ms_e2e * 1e-3) / 1e6, "unit": "MLUPS",
                "h2d_bytes_per_step": n_f * elem * world / args.steps, "d2h_bytes_per_step": 3 * n_m * elem * world / args.steps,
-               "ms_per_call": ms_e2e, "steps_per_call": args.steps, "rho_finite": ok,
+               "ms_per_call": ms_e2e, "steps_per_call": args.steps, "rho_finite": ok, "equals_resident_run": same,
                "call": ("lb_run_streamed(pinned host f, K, pinned rho, u, v): upload, K steps and read-back pipelined by row bands"
                         if world == 1 else "lb_upload_f(pinned host f) + lb_halo_prime + lb_step(K) + lb_download(rho,u,v) per call")}
         del host_f, host_m
