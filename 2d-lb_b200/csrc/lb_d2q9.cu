@@ -606,7 +606,7 @@ static int tb2_find(const char *name)
 // enough to be HBM-bound; small lattices keep the graph-batched one-update kernel.  The decision uses only
 // what every slab of a decomposed lattice knows (global width, height), so all slabs decide alike.
 #ifndef LB_MARCH3_MAX_SEG
-#define LB_MARCH3_MAX_SEG 64
+#define LB_MARCH3_MAX_SEG 128         // with short segments at the end of a launch tall ones pay: C4 +1 % over 64 rows
 #endif
 static int tb2_auto_shape(const lb_sim *sim, bool size_gate = true, bool allow3 = true)
 {
@@ -617,7 +617,7 @@ static int tb2_auto_shape(const lb_sim *sim, bool size_gate = true, bool allow3 
     // ones leave too few (strip, segment) work items to fill and balance 148 SMs x 16-24 warps (profiles/
     // r2_march_segment_height_*.txt, r2_march3_*.txt).  Lattices with enough rows for segments of 16 or more run
     // THREE updates per launch (fp64 with two overlap lanes per side: 56 stored columns per strip); smaller ones two,
-    // with segments down to 8 rows (8 on a 4096 x 1024 lattice, 64 and more on C4 and C5).
+    // with segments down to 8 rows (8 on a 4096 x 1024 lattice, 128 on C4 and C5, 64 on C4's N=8 slabs).
     const bool f32 = sim->elem == 4;
     auto items_per_row = [&](int out) { return (long long)((sim->cfg.nx + out - 1) / out); };
     auto pow2_floor = [](long long want, int lo, int hi) { int s = lo; while (s < hi && 2 * s <= want) s *= 2; return s; };
@@ -690,6 +690,7 @@ static int launch_two_steps(lb_sim *sim, int src_idx, int shape, int write_momen
         p.seg_rows2 = tb2_short_segment_rows(sim, shape);
 #ifdef LB_SEG_ROWS_ENV                                 // side builds of tools/seg_sweep.sh: any segment height
         if (const char *e = getenv("LB_SEG_ROWS")) p.seg_rows = atoi(e) > 0 ? atoi(e) : p.seg_rows;
+        if (const char *e = getenv("LB_SEG_ROWS2")) p.seg_rows2 = atoi(e);
 #endif
         t.launch_march[di][mi](p, sim->stream);
     } else if (t.kind == LB_TB_ROWS) {

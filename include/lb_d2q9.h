@@ -226,7 +226,8 @@ int lb_set_mask_disk(lb_sim *sim, double cx, double cy, double r);
  *    shape -1 = automatic (default): when the WHOLE lattice (global_nx x ny) has at least 2^22 nodes and
  *    ny >= 64, the measured-best shape for this slab -- three updates per launch where the slab is
  *    large enough for segments of 16+ rows, two otherwise; branch-free obstacle code where there is
- *    a mask; a segment height of 8 to 64 rows that gives 25 000 - 50 000 (strip, segment) work items -- and the
+ *    a mask; a segment height of 8 to 128 rows that leaves thousands of (strip, segment) work items, the last rows of a large
+ *    launch in segments a quarter as high -- and the
  *    graph-batched one-update kernel below that size; 0 = off; 1 .. lb_tb2_shape_count()-1 = a compiled shape
  *    by index (lb_tb2_shape_name: "march.w<warps per CTA>b<CTAs per SM>[.sh[.bf] | .scalar].s<rows per segment>"
  *    = two updates per launch, "march3.w..b...s.." = three).  Serves LB_SCHEME_OPENCL /
