@@ -723,6 +723,26 @@ extern "C" {
 
 int lb_temporal_blocking(const lb_sim *sim) { return sim ? tb2_effective_shape(sim) : 0; }
 int lb_tb2_shape_count(void) { return g_ntb; }
+
+// diagnostic (no device needed): the launch geometry the marching kernels' launchers compute
+int lb_plan_march_launch(int nx, int rows, int elem_bytes, int depth, int nw, int minb, int seg_rows, int seg_rows2, int sm_count,
+                         int west_halo, int east_halo, int *n_strips, int *n_edge_strips, int *n_tall, int *n_short, int *short_rows)
+{
+    if (nx < 1 || rows < 1 || (elem_bytes != 4 && elem_bytes != 8) || depth < 2 || depth > 3 || nw < 1 || minb < 1 || seg_rows < 1)
+        return LB_ERR_INVALID;
+    const int out = elem_bytes == 4 ? 120 : (depth > 2 ? 56 : 60);
+    const int nstrips = (nx + out - 1) / out;
+    StepParams p;
+    memset(&p, 0, sizeof(p));
+    p.y_begin = 0; p.y_end = rows; p.seg_rows = seg_rows; p.seg_rows2 = seg_rows2; p.sm_count = sm_count;
+    const int nseg = lb_march_segments(p, nstrips, nw, minb);
+    if (n_strips) *n_strips = nstrips;
+    if (n_edge_strips) *n_edge_strips = lb_march_edge_strips(nx, out, nstrips, west_halo != 0, east_halo != 0);
+    if (n_tall) *n_tall = p.seg_tall;
+    if (n_short) *n_short = nseg - p.seg_tall;
+    if (short_rows) *short_rows = p.seg_rows2;
+    return LB_OK;
+}
 int lb_segment_rows(const lb_sim *sim) { const int k = sim ? tb2_effective_shape(sim) : 0; return k > 0 ? tb2_segment_rows(sim, k) : 0; }
 const char *lb_tb2_shape_name(int shape) { return (shape >= 0 && shape < g_ntb) ? g_tb_shapes[shape].name : nullptr; }
 

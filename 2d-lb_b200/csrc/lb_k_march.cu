@@ -12,42 +12,17 @@
 using namespace lb;
 
 // BF: branch-free obstacle handling (three instantiations: no mask / mask / mask + run-time velocity zeroing)
-// Segments of a launch: p.seg_rows rows each; when the caller names a shorter height too (p.seg_rows2), the last rows of
-// the range -- two waves of short work items' worth -- are cut into segments of that height, so that the launch does
-// not end with half the SMs waiting for a few 64-row items (lattices too small for that stay uniform).
-template <int NW, int MINB>
-static int march_segments(StepParams &p, int nstrips)
-{
-    const int rows = p.y_end - p.y_begin, S1 = p.seg_rows;
-    int n1 = (rows + S1 - 1) / S1, n2 = 0, S2 = S1;
-    if (p.seg_rows2 > 0 && p.seg_rows2 < S1 && p.sm_count > 0) {
-        const long long short_rows = 2ll * p.sm_count * MINB * NW * p.seg_rows2 / nstrips;
-        if (short_rows >= p.seg_rows2 && short_rows < rows / 2) {
-            S2 = p.seg_rows2;
-            n1 = (int)((rows - short_rows) / S1);
-            n2 = (rows - n1 * S1 + S2 - 1) / S2;
-        }
-    }
-    p.seg_tall = n1;
-    p.seg_rows2 = S2;
-    return n1 + n2;
-}
-
 template <typename T, int V, int MATH, int NW, int MINB, bool PACKED, bool PF = false, bool SH = false, bool BF = false>
 static void launch_march(const StepParams &p_in, cudaStream_t st)
 {
     StepParams p = p_in;
     constexpr int OUT = 30 * V;
     const int nstrips = (p.nx + OUT - 1) / OUT;
-    const int nseg = march_segments<NW, MINB>(p, nstrips);
+    const int nseg = lb_march_segments(p, nstrips, NW, MINB);
     // strips next to a halo edge: 0 on a single slab, else strip 0 and / or the last one
     int ne = 0;
     if (p.edge_first) {
-        const bool w = p.west == EDGE_HALO, e = p.east == EDGE_HALO;
-        // a last strip narrower than the published columns shares them with the strip before it: both are edge strips
-        const int ne_e = !e ? 0 : (nstrips > 1 && p.nx - (nstrips - 1) * OUT < GHOST_COLS) ? 2 : 1;
-        ne = (w ? 1 : 0) + ne_e;
-        if (ne > nstrips) ne = nstrips;
+        ne = lb_march_edge_strips(p.nx, OUT, nstrips, p.west == EDGE_HALO, p.east == EDGE_HALO);
     }
     p.tiles_x = nstrips;
     p.tiles_y = nseg;
@@ -72,14 +47,10 @@ static void launch_march_k(const StepParams &p_in, cudaStream_t st)
     StepParams p = p_in;
     constexpr int OUT = (32 - 2 * OVL) * V;
     const int nstrips = (p.nx + OUT - 1) / OUT;
-    const int nseg = march_segments<NW, MINB>(p, nstrips);
+    const int nseg = lb_march_segments(p, nstrips, NW, MINB);
     int ne = 0;
     if (p.edge_first) {
-        const bool w = p.west == EDGE_HALO, e = p.east == EDGE_HALO;
-        // a last strip narrower than the published columns shares them with the strip before it: both are edge strips
-        const int ne_e = !e ? 0 : (nstrips > 1 && p.nx - (nstrips - 1) * OUT < GHOST_COLS) ? 2 : 1;
-        ne = (w ? 1 : 0) + ne_e;
-        if (ne > nstrips) ne = nstrips;
+        ne = lb_march_edge_strips(p.nx, OUT, nstrips, p.west == EDGE_HALO, p.east == EDGE_HALO);
     }
     p.tiles_x = nstrips;
     p.tiles_y = nseg;

@@ -29,7 +29,7 @@ SYMBOLS = [
     "lb_set_mask", "lb_upload_f", "lb_upload_moments", "lb_step", "lb_run_streamed", "lb_sync", "lb_download", "lb_download_strided",
     "lb_stage_move", "lb_stage_move_bcs", "lb_stage_update_hydro", "lb_stage_update_feq",
     "lb_stage_collide", "lb_stage_zero_velocity", "lb_init_synthetic", "lb_set_mask_disk",
-    "lb_total_mass", "lb_checksum", "lb_selftest_rcp", "lb_selftest_copy", "lb_set_temporal_blocking", "lb_temporal_blocking", "lb_segment_rows", "lb_tb2_shape_count", "lb_tb2_shape_name", "lb_launch_count", "lb_set_variant", "lb_variant_count", "lb_variant_name",
+    "lb_total_mass", "lb_checksum", "lb_selftest_rcp", "lb_selftest_copy", "lb_plan_march_launch", "lb_set_temporal_blocking", "lb_temporal_blocking", "lb_segment_rows", "lb_tb2_shape_count", "lb_tb2_shape_name", "lb_launch_count", "lb_set_variant", "lb_variant_count", "lb_variant_name",
     "lb_device_ptr", "lb_stream", "lb_halo_ipc_handle", "lb_halo_connect_ipc", "lb_halo_connect_local",
     "lb_halo_prime", "lb_set_halo_timeout",
     "lb_multi_create", "lb_multi_destroy", "lb_multi_last_error", "lb_multi_slab_count", "lb_multi_slab",
@@ -95,6 +95,7 @@ def _declare(lib):
         "lb_checksum": (i, [vp, ct.POINTER(ct.c_uint64)]),
         "lb_selftest_rcp": (i, [i, ct.c_uint32, ct.c_uint32, ct.POINTER(ct.c_uint64)]),
         "lb_selftest_copy": (i, [vp, i, ct.POINTER(ct.c_double)]),
+        "lb_plan_march_launch": (i, [i] * 11 + [ct.POINTER(i)] * 5),
         "lb_set_temporal_blocking": (i, [vp, i]),
         "lb_temporal_blocking": (i, [vp]),
         "lb_segment_rows": (i, [vp]),

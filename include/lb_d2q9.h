@@ -256,6 +256,14 @@ int lb_selftest_rcp(int device, uint32_t first_bits, uint32_t last_bits, uint64_
  * modified (the scratch buffer is the other half of the ping-pong pair, rewritten by the next step).
  * bench.py reports it beside the roofline; tools/stream_ceiling*.cu are the stand-alone versions. */
 int lb_selftest_copy(lb_sim *sim, int reps, double *ms_per_launch);
+/* Diagnostic, no device needed: the launch geometry the marching kernels' launchers compute for a slab nx columns wide and a
+ * row range of `rows` rows -- strips (120 stored columns per warp in fp32, 60 in fp64, 56 in fp64 with depth 3), strips that
+ * take part in the halo hand-shake (a last strip narrower than the three published columns makes the one before it an edge
+ * strip as well), and the segments: n_tall of seg_rows rows, then n_short of *short_rows (seg_rows2 on entry: 0 = uniform;
+ * the launcher falls back to uniform when two waves of short work items would be half the range or more).  The CPU tests
+ * check that every row is covered exactly once. */
+int lb_plan_march_launch(int nx, int rows, int elem_bytes, int depth, int nw, int minb, int seg_rows, int seg_rows2, int sm_count,
+                         int west_halo, int east_halo, int *n_strips, int *n_edge_strips, int *n_tall, int *n_short, int *short_rows);
 /* sum over all populations and cells of this slab, accumulated in double (mass check) */
 int lb_total_mass(lb_sim *sim, double *out);
 /* order-independent exact checksum of the populations: the 64-bit wrap-around sum of the raw bit

@@ -307,3 +307,54 @@ def test_two_update_halo_protocol_is_sufficient(parts):
             new.append(got.copy())
         slabs = new
         assert np.array_equal(np.concatenate(slabs, axis=2), whole.f)
+
+
+def test_marching_launch_geometry_covers_every_row_once():
+    """lb_plan_march_launch = the launchers' own arithmetic (csrc/lb_host.h), no device needed: tall segments followed by
+    short ones cover the row range exactly once whatever the sizes; small ranges stay uniform; a last strip narrower than
+    the three published columns makes two east edge strips."""
+    import ctypes as ct
+    from lb_b200 import native
+    L = native.lib()
+    rng = np.random.RandomState(12)
+
+    def plan(nx, rows, elem=4, depth=3, nw=4, minb=4, s1=64, s2=16, sms=148, w=0, e=0):
+        out = [ct.c_int() for _ in range(5)]
+        rc = L.lb_plan_march_launch(nx, rows, elem, depth, nw, minb, s1, s2, sms, w, e, *[ct.byref(o) for o in out])
+        assert rc == 0
+        return [o.value for o in out]
+
+    graded = 0
+    for _ in range(400):
+        nx, rows = int(rng.randint(1, 40000)), int(rng.randint(1, 70000))
+        s1 = int(rng.choice([8, 11, 16, 32, 64, 128])); s2 = int(rng.choice([0, s1 // 4, s1 // 2, s1]))
+        elem, depth = int(rng.choice([4, 8])), int(rng.choice([2, 3]))
+        nstrips, ne, n_tall, n_short, short = plan(nx, rows, elem, depth, 4, int(rng.choice([4, 5, 6])), s1, s2)
+        out = 120 if elem == 4 else (56 if depth == 3 else 60)
+        assert nstrips == -(-nx // out) and ne == 0
+        # the kernels' mapping from segment index to rows (lb_march.cuh)
+        covered = np.zeros(rows, dtype=np.int32)
+        for seg in range(n_tall + n_short):
+            tall = seg < n_tall
+            ys = seg * s1 if tall else n_tall * s1 + (seg - n_tall) * short
+            ye = min(ys + (s1 if tall else short), rows)
+            assert ys < rows, (nx, rows, s1, s2, seg)
+            covered[ys:ye] += 1
+        assert (covered == 1).all(), (nx, rows, s1, s2)
+        if n_short:
+            graded += 1
+            assert short == s2 < s1 and n_short * short < rows // 2 + s1 + short
+        else:
+            assert short == s1 and n_tall == -(-rows // s1)
+    assert graded > 20
+    # C4 on one GPU, its N=8 slabs, a lattice too small for short segments
+    assert plan(32768, 32768, s1=128, s2=32)[2:] == [251, 20, 32]
+    assert plan(4096, 32768, s1=64, s2=16)[2:] == [478, 136, 16]
+    assert plan(4096, 1024, depth=2, minb=6, s1=11, s2=0)[2:] == [94, 0, 11]
+    # edge strips: none on a single slab; west + east; a last strip of one or two columns adds the one before it
+    assert plan(4096, 100, w=1, e=1)[1] == 2 and plan(4096, 100, w=0, e=1)[1] == 1 and plan(4096, 100, w=1, e=0)[1] == 1
+    for nx, want in ((121, 2), (122, 2), (123, 1), (240, 1), (241, 2), (120, 1), (2, 1)):
+        assert plan(nx, 100, w=0, e=1)[1] == want, nx
+    assert plan(121, 100, w=1, e=1)[1] == 2 and plan(241, 100, w=1, e=1)[1] == 3
+    assert plan(57, 100, elem=8, depth=3, w=0, e=1)[1] == 2 and plan(59, 100, elem=8, depth=3, w=0, e=1)[1] == 1
+    assert plan(61, 100, elem=8, depth=2, w=0, e=1)[1] == 2
