@@ -15,6 +15,14 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def pytest_sessionstart(session):
+    """A fresh checkout has no built library (it is git-ignored): build it in-tree, as __graft_entry__.build() does.
+    Only when it is MISSING -- an existing one is what the tests are about, stale or not."""
+    from lb_b200 import build
+    if not os.path.exists(build.LIB) and (shutil.which("nvcc") or os.path.exists("/usr/local/cuda/bin/nvcc")):
+        build.build_library(force=True)
+
+
 def _gpu_expected():
     """True where a GPU is supposed to be present: GPU tests must then FAIL, not skip, if the
     CUDA library cannot see it."""
