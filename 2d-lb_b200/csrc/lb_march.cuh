@@ -25,11 +25,12 @@
 //
 // Slab edges (multi-GPU).  A strip next to a halo edge finds the neighbour slab's two
 // outermost columns in its overlap lane: before the x-shift the lane's loaded vectors are patched, as if memory
-// continued beyond the slab, with the nine values per row the neighbour published (StepParams: the three
-// entering populations of its boundary column, that column's populations 0,2,4, the three entering populations
-// one column further in); the obstacle bit of the neighbour's boundary column comes from the exchanged mask
-// column and the closure uses global coordinates.  The strip thus advances the neighbour's boundary column to
-// level t+1 exactly as the neighbour does: the decomposition stays bit-neutral with one exchange per TWO updates.
+// continued beyond the slab, with what the neighbour published (lb_fused.cuh, StepParams: all nine populations of
+// its GHOST_COLS outermost columns, of which a launch K updates deep reads K); the obstacle bits of those columns
+// come from the exchanged mask columns and the closure uses global coordinates.  The strip thus advances the
+// neighbour's outermost columns to the intermediate levels exactly as the neighbour does: the decomposition stays
+// bit-neutral with one exchange per launch.  Every strip that reads ghost columns or publishes some is an edge strip
+// (lb_march_edge_strips in lb_host.h: also the strip before a last one narrower than GHOST_COLS columns).
 // A single-slab periodic box wraps the overlap lanes' load addresses instead (nx a multiple of V).
 //
 // Bit-identical to the one-update path in both math modes: both phases call the same per-node code on the same
