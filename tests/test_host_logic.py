@@ -309,6 +309,52 @@ def test_two_update_halo_protocol_is_sufficient(parts):
         assert np.array_equal(np.concatenate(slabs, axis=2), whole.f)
 
 
+@pytest.mark.parametrize("depth", [1, 2, 3])
+@pytest.mark.parametrize("parts,dtype", [(2, np.float32), (3, np.float64)])
+def test_published_columns_are_sufficient_for_a_launch_k_updates_deep(parts, depth, dtype):
+    """The halo format as shipped (lb_fused.cuh, StepParams): per interior face a slab publishes all nine populations of
+    its three outermost columns and the mask of its two outermost ones.  Model of a launch `depth` updates deep: every slab
+    is advanced `depth` oracle steps on its own columns extended by `depth` ghost columns (NaN in the ghost columns a
+    launch of that depth does not read, mask of depth-1 of them); its own columns come out NaN-free and bit-identical to
+    the undivided lattice -- launches of mixed depth in one run, as lb_step plans them."""
+    from oracle import oracle as orc
+    from util import pipe_case
+    orc.build()
+    nx, ny = 90, 31
+    f0, mask = pipe_case(orc, nx, ny, dtype, mask="touching", seed=8)
+    mask[ny // 2 - 4: ny // 2 + 3, nx // parts - 3: nx // parts + 3] = 1             # a body across the first cut
+    kw = dict(mask=mask, dtype=dtype)
+    whole = orc.OpenCLSchemeOracle(f0, 1.3, 1.01, 1.0, **kw)
+    cuts = [round(k * nx / parts) for k in range(parts + 1)]
+    slabs = [f0[:, :, cuts[k]:cuts[k + 1]].copy() for k in range(parts)]
+    for d in (depth, 1, depth, depth):                                                # e.g. 3 + 1 + 3 + 3 updates
+        whole.run(d)
+        published = [(s[:, :, :3].copy(), s[:, :, -3:].copy()) for s in slabs]       # (west three, east three) of each slab
+        new = []
+        for k, own in enumerate(slabs):
+            x0, x1 = cuts[k], cuts[k + 1]
+            gw = d if k > 0 else 0
+            ge = d if k < parts - 1 else 0
+            ext = np.full((9, ny, gw + (x1 - x0) + ge), np.nan, dtype)
+            ext[:, :, gw:gw + (x1 - x0)] = own
+            if gw:
+                ext[:, :, :gw] = published[k - 1][1][:, :, 3 - gw:]                   # the west neighbour's east columns
+            if ge:
+                ext[:, :, gw + (x1 - x0):] = published[k + 1][0][:, :, :ge]
+            m = np.zeros((ny, ext.shape[2]), np.uint8)
+            mw, me = max(gw - 1, 0), max(ge - 1, 0)                                   # mask columns a launch of this depth reads
+            assert mw <= 2 and me <= 2
+            m[:, gw - mw: gw + (x1 - x0) + me] = mask[:, x0 - mw: x1 + me]
+            sub = orc.OpenCLSchemeOracle(ext, 1.3, 1.01, 1.0, mask=m, dtype=dtype)
+            with np.errstate(all="ignore"):
+                sub.run(d)
+            got = sub.f[:, :, gw:gw + (x1 - x0)]
+            assert np.isfinite(got).all(), (k, d)
+            new.append(got.copy())
+        slabs = new
+        assert np.array_equal(np.concatenate(slabs, axis=2), whole.f), d
+
+
 def test_marching_launch_geometry_covers_every_row_once():
     """lb_plan_march_launch = the launchers' own arithmetic (csrc/lb_host.h), no device needed: tall segments followed by
     short ones cover the row range exactly once whatever the sizes; small ranges stay uniform; a last strip narrower than
